@@ -1,0 +1,167 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference layers.
+
+Run in the build container only (the reference checkout does not travel to the GPU box):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+Each fixture stores the seeded inputs (triples, features, every parameter, the
+upstream gradient) and what the reference produced (output, autograd gradients of
+every parameter and of the features).  The fixtures are the committed evidence that
+`oracle/rgcn_oracle.py` and the CUDA path reproduce the reference; nothing here is
+imported by the product.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+sys.path.insert(0, REF)
+from torch_rgcn.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP  # noqa: E402
+from torch_rgcn.utils import add_inverse_and_self  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rand_triples(gen, n_nodes, n_rels, n_edges, dup=0.25):
+    s = torch.randint(0, n_nodes, (n_edges,), generator=gen)
+    p = torch.randint(0, n_rels, (n_edges,), generator=gen)
+    o = torch.randint(0, n_nodes, (n_edges,), generator=gen)
+    t = torch.stack([s, p, o], dim=1)
+    k = int(n_edges * dup)                       # repeat some rows / share (s,p) so segments have >1 edge
+    if k:
+        t[-k:, 0] = t[:k, 0]
+        t[-k:, 1] = t[:k, 1]
+        h = max(k // 2, 1)
+        t[-h:, 2] = t[:h, 2]                      # and some exact duplicates
+    return t.long()
+
+
+def grads_of(layer, feats):
+    g = {n: p.grad.detach().numpy().copy() for n, p in layer.named_parameters() if p.grad is not None}
+    if feats is not None and feats.grad is not None:
+        g['features'] = feats.grad.detach().numpy().copy()
+    return g
+
+
+def save(name, meta, arrays):
+    arrays = {k: np.asarray(v) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), meta=np.array(json.dumps(meta)), **arrays)
+    print('wrote', name, {k: v.shape for k, v in arrays.items() if k in ('out', 'triples')})
+
+
+def make_nc(name, seed, N, R, E, in_f, out_f, decomposition=None, vertical=False, diag=False, bias=True,
+            shuffle=False):
+    gen = torch.Generator().manual_seed(seed)
+    triples = rand_triples(gen, N, R, E)
+    tp = add_inverse_and_self(triples, N, R)
+    if shuffle:                                   # non-canonical row order: horizontal normalisation depends on it
+        tp = tp[torch.randperm(tp.size(0), generator=gen)]
+    torch.manual_seed(seed + 2)
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=in_f,
+                                         out_features=out_f, bias=bias, decomposition=decomposition,
+                                         vertical_stacking=vertical, diag_weight_matrix=diag)
+    if layer.bias is not None:                    # zero bias would not exercise the add
+        with torch.no_grad():
+            layer.bias.normal_(0, 1, generator=gen)
+    feats = None
+    if in_f is not None:
+        feats = torch.randn(N, in_f, generator=gen).requires_grad_(True)
+    out = layer(feats) if feats is not None else layer()
+    G = torch.randn(out.shape, generator=gen)
+    out.backward(G)
+    arrays = {'triples_plus': tp.numpy(), 'out': out.detach().numpy(), 'G': G.numpy()}
+    if feats is not None:
+        arrays['features'] = feats.detach().numpy()
+    for n, p in layer.named_parameters():
+        arrays['param_' + n] = p.detach().numpy()
+    for n, g in grads_of(layer, feats).items():
+        arrays['grad_' + n] = g
+    meta = dict(kind='nc', N=N, R=R, num_relations=2 * R + 1, in_features=in_f, out_features=layer.out_features,
+                decomposition=decomposition, vertical=vertical, diag=diag, bias=bias)
+    save(name, meta, arrays)
+
+
+def make_lp(name, seed, N, R, E, in_f, out_f, decomposition=None, vertical=False, b_init=None, train=None):
+    gen = torch.Generator().manual_seed(seed)
+    triples = rand_triples(gen, N, R, E)
+    torch.manual_seed(seed + 2)
+    edo = None
+    if train == 'bernoulli':
+        edo = {'general': 0.5, 'self_loop': 0.4, 'self_loop_type': 'plain'}
+    elif train == 'schlichtkrull':
+        edo = {'general': 0.5, 'self_loop': 0.2, 'self_loop_type': 'schlichtkrull-dropout'}
+    layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=2 * R + 1, in_features=in_f, out_features=out_f,
+                                         edge_dropout=edo, decomposition=decomposition, vertical_stacking=vertical,
+                                         w_init='glorot-normal', b_init=b_init)
+    if layer.bias is not None:
+        with torch.no_grad():
+            layer.bias.normal_(0, 1, generator=gen)
+    feats = torch.randn(N, in_f, generator=gen).requires_grad_(True)
+    arrays = {}
+    layer.train(train is not None)
+    rng_seed = seed + 7
+    if train == 'bernoulli':
+        # first RNG draw inside forward is the self-loop keep mask (reference utils.py:120-121)
+        torch.manual_seed(rng_seed)
+        arrays['keep'] = torch.bernoulli(torch.empty(N).fill_(1 - edo['self_loop'])).bool().numpy()
+    elif train == 'schlichtkrull':
+        # forward draws bernoulli(N) with p=1 first, then F.dropout on a (1,N,O) tensor (reference layers.py:545-546)
+        torch.manual_seed(rng_seed)
+        torch.bernoulli(torch.empty(N).fill_(1.0))
+        arrays['self_mask'] = torch.nn.functional.dropout(torch.ones(1, N, out_f), p=edo['self_loop'],
+                                                          training=True)[0].numpy()
+    torch.manual_seed(rng_seed)
+    out = layer(triples, feats)
+    G = torch.randn(out.shape, generator=gen)
+    out.backward(G)
+    arrays.update({'triples': triples.numpy(), 'out': out.detach().numpy(), 'G': G.numpy(),
+                   'features': feats.detach().numpy()})
+    for n, p in layer.named_parameters():
+        arrays['param_' + n] = p.detach().numpy()
+    for n, g in grads_of(layer, feats).items():
+        arrays['grad_' + n] = g
+    meta = dict(kind='lp', N=N, R=R, num_relations=2 * R + 1, in_features=in_f, out_features=out_f,
+                decomposition=decomposition, vertical=vertical, b_init=b_init, train=train, edge_dropout=edo)
+    save(name, meta, arrays)
+
+
+def main():
+    N, R, E = 24, 3, 70
+    basis = {'type': 'basis', 'num_bases': 3}
+    block = {'type': 'block', 'num_blocks': 2}
+    # --- node-classification layer (reference layers.py:101-308)
+    make_nc('nc_none_h_feat', 0, N, R, E, 12, 8)
+    make_nc('nc_none_v_feat', 1, N, R, E, 12, 8, vertical=True)
+    make_nc('nc_none_h_featureless', 2, N, R, E, None, 8)
+    make_nc('nc_basis_h_feat', 3, N, R, E, 12, 8, decomposition=basis)
+    make_nc('nc_basis_v_feat', 4, N, R, E, 12, 8, decomposition=basis, vertical=True)
+    make_nc('nc_basis_h_featureless', 5, N, R, E, None, 8, decomposition=basis)
+    make_nc('nc_block_h_feat', 6, N, R, E, 12, 8, decomposition=block)
+    make_nc('nc_block_v_feat', 7, N, R, E, 12, 8, decomposition=block, vertical=True)
+    make_nc('nc_block_h_featureless', 8, N, R, E, None, 8, decomposition=block)
+    make_nc('nc_diag_h', 9, N, R, E, 12, 12, diag=True)
+    make_nc('nc_none_h_feat_odd', 10, 23, R, E, 10, 3)                      # dims not multiples of 4
+    make_nc('nc_basis_h_featureless_odd', 11, 23, R, E, None, 10, decomposition=basis)
+    make_nc('nc_block_v_feat_odd', 12, 23, R, E, 10, 6, decomposition=block, vertical=True)   # 5x3 blocks
+    make_nc('nc_none_h_feat_nobias', 13, N, R, E, 12, 8, bias=False)
+    make_nc('nc_none_h_feat_shuffled', 14, N, R, E, 12, 8, shuffle=True)
+    make_nc('nc_none_v_feat_shuffled', 15, N, R, E, 12, 8, vertical=True, shuffle=True)
+    make_nc('nc_none_h_feat_wide', 16, 40, 5, 200, 64, 32)
+    make_nc('nc_block_h_feat_wide', 17, 40, 5, 200, 64, 64, decomposition={'type': 'block', 'num_blocks': 4})
+    # --- link-prediction layer (reference layers.py:311-565)
+    make_lp('lp_none_h', 20, N, R, E, 12, 8, b_init='zeros')
+    make_lp('lp_none_v', 21, N, R, E, 12, 8)
+    make_lp('lp_basis_h', 22, N, R, E, 12, 8, decomposition=basis, b_init='normal')
+    make_lp('lp_basis_v', 23, N, R, E, 12, 8, decomposition=basis)
+    make_lp('lp_block_h', 24, N, R, E, 12, 8, decomposition=block, b_init='zeros')
+    make_lp('lp_none_h_train_bernoulli', 25, N, R, E, 12, 8, b_init='zeros', train='bernoulli')
+    make_lp('lp_block_h_train_schlichtkrull', 26, N, R, E, 12, 8, decomposition=block, b_init='zeros',
+            train='schlichtkrull')
+    make_lp('lp_none_h_wn18like', 27, 60, 9, 300, 16, 16, b_init='zeros')
+
+
+if __name__ == '__main__':
+    main()
