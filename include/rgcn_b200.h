@@ -1,0 +1,188 @@
+/*
+ * rgcn_b200.h — C ABI of the B200-native RGCN relational message-passing engine.
+ *
+ * Drop-in boundary for the per-relation aggregation path of thiviyanT/torch-rgcn
+ * (torch_rgcn/layers.py RelationalGraphConvolutionNC.forward :222-308,
+ *  RelationalGraphConvolutionLP.forward :450-565, and the helpers in
+ *  torch_rgcn/utils.py).  The reference has no FFI of its own: the path sits
+ * behind a Python nn.Module.  The thin shim in torch_rgcn_b200/_lib.py binds
+ * these entry points with ctypes and passes raw device pointers; no torch type
+ * crosses this boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - pointers are borrowed for the duration of the call; nothing is allocated
+ *     or freed behind the caller's back: scratch memory is caller-provided and
+ *     sized by the matching *_workspace_bytes() query;
+ *   - all work is enqueued on `stream` (a cudaStream_t cast to void*); calls are
+ *     asynchronous and re-entrant per stream;
+ *   - return value: 0 = ok, negative = error (see enum), message in
+ *     rgcn_last_error() (thread-local);
+ *   - indices: node ids and edge counts fit int32 inside the engine
+ *     (N, nnz < 2^31); triples arrive as int64 (torch.long) like the reference.
+ */
+#ifndef RGCN_B200_H
+#define RGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGCN_ABI_VERSION 1
+
+typedef void* rgcn_stream_t;
+
+enum rgcn_status {
+    RGCN_OK = 0,
+    RGCN_ERR_ARG = -1,          /* bad argument / shape */
+    RGCN_ERR_UNSUPPORTED = -2,  /* combination the engine (like the reference) does not support */
+    RGCN_ERR_CUDA = -3,         /* CUDA runtime error */
+    RGCN_ERR_WORKSPACE = -4     /* workspace too small */
+};
+
+/* how per-edge weights are derived (reference layers.py:263-273 / :498-510) */
+enum rgcn_norm {
+    RGCN_NORM_ROW = 0,          /* vertical stacking: 1 / #{edges with the same (p, s)} */
+    RGCN_NORM_COL_SWAPPED = 1,  /* horizontal stacking: 1 / permuted column counts, the literal
+                                   cat([sums[n:2n], sums[:n], sums[-i:]]) rule */
+    RGCN_NORM_EXPLICIT = 2      /* caller supplies val_in (e.g. a relation shard of a larger graph) */
+};
+
+enum rgcn_weight_form {
+    RGCN_W_DENSE = 0,           /* weights (R', I, O)                         layers.py:155 */
+    RGCN_W_BASIS = 1,           /* bases (B, I, O), comps (R', B)             layers.py:160-161, :242 */
+    RGCN_W_BLOCK = 2,           /* blocks (Rb, nb, I/nb, O/nb) [+ blocks_self] layers.py:169-170, :375-378 */
+    RGCN_W_DIAG = 3             /* weights (R', I), O == I                    layers.py:147-151 */
+};
+
+enum rgcn_dtype { RGCN_F32 = 0, RGCN_BF16 = 1 };
+
+const char* rgcn_last_error(void);   /* host string, valid until the next failing call on this thread */
+int rgcn_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Helper kernels — device versions of torch_rgcn/utils.py.
+ * ---------------------------------------------------------------------------------------- */
+
+/* utils.py:127-141  add_inverse_and_self: out is (2E+N, 3) = [triples; (o, p+R, s); (v, 2R, v)] */
+int rgcn_add_inverse_and_self(const int64_t* triples, int64_t num_triples, int64_t num_nodes, int64_t num_rels,
+                              int64_t* out, rgcn_stream_t stream);
+
+/* utils.py:100-107  generate_inverses: out is (E, 3) = (o, p+R, s) */
+int rgcn_generate_inverses(const int64_t* triples, int64_t num_triples, int64_t num_rels, int64_t* out,
+                           rgcn_stream_t stream);
+
+/* layers.py:481-487 + utils.py:110-124: the edge list the LP layer walks,
+ * out is (3E + n_self, 3) = [T; inverse(T); T; (v, 2R, v) for v in self_nodes].
+ * self_nodes lists the nodes whose self-loop survived edge dropout (all nodes in eval mode). */
+int rgcn_lp_triples_plus(const int64_t* triples, int64_t num_triples, int64_t num_rels,
+                         const int64_t* self_nodes, int64_t num_self, int64_t* out, rgcn_stream_t stream);
+
+/* utils.py:143-166  stack_matrices: indices_out is (nnz, 2); vertical: (p*N+s, o), horizontal: (s, p*N+o).
+ * bounds_out (2 x int64, device) receives max(indices[:,0]) and max(indices[:,1]) for the reference's asserts
+ * (utils.py:163-164); may be NULL. */
+int rgcn_stack_matrices(const int64_t* triples, int64_t nnz, int64_t num_nodes, int64_t num_rels, int vertical,
+                        int64_t* indices_out, int64_t* bounds_out, rgcn_stream_t stream);
+
+/* utils.py:71-97  sum_sparse: sums_out[k] = sum of values over the row (row_normalisation != 0) or column
+ * of entry k.  table_ws: scratch of `rows` (or `cols`) floats. */
+int rgcn_sum_sparse(const int64_t* indices, const float* values, int64_t nnz, int64_t rows, int64_t cols,
+                    int row_normalisation, float* table_ws, float* sums_out, rgcn_stream_t stream);
+
+/* utils.py:168-196  block_diag: blocks (R, nb, bi, bo) -> out (R, nb*bi, nb*bo), zero off the diagonal */
+int rgcn_block_diag(const float* blocks, int64_t num_rels, int64_t num_blocks, int64_t block_in, int64_t block_out,
+                    float* out, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph plan: the sorted edge lists the propagation kernels walk.
+ * Replaces stack_matrices + sum_sparse + the COO constructor on every forward
+ * (layers.py:255-279 / :490-516).  All arrays are caller-allocated device memory.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rgcn_graph {
+    int64_t num_nodes;
+    int64_t num_rels;       /* R' = number of relation ids the layer sees */
+    int64_t nnz;            /* rows of triples_plus */
+    /* destination-major CSR (rows = subject s), sorted by (s, p, o) — forward walk */
+    int32_t* d_rowptr;      /* N+1 */
+    int32_t* d_src;         /* nnz: object o */
+    int32_t* d_rel;         /* nnz */
+    float* d_val;           /* nnz */
+    /* source-major CSR (rows = object o), sorted by (o, p, s) — backward-to-features walk */
+    int32_t* s_rowptr;      /* N+1 */
+    int32_t* s_dst;         /* nnz: subject s */
+    int32_t* s_rel;         /* nnz */
+    float* s_val;           /* nnz */
+    /* relation-major list, sorted by (p, s, o) — weight-gradient walk */
+    int32_t* r_relptr;      /* R'+1 */
+    int32_t* r_dst;         /* nnz */
+    int32_t* r_src;         /* nnz */
+    float* r_val;           /* nnz */
+    float* val;             /* nnz, in the caller's edge order: the reference's `vals` (layers.py:273) */
+    int32_t* status;        /* 4 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164) */
+} rgcn_graph;
+
+size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels);
+
+/* n_general / n_self are the (n, i) of the horizontal permutation: NC ((nnz-N)/2, N), LP (|T|, |T|+|self|).
+ * val_in (nnz floats, caller order) is read only for RGCN_NORM_EXPLICIT. */
+int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t num_nodes, int64_t num_rels,
+                     int norm, int64_t n_general, int64_t n_self, const float* val_in,
+                     rgcn_graph* graph, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Propagation: out[s] = bias + sum_e val_e * T_{p_e}(X[o_e]) and its gradients.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rgcn_params {
+    int32_t form;           /* enum rgcn_weight_form */
+    int32_t featureless;    /* X = identity: in_dim == num_nodes, messages are weight rows (layers.py:286-288) */
+    int64_t in_dim;
+    int64_t out_dim;
+    int64_t num_bases;
+    int64_t num_blocks;
+    int64_t num_block_rels; /* relations stored in `blocks`: R' (NC) or R'-1 (LP, self relation dense) */
+    const float* weights;   /* DENSE (R', I, O) | DIAG (R', I) */
+    const float* bases;     /* (B, I, O) */
+    const float* comps;     /* (R', B) */
+    const float* blocks;    /* (num_block_rels, nb, I/nb, O/nb) */
+    const float* blocks_self; /* (I, O) dense weight of relation R'-1, or NULL   layers.py:378, :544 */
+    const float* bias;      /* (O) or NULL */
+    const float* self_mask; /* (N, O) or NULL: dropout mask on the transformed features of relation R'-1
+                               ('schlichtkrull-dropout', layers.py:545-546) */
+} rgcn_params;
+
+typedef struct rgcn_grads { /* NULL = gradient not wanted; buffers are overwritten, not accumulated */
+    float* features;        /* (N, I) */
+    float* weights;
+    float* bases;
+    float* comps;
+    float* blocks;
+    float* blocks_self;
+    float* bias;
+} rgcn_grads;
+
+size_t rgcn_forward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params);
+int rgcn_forward(const rgcn_graph* graph, const rgcn_params* params, const void* features, int feature_dtype,
+                 float* out, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+size_t rgcn_backward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params);
+int rgcn_backward(const rgcn_graph* graph, const rgcn_params* params, const void* features, int feature_dtype,
+                  const float* grad_out, const rgcn_grads* grads, void* workspace, size_t workspace_bytes,
+                  rgcn_stream_t stream);
+
+/* number of kernels the engine has launched on this process since load (bench.py's gpu_launches) */
+int64_t rgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Relation sharding (new capability; the reference is single-device).
+ * Greedy longest-processing-time bin packing of relations onto `world` ranks by edge count.
+ * rel_nnz and rel_to_rank are HOST arrays of length num_rels.
+ * ---------------------------------------------------------------------------------------- */
+int rgcn_shard_plan(const int64_t* rel_nnz, int64_t num_rels, int32_t world, int32_t* rel_to_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGCN_B200_H */

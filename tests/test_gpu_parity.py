@@ -1,0 +1,357 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures and the oracle.
+
+Tolerance: north_star asks for 1e-4 absolute in fp32; bf16-feature runs use 2e-2 (bf16 storage, fp32
+accumulation) and say so.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_names
+from oracle import rgcn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-4
+
+
+def _t(a, dev, dtype=None):
+    t = torch.as_tensor(np.asarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def _load_params(layer, params, dev):
+    layer.to(dev)
+    with torch.no_grad():
+        for n, p in layer.named_parameters():
+            p.copy_(_t(params[n], dev))
+
+
+def _compare(out, grads_ref, layer, feats, out_ref, atol=ATOL, rtol=1e-4):
+    np.testing.assert_allclose(out.detach().cpu().numpy(), out_ref, atol=atol, rtol=rtol)
+    for name, g in grads_ref.items():
+        if name == 'features':
+            got = feats.grad
+        else:
+            got = dict(layer.named_parameters())[name].grad
+        assert got is not None, name
+        np.testing.assert_allclose(got.float().cpu().numpy(), g, atol=atol, rtol=rtol, err_msg=name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# helper kernels against the reference's own unit-test vectors
+# ---------------------------------------------------------------------------------------------------
+def test_helpers_reference_vectors(cuda_device):
+    from torch_rgcn_b200 import utils as U
+    from test_oracle_golden import (STACK_TRIPLES, STACK_VER, STACK_HOR, SUM_VER_IND, SUM_HOR_IND, ARR_ROW_IND,
+                                    ARR_ROW_VAL, ARR_COL_IND, ARR_COL_VAL, ARR_EXPECT)
+    # reference tests/test_utils.py:5-25
+    t = torch.tensor([[0, 0, -1], [1, 1, -2], [2, 2, -3]])
+    exp = torch.tensor([[0, 0, -1], [1, 1, -2], [2, 2, -3], [-1, 3, 0], [-2, 4, 1], [-3, 5, 2],
+                        [0, 6, 0], [1, 6, 1], [2, 6, 2]])
+    assert torch.equal(U.add_inverse_and_self(t, 3, 3), exp)
+    assert torch.equal(U.generate_inverses(t, 3), exp[3:6])
+    # reference tests/test_utils.py:28-84
+    st = torch.tensor(STACK_TRIPLES)
+    ind, size = U.stack_matrices(st, 9, 7, vertical_stacking=True)
+    assert torch.equal(ind, torch.tensor(STACK_VER)) and size == (63, 9)
+    ind, size = U.stack_matrices(st, 9, 7, vertical_stacking=False)
+    assert torch.equal(ind, torch.tensor(STACK_HOR)) and size == (9, 63)
+    with pytest.raises(AssertionError):
+        U.stack_matrices(torch.tensor([[0, 7, 1]]), 9, 7, vertical_stacking=True)
+    # reference tests/test_utils.py:87-123 (exact equality, as upstream)
+    v = torch.ones(6)
+    out = v / U.sum_sparse(torch.tensor(SUM_VER_IND), v, (9, 3), row_normalisation=True)
+    assert torch.equal(out, torch.tensor([1 / 3, 1 / 3, 1 / 3, 1, 1, 1]))
+    v = torch.ones(7)
+    out = v / U.sum_sparse(torch.tensor(SUM_HOR_IND), v, (4, 9), row_normalisation=False)
+    assert torch.equal(out, torch.tensor([1 / 4, 1 / 4, 1 / 4, 1 / 4, 1, 1, 1]))
+    # reference tests/test_utils.py:170-220 (float values)
+    s = U.sum_sparse(torch.tensor(ARR_ROW_IND), torch.tensor(ARR_ROW_VAL), (15, 3), True)
+    assert torch.equal(s, torch.tensor(ARR_EXPECT, dtype=torch.float32))
+    s = U.sum_sparse(torch.tensor(ARR_COL_IND), torch.tensor(ARR_COL_VAL), (3, 15), False)
+    r = (len(ARR_COL_VAL) - 3) // 2
+    s = torch.cat([s[r:2 * r], s[:r], s[2 * r:]])
+    assert torch.equal(s, torch.tensor(ARR_EXPECT, dtype=torch.float32))
+    # block_diag against the oracle
+    b = torch.randn(3, 4, 5, 2)
+    np.testing.assert_array_equal(U.block_diag(b).numpy(), orc.block_diag(b.numpy()).astype(np.float32))
+
+
+def test_generate_self_loops_and_lp_edge_list(cuda_device):
+    from torch_rgcn_b200 import utils as U, _lib
+    t = torch.tensor([[0, 0, 1], [2, 1, 3], [3, 0, 0]], device=cuda_device)
+    out = U.generate_self_loops(t, 5, 2, 1.0, device=cuda_device)
+    exp, _, _ = orc.lp_triples_plus(t.cpu().numpy(), 5, 2)
+    assert np.array_equal(out.cpu().numpy(), exp[6:])
+    nodes = torch.tensor([0, 2, 4], device=cuda_device)
+    tp = torch.empty(3 * 3 + 3, 3, dtype=torch.long, device=cuda_device)
+    _lib.check(_lib.lib.rgcn_lp_triples_plus(_lib.ptr(t), 3, 2, _lib.ptr(nodes), 3, _lib.ptr(tp), _lib.stream_ptr()))
+    keep = np.array([1, 0, 1, 0, 1], bool)
+    exp, n, i = orc.lp_triples_plus(t.cpu().numpy(), 5, 2, keep)
+    assert np.array_equal(tp.cpu().numpy(), exp) and (n, i) == (3, 6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-edge weights are bit-exact
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('vertical', [True, False])
+@pytest.mark.parametrize('shuffle', [False, True])
+def test_edge_values_bit_exact(cuda_device, vertical, shuffle):
+    from torch_rgcn_b200 import GraphPlan, _lib
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R = 501, 7
+    t = random_triples(N, R, 6000, seed=3, rel_dist='zipf', node_skew=True)
+    tp = orc.add_inverse_and_self(t.numpy(), N, R)
+    if shuffle:
+        tp = tp[np.random.RandomState(0).permutation(len(tp))]
+    n = int((len(tp) - N) / 2)
+    ref = orc.edge_values(tp, N, 2 * R + 1, vertical, n, N)
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, 2 * R + 1,
+                     _lib.NORM_ROW if vertical else _lib.NORM_COL_SWAPPED, n, N)
+    assert np.array_equal(plan.val.cpu().numpy(), ref)
+    # CSR invariants: rows sorted, every list is a permutation of the edge set
+    rp = plan.d_rowptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == len(tp) and np.all(np.diff(rp) >= 0)
+    s_sorted = np.repeat(np.arange(N), np.diff(rp))
+    got = np.stack([s_sorted, plan.d_rel.cpu().numpy(), plan.d_src.cpu().numpy()], 1)
+    assert np.array_equal(got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))], tp[np.lexsort((tp[:, 2], tp[:, 1], tp[:, 0]))])
+    assert np.array_equal(got, got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))])
+    rrp = plan.r_relptr.cpu().numpy()
+    assert np.array_equal(np.diff(rrp), np.bincount(tp[:, 1], minlength=2 * R + 1))
+    srp = plan.s_rowptr.cpu().numpy()
+    assert np.array_equal(np.diff(srp), np.bincount(tp[:, 2], minlength=N))
+
+
+def test_out_of_range_triples_raise(cuda_device):
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    tp = torch.tensor([[0, 0, 1], [1, 1, 0], [0, 2, 0], [1, 2, 9]])       # object id 9 >= N
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=2, num_relations=3, in_features=4, out_features=4)
+    layer.to(cuda_device)
+    with pytest.raises(AssertionError):
+        layer(torch.randn(2, 4, device=cuda_device))
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures produced by the real reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', golden_names('nc_'))
+def test_nc_layer_matches_reference(cuda_device, name):
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    meta, d, params, grads = load_golden(name)
+    layer = RelationalGraphConvolutionNC(triples=torch.as_tensor(d['triples_plus']), num_nodes=meta['N'],
+                                         num_relations=meta['num_relations'], in_features=meta['in_features'],
+                                         out_features=meta['out_features'], bias=meta['bias'],
+                                         decomposition=meta['decomposition'], vertical_stacking=meta['vertical'],
+                                         diag_weight_matrix=meta['diag'])
+    assert {n: tuple(p.shape) for n, p in layer.named_parameters()} == {n: v.shape for n, v in params.items()}
+    _load_params(layer, params, cuda_device)
+    feats = None
+    if 'features' in d:
+        feats = _t(d['features'], cuda_device).requires_grad_(True)
+    out = layer(feats) if feats is not None else layer()
+    out.backward(_t(d['G'], cuda_device))
+    _compare(out, grads, layer, feats, d['out'])
+
+
+@pytest.mark.parametrize('name', golden_names('lp_'))
+def test_lp_layer_matches_reference(cuda_device, name):
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionLP
+    meta, d, params, grads = load_golden(name)
+    layer = RelationalGraphConvolutionLP(num_nodes=meta['N'], num_relations=meta['num_relations'],
+                                         in_features=meta['in_features'], out_features=meta['out_features'],
+                                         edge_dropout=meta['edge_dropout'], decomposition=meta['decomposition'],
+                                         vertical_stacking=meta['vertical'], w_init='glorot-normal',
+                                         b_init=meta['b_init'])
+    assert {n: tuple(p.shape) for n, p in layer.named_parameters()} == {n: v.shape for n, v in params.items()}
+    _load_params(layer, params, cuda_device)
+    layer.train(meta['train'] is not None)
+    if 'keep' in d:
+        layer._test_keep = _t(d['keep'], cuda_device)
+    if 'self_mask' in d:
+        layer._test_self_mask = _t(d['self_mask'], cuda_device)
+    feats = _t(d['features'], cuda_device).requires_grad_(True)
+    out = layer(_t(d['triples'], cuda_device), feats)
+    out.backward(_t(d['G'], cuda_device))
+    _compare(out, grads, layer, feats, d['out'])
+
+
+def test_reference_test_nn_shapes(cuda_device):
+    """The reference's tests/test_nn.py:22-121 scenario (shape asserts) on the drop-in layer."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    triples = torch.tensor([[0, 0, 1], [1, 1, 2], [2, 2, 3], [1, 3, 0], [2, 4, 1], [3, 5, 2],
+                            [0, 6, 0], [1, 6, 1], [2, 6, 2], [3, 6, 3]])
+    for decomp, attr, shape1, shape2 in [
+            (None, 'weights', (7, 4, 16), (7, 16, 16)),
+            ({'type': 'basis', 'num_bases': 2}, 'bases', (2, 4, 16), (2, 16, 16)),
+            ({'type': 'block', 'num_blocks': 2}, 'blocks', (7, 2, 2, 8), (7, 2, 8, 8))]:
+        l1 = RelationalGraphConvolutionNC(triples=triples, num_nodes=4, num_relations=7, in_features=None,
+                                          out_features=16, decomposition=decomp).to(cuda_device)
+        l2 = RelationalGraphConvolutionNC(triples=triples, num_nodes=4, num_relations=7, in_features=16,
+                                          out_features=16, decomposition=decomp).to(cuda_device)
+        z = l1.forward()
+        z2 = l2.forward(z)
+        assert getattr(l1, attr).size() == torch.Size(shape1) and getattr(l2, attr).size() == torch.Size(shape2)
+        assert z.size() == z2.size() == torch.Size([4, 16])
+
+
+# ---------------------------------------------------------------------------------------------------
+# larger seeded graphs against the oracle
+# ---------------------------------------------------------------------------------------------------
+CASES = [
+    # name, N, R, E, in, out, decomposition, vertical, featureless, diag
+    ('dense16', 3000, 11, 40000, 16, 16, None, False, False, False),
+    ('dense16_v', 3000, 11, 40000, 16, 16, None, True, False, False),
+    ('dense_odd', 2000, 5, 20000, 10, 3, None, True, False, False),
+    ('block16', 3000, 11, 40000, 16, 16, {'type': 'block', 'num_blocks': 2}, False, False, False),
+    ('block64', 2500, 9, 30000, 64, 64, {'type': 'block', 'num_blocks': 4}, True, False, False),
+    ('block_5x5', 1500, 4, 15000, 50, 50, {'type': 'block', 'num_blocks': 10}, False, False, False),
+    ('basis200', 1200, 6, 12000, 200, 200, {'type': 'basis', 'num_bases': 2}, False, False, False),
+    ('basis16x2', 3000, 11, 40000, 16, 2, {'type': 'basis', 'num_bases': 30}, True, False, False),
+    ('featureless16', 3000, 11, 40000, None, 16, None, False, True, False),
+    ('featureless_basis', 2400, 7, 30000, None, 16, {'type': 'basis', 'num_bases': 30}, False, True, False),
+    ('featureless_basis10', 2400, 7, 30000, None, 10, {'type': 'basis', 'num_bases': 40}, False, True, False),
+    ('featureless_block', 2400, 7, 30000, None, 16, {'type': 'block', 'num_blocks': 4}, False, True, False),
+    ('diag32', 3000, 11, 40000, 32, 32, None, False, False, True),
+    ('dense128', 1500, 5, 20000, 128, 96, None, False, False, False),
+]
+
+
+def _params_np(layer):
+    return {n: p.detach().cpu().numpy() for n, p in layer.named_parameters()}
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_nc_vs_oracle_seeded(cuda_device, case):
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    from torch_rgcn_b200.synthetic import random_triples
+    name, N, R, E, in_f, out_f, decomp, vertical, featureless, diag = case
+    t = random_triples(N, R, E, seed=1, rel_dist='zipf', node_skew=True)
+    tp = torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, R))
+    torch.manual_seed(5)
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=in_f,
+                                         out_features=out_f, decomposition=decomp, vertical_stacking=vertical,
+                                         diag_weight_matrix=diag).to(cuda_device)
+    if layer.bias is not None:
+        with torch.no_grad():
+            layer.bias.normal_()
+    feats = None if featureless else torch.randn(N, in_f, device=cuda_device, requires_grad=True)
+    out = layer(feats) if feats is not None else layer()
+    G = torch.randn_like(out)
+    out.backward(G)
+    ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer),
+                                  None if featureless else feats.detach().cpu().numpy(), vertical, G.cpu().numpy())
+    ref_g = {k: v for k, v in ref_g.items() if v is not None}
+    # sums over up to ~1e4 edges per relation: relative tolerance on the weight gradients
+    _compare(out, ref_g, layer, feats, ref_out, atol=ATOL, rtol=2e-4)
+
+
+@pytest.mark.parametrize('decomp,vertical', [(None, False), (None, True), ({'type': 'basis', 'num_bases': 2}, False),
+                                             ({'type': 'block', 'num_blocks': 4}, False)])
+def test_lp_vs_oracle_seeded(cuda_device, decomp, vertical):
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionLP
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = 4000, 18, 14000        # WN18-like relation count
+    t = random_triples(N, R, E, seed=2).to(cuda_device)
+    torch.manual_seed(6)
+    layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=2 * R + 1, in_features=16, out_features=16,
+                                         decomposition=decomp, vertical_stacking=vertical, b_init='zeros').to(cuda_device)
+    feats = torch.randn(N, 16, device=cuda_device, requires_grad=True)
+    layer.eval()
+    out = layer(t, feats)
+    G = torch.randn_like(out)
+    out.backward(G)
+    ref_out, ref_g = orc.lp_layer(t.cpu().numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().cpu().numpy(),
+                                  vertical, G.cpu().numpy())
+    _compare(out, ref_g, layer, feats, ref_out, atol=ATOL, rtol=2e-4)
+
+
+def test_lp_empty_graph_and_isolated_nodes(cuda_device):
+    """E = 0: only self-loops remain; with self-loop dropout some nodes receive nothing at all."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionLP
+    N, R = 50, 3
+    layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=2 * R + 1, in_features=8, out_features=8,
+                                         edge_dropout={'general': 0.5, 'self_loop': 0.5, 'self_loop_type': 'x'},
+                                         b_init='ones').to(cuda_device)
+    feats = torch.randn(N, 8, device=cuda_device, requires_grad=True)
+    empty = torch.empty(0, 3, dtype=torch.long, device=cuda_device)
+    layer.eval()
+    out = layer(empty, feats)
+    ref = orc.lp_layer(np.zeros((0, 3), np.int64), N, 2 * R + 1, _params_np(layer), feats.detach().cpu().numpy())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, atol=ATOL)
+    layer.train()
+    keep = torch.zeros(N, dtype=torch.bool)
+    keep[::3] = True
+    layer._test_keep = keep
+    out = layer(empty, feats)
+    out.sum().backward()
+    ref = orc.lp_layer(np.zeros((0, 3), np.int64), N, 2 * R + 1, _params_np(layer), feats.detach().cpu().numpy(),
+                       keep=keep.numpy())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, atol=ATOL)
+    assert torch.all(out[1] == 1.0)                      # isolated node: bias only
+    assert torch.all(feats.grad[1] == 0)
+
+
+def test_bf16_features(cuda_device):
+    """bf16 feature storage, fp32 accumulation: compared with the fp64 oracle on the rounded inputs."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = 3000, 9, 40000
+    t = random_triples(N, R, E, seed=4)
+    tp = torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, R))
+    torch.manual_seed(8)
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=64,
+                                         out_features=64, decomposition={'type': 'block', 'num_blocks': 4},
+                                         vertical_stacking=True).to(cuda_device)
+    feats = torch.randn(N, 64, device=cuda_device).to(torch.bfloat16).requires_grad_(True)
+    out = layer(feats)
+    assert out.dtype == torch.float32
+    G = torch.randn_like(out)
+    out.backward(G)
+    ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().float().cpu().numpy(),
+                                  True, G.cpu().numpy())
+    # inputs are identical (already rounded), so only accumulation order differs: fp32 tolerance holds for out
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_out, atol=ATOL, rtol=1e-4)
+    np.testing.assert_allclose(layer.blocks.grad.cpu().numpy(), ref_g['blocks'], atol=ATOL, rtol=2e-4)
+    assert feats.grad.dtype == torch.bfloat16            # gradient is rounded to the feature dtype
+    np.testing.assert_allclose(feats.grad.float().cpu().numpy(), ref_g['features'], atol=2e-2, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at a large shape
+# ---------------------------------------------------------------------------------------------------
+def test_properties_large(cuda_device):
+    """AM-scale-ish graph (1/8): linearity in X, and the closed-form row identity
+    out[s] = (#distinct relations at s) * colsum(W) when X = 1, all W_p = W, vertical normalisation."""
+    from torch_rgcn_b200 import GraphPlan, rgcn_propagate, _lib
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = 200000, 133, 750000
+    t = random_triples(N, R, E, seed=0, device=cuda_device)
+    from torch_rgcn_b200.utils import add_inverse_and_self
+    tp = add_inverse_and_self(t, N, R, device=cuda_device)
+    Rp = 2 * R + 1
+    plan = GraphPlan(tp, N, Rp, _lib.NORM_ROW)
+    I = O = 16
+    W1 = torch.randn(I, O, device=cuda_device)
+    W = W1.expand(Rp, I, O).contiguous()
+    ones = torch.ones(N, I, device=cuda_device)
+    out = rgcn_propagate(plan, 'dense', I, O, ones, weights=W)
+    key = tp[:, 0] * Rp + tp[:, 1]
+    distinct = torch.bincount(torch.unique(key) // Rp, minlength=N).float()
+    expect = distinct[:, None] * W1.sum(0)[None, :]
+    torch.testing.assert_close(out, expect, atol=2e-4, rtol=1e-4)
+    # linearity
+    Wr = torch.randn(Rp, I, O, device=cuda_device)
+    x1, x2 = torch.randn(N, I, device=cuda_device), torch.randn(N, I, device=cuda_device)
+    a = rgcn_propagate(plan, 'dense', I, O, x1, weights=Wr)
+    b = rgcn_propagate(plan, 'dense', I, O, x2, weights=Wr)
+    c = rgcn_propagate(plan, 'dense', I, O, x1 + 2 * x2, weights=Wr)
+    torch.testing.assert_close(c, a + 2 * b, atol=2e-4, rtol=1e-4)
+    # adjointness: <A(x), g> == <x, A^T(g)>
+    x = x1.clone().requires_grad_(True)
+    y = rgcn_propagate(plan, 'dense', I, O, x, weights=Wr)
+    g = torch.randn_like(y)
+    y.backward(g)
+    lhs = (y.detach().double() * g.double()).sum()
+    rhs = (x.detach().double() * x.grad.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5

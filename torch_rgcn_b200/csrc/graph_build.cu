@@ -1,0 +1,379 @@
+// Integer side of the path: triple augmentation, adjacency stacking, degree normalisation and the
+// sorted edge lists ("graph plan") that the propagation kernels walk.
+//
+// Reference behaviour restated here (never its code): torch_rgcn/utils.py:71-97 (sum_sparse),
+// :100-141 (inverse / self-loop triples), :143-166 (stack_matrices), :168-196 (block_diag) and the
+// normalisation glue in torch_rgcn/layers.py:255-273 / :490-510.
+//
+// Sorting uses cub::DeviceRadixSort / DeviceScan from the CUDA toolkit (header-only, compiled into
+// this library); everything else is hand-written.  All of this is O(nnz) integer work done once per
+// graph (NC) or once per forward (LP).
+#include <cub/cub.cuh>
+#include "common.cuh"
+
+using namespace rgcn;
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------------------------------
+// helper kernels (utils.py equivalents)
+// ------------------------------------------------------------------------------------------
+__global__ void k_add_inverse_and_self(const int64_t* __restrict__ t, int64_t E, int64_t N, int64_t R,
+                                       int64_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t total = 2 * E + N;
+    if (i >= total) return;
+    int64_t s, p, o;
+    if (i < E) {
+        s = t[3 * i]; p = t[3 * i + 1]; o = t[3 * i + 2];
+    } else if (i < 2 * E) {
+        int64_t j = i - E;
+        s = t[3 * j + 2]; p = t[3 * j + 1] + R; o = t[3 * j];
+    } else {
+        s = o = i - 2 * E; p = 2 * R;
+    }
+    out[3 * i] = s; out[3 * i + 1] = p; out[3 * i + 2] = o;
+}
+
+__global__ void k_generate_inverses(const int64_t* __restrict__ t, int64_t E, int64_t R, int64_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    out[3 * i] = t[3 * i + 2]; out[3 * i + 1] = t[3 * i + 1] + R; out[3 * i + 2] = t[3 * i];
+}
+
+__global__ void k_lp_triples_plus(const int64_t* __restrict__ t, int64_t E, int64_t R,
+                                  const int64_t* __restrict__ self_nodes, int64_t n_self, int64_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t total = 3 * E + n_self;
+    if (i >= total) return;
+    int64_t s, p, o;
+    if (i < E) {
+        s = t[3 * i]; p = t[3 * i + 1]; o = t[3 * i + 2];
+    } else if (i < 2 * E) {
+        int64_t j = i - E;
+        s = t[3 * j + 2]; p = t[3 * j + 1] + R; o = t[3 * j];
+    } else if (i < 3 * E) {                       // the reference appends the triples a second time (utils.py:124)
+        int64_t j = i - 2 * E;
+        s = t[3 * j]; p = t[3 * j + 1]; o = t[3 * j + 2];
+    } else {
+        s = o = self_nodes[i - 3 * E]; p = 2 * R;
+    }
+    out[3 * i] = s; out[3 * i + 1] = p; out[3 * i + 2] = o;
+}
+
+__global__ void k_init_bounds(int64_t* b) { b[0] = INT64_MIN; b[1] = INT64_MIN; }
+
+__global__ void k_stack_matrices(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int vertical,
+                                 int64_t* __restrict__ out, int64_t* bounds) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int64_t fr = t[3 * i], off = t[3 * i + 1] * N, to = t[3 * i + 2];
+    if (vertical) fr += off; else to += off;
+    out[2 * i] = fr; out[2 * i + 1] = to;
+    if (bounds) {
+        atomicMax(reinterpret_cast<long long*>(bounds), (long long)fr);
+        atomicMax(reinterpret_cast<long long*>(bounds + 1), (long long)to);
+    }
+}
+
+__global__ void k_table_add(const int64_t* __restrict__ idx, const float* __restrict__ v, int64_t nnz, int sel,
+                            float* table) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nnz) atomicAdd(table + idx[2 * i + sel], v[i]);
+}
+
+__global__ void k_table_gather(const int64_t* __restrict__ idx, int64_t nnz, int sel, const float* __restrict__ table,
+                               float* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nnz) out[i] = table[idx[2 * i + sel]];
+}
+
+__global__ void k_block_diag(const float* __restrict__ b, int64_t R, int64_t nb, int64_t bi, int64_t bo,
+                             float* __restrict__ out) {
+    int64_t I = nb * bi, O = nb * bo;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= R * I * O) return;
+    int64_t y = i % O, x = (i / O) % I, r = i / (I * O);
+    int64_t kb = x / bi;
+    out[i] = (y / bo == kb) ? b[((r * nb + kb) * bi + x % bi) * bo + y % bo] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan build
+// ------------------------------------------------------------------------------------------
+enum Ordering { ORD_DST = 0, ORD_SRC = 1, ORD_REL = 2 };
+
+// key layouts: DST (s*R'+p)*N+o, SRC (o*R'+p)*N+s, REL (p*N+s)*N+o
+__global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int ord,
+                            uint64_t* __restrict__ keys, int32_t* __restrict__ idx, int32_t* status) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int64_t s = t[3 * e], p = t[3 * e + 1], o = t[3 * e + 2];
+    if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) {
+        if (status) atomicAdd(status, 1);
+        s = p = o = 0;                              // keep the walk in bounds; the caller raises on status != 0
+    }
+    uint64_t k;
+    if (ord == ORD_DST) k = ((uint64_t)s * Rp + p) * N + o;
+    else if (ord == ORD_SRC) k = ((uint64_t)o * Rp + p) * N + s;
+    else k = ((uint64_t)p * N + s) * N + o;
+    keys[e] = k;
+    idx[e] = (int32_t)e;
+}
+
+// sorted keys -> index arrays + row pointer.  `a` = row id (s / o / p), written only through rowptr.
+__global__ void k_decode(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int64_t Rp, int ord,
+                         int64_t nrows, int32_t* __restrict__ rowptr, int32_t* __restrict__ c0,
+                         int32_t* __restrict__ c1) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    uint64_t k = keys[e];
+    int64_t row, prev;
+    if (ord == ORD_REL) {
+        uint64_t ps = k / N;                 // p*N + s
+        row = (int64_t)(ps / N);
+        c0[e] = (int32_t)(ps % N);           // dst s
+        c1[e] = (int32_t)(k % N);            // src o
+        prev = e ? (int64_t)(keys[e - 1] / N / N) : -1;
+    } else {
+        uint64_t ap = k / N;                 // a*R' + p
+        row = (int64_t)(ap / Rp);
+        c0[e] = (int32_t)(k % N);            // the other endpoint
+        c1[e] = (int32_t)(ap % Rp);          // relation
+        prev = e ? (int64_t)(keys[e - 1] / N / Rp) : -1;
+    }
+    for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = (int32_t)e;
+    if (e == nnz - 1)
+        for (int64_t r = row + 1; r <= nrows; ++r) rowptr[r] = (int32_t)nnz;
+}
+
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// segment = run of equal key / N in the sorted list ((s,p) for DST, (o,p) for SRC)
+__global__ void k_seg_flags(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int32_t* __restrict__ flag) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    flag[e] = (e == 0 || keys[e] / N != keys[e - 1] / N) ? 1 : 0;
+}
+
+__global__ void k_seg_bounds(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N,
+                             const int32_t* __restrict__ segid, int32_t* __restrict__ starts,
+                             int32_t* __restrict__ ends) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    uint64_t k = keys[e] / N;
+    int32_t sgm = segid[e] - 1;
+    if (e == 0 || keys[e - 1] / N != k) starts[sgm] = (int32_t)e;
+    if (e == nnz - 1 || keys[e + 1] / N != k) ends[sgm] = (int32_t)e + 1;
+}
+
+// count of the segment each edge belongs to, scattered back to the caller's edge order
+__global__ void k_seg_count_scatter(int64_t nnz, const int32_t* __restrict__ segid, const int32_t* __restrict__ starts,
+                                    const int32_t* __restrict__ ends, const int32_t* __restrict__ perm,
+                                    int32_t* __restrict__ cnt_orig) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int32_t sgm = segid[e] - 1;
+    cnt_orig[perm[e]] = ends[sgm] - starts[sgm];
+}
+
+// val = 1 / sums, with the horizontal-mode permutation cat([sums[n:2n], sums[:n], sums[-i:]])
+// (layers.py:271-273 / :509-510).  IEEE division, like torch's vals / sums.
+__global__ void k_edge_values(int64_t nnz, const int32_t* __restrict__ cnt, int norm, int64_t n, int64_t i,
+                              float* __restrict__ val) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int64_t src = e;
+    if (norm == RGCN_NORM_COL_SWAPPED) {
+        if (e < n) src = e + n;
+        else if (e < 2 * n) src = e - n;
+        else src = nnz - i + (e - 2 * n);
+    }
+    val[e] = __fdiv_rn(1.0f, (float)cnt[src]);
+}
+
+__global__ void k_gather_val(int64_t nnz, const int32_t* __restrict__ perm, const float* __restrict__ val,
+                             float* __restrict__ out) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < nnz) out[e] = val[perm[e]];
+}
+
+int bits_for(unsigned __int128 maxkey) {
+    int b = 1;
+    while (b < 64 && (maxkey >> b) != 0) ++b;
+    return b;
+}
+
+struct BuildWs {
+    uint64_t *k0, *k1;
+    int32_t *i0, *i1, *flag, *segid, *starts, *ends, *cnt;
+    void* cub;
+    size_t cub_bytes;
+    size_t total;
+};
+
+BuildWs carve_build(void* ws, int64_t nnz) {
+    BuildWs b;
+    size_t n = (size_t)(nnz > 0 ? nnz : 1);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    Carver c(ws);
+    b.k0 = c.take<uint64_t>(n); b.k1 = c.take<uint64_t>(n);
+    b.i0 = c.take<int32_t>(n); b.i1 = c.take<int32_t>(n);
+    b.flag = c.take<int32_t>(n); b.segid = c.take<int32_t>(n);
+    b.starts = c.take<int32_t>(n); b.ends = c.take<int32_t>(n);
+    b.cnt = c.take<int32_t>(n);
+    b.cub_bytes = align_up(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+    b.cub = c.take<char>(b.cub_bytes);
+    b.total = c.off;
+    return b;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int rgcn_add_inverse_and_self(const int64_t* triples, int64_t E, int64_t N, int64_t R, int64_t* out,
+                                         rgcn_stream_t stream) {
+    RGCN_REQUIRE(E >= 0 && N >= 0 && out && (triples || E == 0), RGCN_ERR_ARG, "rgcn_add_inverse_and_self: bad arguments");
+    int64_t total = 2 * E + N;
+    if (total == 0) return RGCN_OK;
+    RGCN_LAUNCH(k_add_inverse_and_self, grid_for(total, kBlock), kBlock, 0, (cudaStream_t)stream, triples, E, N, R, out);
+    return RGCN_OK;
+}
+
+extern "C" int rgcn_generate_inverses(const int64_t* triples, int64_t E, int64_t R, int64_t* out, rgcn_stream_t stream) {
+    RGCN_REQUIRE(E >= 0 && (E == 0 || (triples && out)), RGCN_ERR_ARG, "rgcn_generate_inverses: bad arguments");
+    if (E == 0) return RGCN_OK;
+    RGCN_LAUNCH(k_generate_inverses, grid_for(E, kBlock), kBlock, 0, (cudaStream_t)stream, triples, E, R, out);
+    return RGCN_OK;
+}
+
+extern "C" int rgcn_lp_triples_plus(const int64_t* triples, int64_t E, int64_t R, const int64_t* self_nodes,
+                                    int64_t n_self, int64_t* out, rgcn_stream_t stream) {
+    RGCN_REQUIRE(E >= 0 && n_self >= 0 && (E == 0 || triples) && (n_self == 0 || self_nodes), RGCN_ERR_ARG,
+                 "rgcn_lp_triples_plus: bad arguments");
+    int64_t total = 3 * E + n_self;
+    if (total == 0) return RGCN_OK;
+    RGCN_REQUIRE(out, RGCN_ERR_ARG, "rgcn_lp_triples_plus: out is NULL");
+    RGCN_LAUNCH(k_lp_triples_plus, grid_for(total, kBlock), kBlock, 0, (cudaStream_t)stream, triples, E, R, self_nodes,
+                n_self, out);
+    return RGCN_OK;
+}
+
+extern "C" int rgcn_stack_matrices(const int64_t* triples, int64_t nnz, int64_t N, int64_t Rp, int vertical,
+                                   int64_t* indices_out, int64_t* bounds_out, rgcn_stream_t stream) {
+    (void)Rp;
+    RGCN_REQUIRE(nnz >= 0 && (nnz == 0 || (triples && indices_out)), RGCN_ERR_ARG, "rgcn_stack_matrices: bad arguments");
+    if (bounds_out) RGCN_LAUNCH(k_init_bounds, 1, 1, 0, (cudaStream_t)stream, bounds_out);
+    if (nnz == 0) return RGCN_OK;
+    RGCN_LAUNCH(k_stack_matrices, grid_for(nnz, kBlock), kBlock, 0, (cudaStream_t)stream, triples, nnz, N, vertical,
+                indices_out, bounds_out);
+    return RGCN_OK;
+}
+
+extern "C" int rgcn_sum_sparse(const int64_t* indices, const float* values, int64_t nnz, int64_t rows, int64_t cols,
+                               int row_normalisation, float* table_ws, float* sums_out, rgcn_stream_t stream) {
+    RGCN_REQUIRE(nnz >= 0 && rows >= 0 && cols >= 0, RGCN_ERR_ARG, "rgcn_sum_sparse: bad sizes");
+    if (nnz == 0) return RGCN_OK;
+    RGCN_REQUIRE(indices && values && table_ws && sums_out, RGCN_ERR_ARG, "rgcn_sum_sparse: NULL pointer");
+    int sel = row_normalisation ? 0 : 1;
+    int64_t len = row_normalisation ? rows : cols;
+    RGCN_CHECK_CUDA(cudaMemsetAsync(table_ws, 0, (size_t)len * sizeof(float), (cudaStream_t)stream));
+    RGCN_LAUNCH(k_table_add, grid_for(nnz, kBlock), kBlock, 0, (cudaStream_t)stream, indices, values, nnz, sel, table_ws);
+    RGCN_LAUNCH(k_table_gather, grid_for(nnz, kBlock), kBlock, 0, (cudaStream_t)stream, indices, nnz, sel, table_ws,
+                sums_out);
+    return RGCN_OK;
+}
+
+extern "C" int rgcn_block_diag(const float* blocks, int64_t R, int64_t nb, int64_t bi, int64_t bo, float* out,
+                               rgcn_stream_t stream) {
+    RGCN_REQUIRE(R >= 0 && nb > 0 && bi > 0 && bo > 0, RGCN_ERR_ARG, "rgcn_block_diag: bad sizes");
+    int64_t total = R * nb * bi * nb * bo;
+    if (total == 0) return RGCN_OK;
+    RGCN_REQUIRE(blocks && out, RGCN_ERR_ARG, "rgcn_block_diag: NULL pointer");
+    RGCN_LAUNCH(k_block_diag, grid_for(total, kBlock), kBlock, 0, (cudaStream_t)stream, blocks, R, nb, bi, bo, out);
+    return RGCN_OK;
+}
+
+extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp) {
+    (void)N; (void)Rp;
+    return carve_build(nullptr, nnz).total;
+}
+
+extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, int64_t Rp, int norm,
+                                int64_t n_general, int64_t n_self, const float* val_in, rgcn_graph* g, void* ws,
+                                size_t ws_bytes, rgcn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RGCN_REQUIRE(g, RGCN_ERR_ARG, "rgcn_graph_build: graph is NULL");
+    RGCN_REQUIRE(nnz >= 0 && N > 0 && Rp > 0, RGCN_ERR_ARG, "rgcn_graph_build: bad sizes nnz=%lld N=%lld R'=%lld",
+                 (long long)nnz, (long long)N, (long long)Rp);
+    RGCN_REQUIRE(nnz < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED,
+                 "rgcn_graph_build: nnz and num_nodes must fit int32");
+    unsigned __int128 maxkey = (unsigned __int128)N * (unsigned __int128)Rp * (unsigned __int128)N;
+    RGCN_REQUIRE((maxkey >> 63) == 0, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: N*R'*N does not fit a 64-bit sort key");
+    RGCN_REQUIRE(norm == RGCN_NORM_ROW || norm == RGCN_NORM_COL_SWAPPED || norm == RGCN_NORM_EXPLICIT, RGCN_ERR_ARG,
+                 "rgcn_graph_build: unknown normalisation %d", norm);
+    if (norm == RGCN_NORM_COL_SWAPPED)
+        RGCN_REQUIRE(n_general >= 0 && n_self >= 0 && 2 * n_general + n_self == nnz && (n_self > 0 || nnz == 0),
+                     RGCN_ERR_ARG,
+                     "rgcn_graph_build: horizontal permutation needs 2n+i == nnz (n=%lld i=%lld nnz=%lld)",
+                     (long long)n_general, (long long)n_self, (long long)nnz);
+    if (norm == RGCN_NORM_EXPLICIT) RGCN_REQUIRE(val_in || nnz == 0, RGCN_ERR_ARG, "rgcn_graph_build: val_in is NULL");
+    RGCN_REQUIRE(g->d_rowptr && g->s_rowptr && g->r_relptr && g->status, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
+    if (nnz > 0)
+        RGCN_REQUIRE(triples && g->d_src && g->d_rel && g->d_val && g->s_dst && g->s_rel && g->s_val && g->r_dst &&
+                         g->r_src && g->r_val && g->val, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
+    BuildWs b = carve_build(ws, nnz);
+    RGCN_REQUIRE(ws_bytes >= b.total && (ws || b.total == 0), RGCN_ERR_WORKSPACE,
+                 "rgcn_graph_build: workspace %zu < %zu bytes", ws_bytes, b.total);
+    g->num_nodes = N; g->num_rels = Rp; g->nnz = nnz;
+    RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 4 * sizeof(int32_t), stream));
+    if (nnz == 0) {
+        RGCN_CHECK_CUDA(cudaMemsetAsync(g->d_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
+        RGCN_CHECK_CUDA(cudaMemsetAsync(g->s_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
+        RGCN_CHECK_CUDA(cudaMemsetAsync(g->r_relptr, 0, (size_t)(Rp + 1) * sizeof(int32_t), stream));
+        return RGCN_OK;
+    }
+    const int grid = grid_for(nnz, kBlock);
+    const int key_bits = bits_for(maxkey);
+    if (norm == RGCN_NORM_EXPLICIT)
+        RGCN_CHECK_CUDA(cudaMemcpyAsync(g->val, val_in, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+
+    // the ordering whose segments give the normalisation counts goes first
+    const int first = (norm == RGCN_NORM_COL_SWAPPED) ? ORD_SRC : ORD_DST;
+    const int order[3] = {first, first == ORD_DST ? ORD_SRC : ORD_DST, ORD_REL};
+    for (int step = 0; step < 3; ++step) {
+        const int ord = order[step];
+        RGCN_LAUNCH(k_make_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, ord, b.k0, b.i0,
+                    step == 0 ? g->status : (int32_t*)nullptr);
+        size_t cub_bytes = b.cub_bytes;
+        RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, key_bits,
+                                                        stream));
+        rgcn::g_launches.fetch_add((key_bits + 7) / 8 + 1, std::memory_order_relaxed);
+        int32_t *rowptr, *c0, *c1; float* oval; int64_t nrows;
+        if (ord == ORD_DST) { rowptr = g->d_rowptr; c0 = g->d_src; c1 = g->d_rel; oval = g->d_val; nrows = N; }
+        else if (ord == ORD_SRC) { rowptr = g->s_rowptr; c0 = g->s_dst; c1 = g->s_rel; oval = g->s_val; nrows = N; }
+        else { rowptr = g->r_relptr; c0 = g->r_dst; c1 = g->r_src; oval = g->r_val; nrows = Rp; }
+        RGCN_LAUNCH(k_decode, grid, kBlock, 0, stream, b.k1, nnz, N, Rp, ord, nrows, rowptr, c0, c1);
+        if (step == 0 && norm != RGCN_NORM_EXPLICIT) {
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, N, b.flag);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
+            rgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, N, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_seg_count_scatter, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.i1, b.cnt);
+            RGCN_LAUNCH(k_edge_values, grid, kBlock, 0, stream, nnz, b.cnt, norm, n_general, n_self, g->val);
+        }
+        RGCN_LAUNCH(k_gather_val, grid, kBlock, 0, stream, nnz, b.i1, g->val, oval);
+    }
+    return RGCN_OK;
+}

@@ -1,0 +1,348 @@
+// rgcn_forward / rgcn_backward: argument checking, workspace layout and kernel dispatch.
+//
+// Forward  (reference layers.py:286-306 / :518-556):  out[s] = bias + sum_e val_e * T_p(X[o])
+// Backward (reference: autograd only; closed forms in SURVEY a10):
+//   gX[o]  = sum_e val_e * T_p^T(G[s])        -- same walk on the source-major CSR, transposed weights
+//   gW_p   = sum_{e in p} val_e X[o]^T G[s]   -- relation-major walk, projected onto the decomposition
+//   gbias  = sum_s G[s]
+#include "common.cuh"
+#include "propagate_generic.cuh"
+#include "propagate_fast.cuh"
+
+using namespace rgcn;
+
+namespace {
+
+int pow2_slots(int dim) {   // lane-strided register slots needed to cover `dim` values with 32 lanes
+    int k = (dim + 31) / 32;
+    int p = 1;
+    while (p < k) p <<= 1;
+    return p;
+}
+
+template <typename XT>
+int launch_prop_generic(const PropArgs& A, const XT* X, cudaStream_t st) {
+    const int maxdim = A.featureless ? A.O : (A.I > A.O ? A.I : A.O);
+    const int K = pow2_slots(maxdim);
+    RGCN_REQUIRE(K <= 16, RGCN_ERR_UNSUPPORTED, "generic propagate: feature width %d > 512 not supported yet", maxdim);
+    const int wpb = 8, block = wpb * 32;
+    const size_t smem = (A.featureless || A.form == RGCN_W_DIAG) ? 0 : (size_t)wpb * A.I * sizeof(float);
+    int64_t want = (A.nrows + wpb - 1) / wpb;
+    int grid = (int)(want < (int64_t)kNumSMs * 64 ? want : (int64_t)kNumSMs * 64);
+    if (grid < 1) grid = 1;
+    switch (K) {
+        case 1: RGCN_LAUNCH((k_prop_generic<XT, 1>), grid, block, smem, st, A, X); break;
+        case 2: RGCN_LAUNCH((k_prop_generic<XT, 2>), grid, block, smem, st, A, X); break;
+        case 4: RGCN_LAUNCH((k_prop_generic<XT, 4>), grid, block, smem, st, A, X); break;
+        case 8: RGCN_LAUNCH((k_prop_generic<XT, 8>), grid, block, smem, st, A, X); break;
+        default: RGCN_LAUNCH((k_prop_generic<XT, 16>), grid, block, smem, st, A, X); break;
+    }
+    return RGCN_OK;
+}
+
+template <typename XT>
+int launch_prop(const PropArgs& A, const XT* X, cudaStream_t st) {
+    int rc = try_launch_prop_fast(A, X, st);       // > 0: no fast path for this shape
+    if (rc <= 0) return rc;
+    return launch_prop_generic(A, X, st);
+}
+
+template <typename XT>
+int launch_wgrad_generic(WGradArgs A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
+    int nel = (A.form == RGCN_W_DIAG) ? A.I : (A.form == RGCN_W_BLOCK ? A.nb * A.bi * A.bo : A.I * A.O);
+    if (A.form == RGCN_W_BLOCK && A.self_rel >= 0 && A.I * A.O > nel) nel = A.I * A.O;
+    int KE = 1;
+    while (KE < 32 && KE * 256 < nel) KE <<= 1;
+    int tile = (int)(40960 / ((size_t)(A.I + A.O) * sizeof(float)));
+    tile = tile < 1 ? 1 : (tile > 32 ? 32 : tile);
+    A.tile = tile;
+    const size_t smem = (size_t)tile * (A.I + A.O) * sizeof(float);
+    RGCN_REQUIRE(smem <= 48 * 1024, RGCN_ERR_UNSUPPORTED, "generic weight-grad: I+O=%d too wide", A.I + A.O);
+    int64_t gy = nnz / ((int64_t)Rp * 2048) + 1;
+    if (gy > 1024) gy = 1024;
+    dim3 grid(Rp, (unsigned)gy);
+    switch (KE) {
+        case 1: RGCN_LAUNCH((k_wgrad_generic<XT, 1>), grid, 256, smem, st, A, X, G); break;
+        case 2: RGCN_LAUNCH((k_wgrad_generic<XT, 2>), grid, 256, smem, st, A, X, G); break;
+        case 4: RGCN_LAUNCH((k_wgrad_generic<XT, 4>), grid, 256, smem, st, A, X, G); break;
+        case 8: RGCN_LAUNCH((k_wgrad_generic<XT, 8>), grid, 256, smem, st, A, X, G); break;
+        case 16: RGCN_LAUNCH((k_wgrad_generic<XT, 16>), grid, 256, smem, st, A, X, G); break;
+        default: RGCN_LAUNCH((k_wgrad_generic<XT, 32>), grid, 256, smem, st, A, X, G); break;
+    }
+    return RGCN_OK;
+}
+
+template <typename XT>
+int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
+    int rc = try_launch_wgrad_fast(A, X, G, nnz, Rp, st);
+    if (rc <= 0) return rc;
+    return launch_wgrad_generic(A, X, G, nnz, Rp, st);
+}
+
+int launch_featureless_grad(FeaturelessGradArgs A, const float* G, cudaStream_t st) {
+    const int K = pow2_slots(A.O);
+    RGCN_REQUIRE(K <= 16, RGCN_ERR_UNSUPPORTED, "featureless weight-grad: out_dim %d > 512 not supported yet", A.O);
+    int wpb = 8;
+    size_t per_warp = (A.form == RGCN_W_BASIS) ? (size_t)A.B * A.O * sizeof(float) : 0;
+    while (wpb > 1 && per_warp * wpb > 32 * 1024) wpb >>= 1;
+    RGCN_REQUIRE(per_warp * wpb <= 40 * 1024, RGCN_ERR_UNSUPPORTED, "featureless basis grad: B*O=%d too large", A.B * A.O);
+    size_t comps_bytes = (A.form == RGCN_W_BASIS) ? (size_t)A.num_rels * A.B * sizeof(float) : 0;
+    A.comps_in_smem = (comps_bytes > 0 && per_warp * wpb + comps_bytes <= 48 * 1024) ? 1 : 0;
+    const size_t smem = per_warp * wpb + (A.comps_in_smem ? comps_bytes : 0);
+    int64_t want = (A.N + wpb - 1) / wpb;
+    int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+    if (grid < 1) grid = 1;
+    const int block = wpb * 32;
+    switch (K) {
+        case 1: RGCN_LAUNCH((k_wgrad_featureless<1>), grid, block, smem, st, A, G); break;
+        case 2: RGCN_LAUNCH((k_wgrad_featureless<2>), grid, block, smem, st, A, G); break;
+        case 4: RGCN_LAUNCH((k_wgrad_featureless<4>), grid, block, smem, st, A, G); break;
+        case 8: RGCN_LAUNCH((k_wgrad_featureless<8>), grid, block, smem, st, A, G); break;
+        default: RGCN_LAUNCH((k_wgrad_featureless<16>), grid, block, smem, st, A, G); break;
+    }
+    return RGCN_OK;
+}
+
+int launch_transpose(const float* in, int64_t n, int rows, int cols, float* out, cudaStream_t st) {
+    int64_t total = n * rows * cols;
+    if (total == 0) return RGCN_OK;
+    RGCN_LAUNCH(k_transpose_batched, grid_for(total, 256), 256, 0, st, in, n, rows, cols, out);
+    return RGCN_OK;
+}
+
+struct Shape {
+    int64_t N, Rp, nnz;
+    int I, O, B, nb, bi, bo, Rb;
+    size_t w_elems;          // elements of the effective dense (R', I, O) weight (featured forms)
+    size_t blocks_elems;
+};
+
+int check_common(const rgcn_graph* g, const rgcn_params* p, Shape* s, const char* who) {
+    RGCN_REQUIRE(g && p, RGCN_ERR_ARG, "%s: NULL graph or params", who);
+    s->N = g->num_nodes; s->Rp = g->num_rels; s->nnz = g->nnz;
+    RGCN_REQUIRE(p->out_dim > 0 && p->in_dim > 0, RGCN_ERR_ARG, "%s: bad dims in=%lld out=%lld", who,
+                 (long long)p->in_dim, (long long)p->out_dim);
+    RGCN_REQUIRE(p->out_dim < (1 << 30) && (p->featureless || p->in_dim < (1 << 30)), RGCN_ERR_ARG, "%s: dims too large", who);
+    s->I = (int)p->in_dim; s->O = (int)p->out_dim;
+    s->B = (int)p->num_bases; s->nb = (int)p->num_blocks; s->bi = s->bo = 0; s->Rb = (int)p->num_block_rels;
+    if (p->featureless) {
+        RGCN_REQUIRE(p->in_dim == g->num_nodes, RGCN_ERR_ARG, "%s: featureless layer needs in_dim == num_nodes", who);
+        RGCN_REQUIRE(p->form != RGCN_W_DIAG, RGCN_ERR_UNSUPPORTED, "%s: featureless diagonal weights are not defined", who);
+        RGCN_REQUIRE(!p->blocks_self && !p->self_mask, RGCN_ERR_UNSUPPORTED,
+                     "%s: featureless layers with blocks_self / self_mask are unreachable in the reference", who);
+    }
+    switch (p->form) {
+        case RGCN_W_DENSE: RGCN_REQUIRE(p->weights, RGCN_ERR_ARG, "%s: weights is NULL", who); break;
+        case RGCN_W_DIAG:
+            RGCN_REQUIRE(p->weights, RGCN_ERR_ARG, "%s: weights is NULL", who);
+            RGCN_REQUIRE(p->in_dim == p->out_dim, RGCN_ERR_ARG, "%s: diagonal weights need in_dim == out_dim", who);
+            break;
+        case RGCN_W_BASIS:
+            RGCN_REQUIRE(p->bases && p->comps && p->num_bases > 0, RGCN_ERR_ARG, "%s: bases/comps missing", who);
+            break;
+        case RGCN_W_BLOCK:
+            RGCN_REQUIRE(p->blocks && p->num_blocks > 0, RGCN_ERR_ARG, "%s: blocks missing", who);
+            RGCN_REQUIRE(p->in_dim % p->num_blocks == 0 && p->out_dim % p->num_blocks == 0, RGCN_ERR_ARG,
+                         "%s: dims (%lld, %lld) not divisible by num_blocks %lld", who, (long long)p->in_dim,
+                         (long long)p->out_dim, (long long)p->num_blocks);
+            s->bi = (int)(p->in_dim / p->num_blocks); s->bo = (int)(p->out_dim / p->num_blocks);
+            RGCN_REQUIRE(p->num_block_rels == s->Rp - (p->blocks_self ? 1 : 0), RGCN_ERR_ARG,
+                         "%s: num_block_rels %lld inconsistent with R'=%lld", who, (long long)p->num_block_rels,
+                         (long long)s->Rp);
+            break;
+        default: RGCN_REQUIRE(false, RGCN_ERR_ARG, "%s: unknown weight form %d", who, p->form);
+    }
+    s->w_elems = p->featureless ? 0 : (size_t)s->Rp * s->I * s->O;
+    s->blocks_elems = (p->form == RGCN_W_BLOCK) ? (size_t)s->Rb * s->nb * s->bi * s->bo : 0;
+    return RGCN_OK;
+}
+
+void fill_weights(PropArgs& A, const rgcn_params* p, const Shape& s) {
+    A.form = p->form; A.featureless = p->featureless;
+    A.I = s.I; A.O = s.O; A.B = s.B; A.nb = s.nb; A.bi = s.bi; A.bo = s.bo;
+    A.self_rel = p->blocks_self ? (int)s.Rp - 1 : -1;
+    A.W = p->weights; A.bases = p->bases; A.comps = p->comps; A.blocks = p->blocks; A.blocks_self = p->blocks_self;
+    A.bias = nullptr; A.out_mask = nullptr; A.in_mask = nullptr; A.mask_rel = (int)s.Rp - 1;
+}
+
+}  // namespace
+
+extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p) {
+    if (!g || !p) return 0;
+    if (p->form == RGCN_W_BASIS && !p->featureless)
+        return align_up((size_t)g->num_rels * p->in_dim * p->out_dim * sizeof(float));
+    return 0;
+}
+
+extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const void* X, int x_dtype, float* out,
+                            void* ws, size_t ws_bytes, rgcn_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    Shape s;
+    int rc = check_common(g, p, &s, "rgcn_forward");
+    if (rc) return rc;
+    RGCN_REQUIRE(out, RGCN_ERR_ARG, "rgcn_forward: out is NULL");
+    RGCN_REQUIRE(p->featureless || X, RGCN_ERR_ARG, "rgcn_forward: features is NULL");
+    RGCN_REQUIRE(x_dtype == RGCN_F32 || x_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_forward: unknown dtype %d", x_dtype);
+    size_t need = rgcn_forward_workspace_bytes(g, p);
+    RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_forward: workspace %zu < %zu", ws_bytes, need);
+
+    PropArgs A{};
+    A.rowptr = g->d_rowptr; A.col = g->d_src; A.rel = g->d_rel; A.val = g->d_val;
+    A.nrows = s.N; A.N = s.N;
+    fill_weights(A, p, s);
+    A.bias = p->bias; A.out_mask = p->self_mask; A.out = out;
+    if (p->form == RGCN_W_BASIS && !p->featureless) {      // materialise the small (R', I, O) table only
+        float* weff = static_cast<float*>(ws);
+        int64_t IO = (int64_t)s.I * s.O;
+        dim3 grid(grid_for(IO, 256), (unsigned)s.Rp);
+        RGCN_LAUNCH(k_basis_combine, grid, 256, 0, st, p->comps, p->bases, (int)s.Rp, s.B, IO, weff);
+        A.form = RGCN_W_DENSE; A.W = weff;
+    }
+    if (x_dtype == RGCN_BF16 && !p->featureless) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
+    return launch_prop(A, static_cast<const float*>(X), st);
+}
+
+extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p) {
+    if (!g || !p || p->featureless) return 0;
+    size_t w = align_up((size_t)g->num_rels * p->in_dim * p->out_dim * sizeof(float));
+    switch (p->form) {
+        case RGCN_W_DENSE: return w;                       // W^T
+        case RGCN_W_BASIS: return 3 * w;                   // W_eff, W_eff^T, gW_eff
+        case RGCN_W_BLOCK: {
+            size_t nb = (size_t)p->num_blocks;
+            size_t blocks = align_up((size_t)p->num_block_rels * nb * (p->in_dim / nb) * (p->out_dim / nb) * sizeof(float));
+            return blocks + (p->blocks_self ? align_up((size_t)p->in_dim * p->out_dim * sizeof(float)) : 0);
+        }
+        default: return 0;
+    }
+}
+
+extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const void* X, int x_dtype,
+                             const float* G, const rgcn_grads* gr, void* ws, size_t ws_bytes, rgcn_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    Shape s;
+    int rc = check_common(g, p, &s, "rgcn_backward");
+    if (rc) return rc;
+    RGCN_REQUIRE(G && gr, RGCN_ERR_ARG, "rgcn_backward: grad_out or grads is NULL");
+    RGCN_REQUIRE(p->featureless || X, RGCN_ERR_ARG, "rgcn_backward: features is NULL");
+    RGCN_REQUIRE(x_dtype == RGCN_F32 || x_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_backward: unknown dtype %d", x_dtype);
+    size_t need = rgcn_backward_workspace_bytes(g, p);
+    RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_backward: workspace %zu < %zu", ws_bytes, need);
+    Carver carve(ws);
+    const int64_t IO = (int64_t)s.I * s.O;
+
+    // ---- gbias
+    if (gr->bias) {
+        RGCN_CHECK_CUDA(cudaMemsetAsync(gr->bias, 0, (size_t)s.O * sizeof(float), st));
+        int64_t rows_per_block = (s.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
+        if (rows_per_block < 64) rows_per_block = 64;
+        int grid = (int)((s.N + rows_per_block - 1) / rows_per_block);
+        RGCN_LAUNCH(k_colsum, grid, 256, (size_t)s.O * sizeof(float), st, G, s.N, s.O, rows_per_block, gr->bias);
+    }
+
+    // ---- featureless: weight rows are the messages
+    if (p->featureless) {
+        FeaturelessGradArgs F{};
+        F.rowptr = g->s_rowptr; F.col = g->s_dst; F.rel = g->s_rel; F.val = g->s_val;
+        F.N = s.N; F.num_rels = (int)s.Rp; F.form = p->form; F.O = s.O; F.B = s.B; F.nb = s.nb; F.bi = s.bi; F.bo = s.bo;
+        F.comps = p->comps; F.bases = p->bases;
+        F.gW = gr->weights; F.gblocks = gr->blocks; F.gbases = gr->bases; F.gcomps = gr->comps;
+        if (p->form == RGCN_W_DENSE) {
+            if (!gr->weights) return RGCN_OK;
+            RGCN_CHECK_CUDA(cudaMemsetAsync(gr->weights, 0, (size_t)s.Rp * s.N * s.O * sizeof(float), st));
+        } else if (p->form == RGCN_W_BLOCK) {
+            if (!gr->blocks) return RGCN_OK;
+            RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        } else {
+            if (!gr->bases && !gr->comps) return RGCN_OK;
+            RGCN_REQUIRE(gr->bases && gr->comps, RGCN_ERR_ARG, "rgcn_backward: basis gradients come as a pair");
+            RGCN_CHECK_CUDA(cudaMemsetAsync(gr->comps, 0, (size_t)s.Rp * s.B * sizeof(float), st));
+        }
+        return launch_featureless_grad(F, G, st);
+    }
+
+    // ---- effective / transposed weights for the feature gradient
+    float* weff = nullptr;
+    if (p->form == RGCN_W_BASIS) {
+        weff = carve.take<float>((size_t)s.Rp * IO);
+        dim3 grid(grid_for(IO, 256), (unsigned)s.Rp);
+        RGCN_LAUNCH(k_basis_combine, grid, 256, 0, st, p->comps, p->bases, (int)s.Rp, s.B, IO, weff);
+    }
+    if (gr->features) {
+        PropArgs A{};
+        A.rowptr = g->s_rowptr; A.col = g->s_dst; A.rel = g->s_rel; A.val = g->s_val;
+        A.nrows = s.N; A.N = s.N;
+        fill_weights(A, p, s);
+        A.I = s.O; A.O = s.I; A.bi = s.bo; A.bo = s.bi;
+        A.in_mask = p->self_mask; A.out = gr->features;
+        if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
+            float* wt = carve.take<float>((size_t)s.Rp * IO);
+            rc = launch_transpose(p->form == RGCN_W_BASIS ? weff : p->weights, s.Rp, s.I, s.O, wt, st);
+            if (rc) return rc;
+            A.form = RGCN_W_DENSE; A.W = wt;
+        } else if (p->form == RGCN_W_BLOCK) {
+            float* bt = carve.take<float>(s.blocks_elems);
+            rc = launch_transpose(p->blocks, (int64_t)s.Rb * s.nb, s.bi, s.bo, bt, st);
+            if (rc) return rc;
+            A.blocks = bt;
+            if (p->blocks_self) {
+                float* stp = carve.take<float>((size_t)IO);
+                rc = launch_transpose(p->blocks_self, 1, s.I, s.O, stp, st);
+                if (rc) return rc;
+                A.blocks_self = stp;
+            }
+        }
+        rc = launch_prop(A, G, st);
+        if (rc) return rc;
+    } else if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
+        carve.take<float>((size_t)s.Rp * IO);            // keep the layout identical to the query
+    }
+
+    // ---- weight gradients
+    WGradArgs Wg{};
+    Wg.relptr = g->r_relptr; Wg.dst = g->r_dst; Wg.src = g->r_src; Wg.val = g->r_val;
+    Wg.form = p->form; Wg.I = s.I; Wg.O = s.O; Wg.nb = s.nb; Wg.bi = s.bi; Wg.bo = s.bo;
+    Wg.self_rel = p->blocks_self ? (int)s.Rp - 1 : -1; Wg.num_block_rels = s.Rb;
+    Wg.mask = p->self_mask; Wg.mask_rel = (int)s.Rp - 1;
+    bool want = false;
+    if (p->form == RGCN_W_DENSE) {
+        want = gr->weights != nullptr;
+        if (want) { RGCN_CHECK_CUDA(cudaMemsetAsync(gr->weights, 0, (size_t)s.Rp * IO * sizeof(float), st)); Wg.gW = gr->weights; }
+    } else if (p->form == RGCN_W_DIAG) {
+        want = gr->weights != nullptr;
+        if (want) { RGCN_CHECK_CUDA(cudaMemsetAsync(gr->weights, 0, (size_t)s.Rp * s.I * sizeof(float), st)); Wg.gW = gr->weights; }
+    } else if (p->form == RGCN_W_BLOCK) {
+        want = gr->blocks || gr->blocks_self;
+        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        if (gr->blocks_self) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks_self, 0, (size_t)IO * sizeof(float), st));
+        Wg.gblocks = gr->blocks; Wg.gself = gr->blocks_self;
+    } else {
+        want = gr->bases || gr->comps;
+        if (want) {
+            Wg.form = RGCN_W_DENSE;
+            Wg.gW = carve.take<float>((size_t)s.Rp * IO);
+            RGCN_CHECK_CUDA(cudaMemsetAsync(Wg.gW, 0, (size_t)s.Rp * IO * sizeof(float), st));
+        }
+    }
+    if (!want || s.nnz == 0) {
+        if (want && p->form == RGCN_W_BASIS) {
+            if (gr->comps) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->comps, 0, (size_t)s.Rp * s.B * sizeof(float), st));
+            if (gr->bases) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->bases, 0, (size_t)s.B * IO * sizeof(float), st));
+        }
+        return RGCN_OK;
+    }
+    if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
+    else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+    if (rc) return rc;
+    if (p->form == RGCN_W_BASIS) {
+        if (gr->comps) {
+            dim3 grid((unsigned)s.Rp, (unsigned)s.B);
+            RGCN_LAUNCH(k_basis_grad_comps, grid, 256, 0, st, Wg.gW, p->bases, s.B, IO, gr->comps);
+        }
+        if (gr->bases) {
+            dim3 grid(grid_for(IO, 256), (unsigned)s.B);
+            RGCN_LAUNCH(k_basis_grad_bases, grid, 256, 0, st, Wg.gW, p->comps, (int)s.Rp, s.B, IO, gr->bases);
+        }
+    }
+    return RGCN_OK;
+}

@@ -1,0 +1,63 @@
+"""GraphPlan: the sorted edge lists + per-edge weights the CUDA kernels walk.
+
+Replaces what the reference rebuilds on every forward — stack_matrices, sum_sparse, the
+'transpose trick' permutation and the sparse COO constructor (reference torch_rgcn/layers.py:255-279,
+:490-516) — with one device-side build.  torch is used only to own the device memory.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class GraphPlan:
+    """Device-resident plan for one edge list `triples_plus` (nnz, 3) int64.
+
+    norm: _lib.NORM_ROW (vertical stacking), _lib.NORM_COL_SWAPPED (horizontal stacking; needs the
+    reference's (n, i) = (n_general, n_self)) or _lib.NORM_EXPLICIT (caller-provided `val`).
+    """
+
+    def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True):
+        _lib.require_cuda(triples_plus)
+        assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
+        t = triples_plus.contiguous()
+        dev = t.device
+        nnz = int(t.size(0))
+        self.num_nodes, self.num_rels, self.nnz, self.device = int(num_nodes), int(num_rels), nnz, dev
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        n1 = max(nnz, 1)
+        self.d_rowptr = torch.empty(num_nodes + 1, **i32)
+        self.s_rowptr = torch.empty(num_nodes + 1, **i32)
+        self.r_relptr = torch.empty(num_rels + 1, **i32)
+        # one allocation each for the int and float edge arrays
+        self._ints = torch.empty(6, n1, **i32)
+        self._floats = torch.empty(4, n1, **f32)
+        self.d_src, self.d_rel, self.s_dst, self.s_rel, self.r_dst, self.r_src = self._ints.unbind(0)
+        self.d_val, self.s_val, self.r_val, self.val = self._floats.unbind(0)
+        self.status = torch.zeros(4, **i32)
+        g = _lib.Graph()
+        g.num_nodes, g.num_rels, g.nnz = num_nodes, num_rels, nnz
+        for name in ('d_rowptr', 'd_src', 'd_rel', 'd_val', 's_rowptr', 's_dst', 's_rel', 's_val',
+                     'r_relptr', 'r_dst', 'r_src', 'r_val', 'val', 'status'):
+            setattr(g, name, getattr(self, name).data_ptr())
+        self.c = g
+        if val is not None:
+            val = val.to(device=dev, dtype=torch.float32).contiguous()
+            assert val.numel() == nnz
+        ws_bytes = _lib.lib.rgcn_graph_workspace_bytes(nnz, num_nodes, num_rels)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.rgcn_graph_build(_lib.ptr(t), nnz, num_nodes, num_rels, norm, int(n_general),
+                                                 int(n_self), _lib.ptr(val), C.byref(g), _lib.ptr(ws), ws_bytes,
+                                                 _lib.stream_ptr()))
+        if validate:
+            bad = int(self.status[0].item())
+            # the reference asserts index bounds in stack_matrices (utils.py:163-164)
+            assert bad == 0, f'{bad} triples have a node or relation id out of range ' \
+                             f'(num_nodes={num_nodes}, num_relations={num_rels})'
+
+    def relation_counts(self):
+        """Edges per relation (host tensor), e.g. for the relation shard planner."""
+        return (self.r_relptr[1:] - self.r_relptr[:-1]).to(torch.int64).cpu()

@@ -1,0 +1,285 @@
+"""Drop-in RGCN layers backed by the B200 CUDA engine.
+
+`RelationalGraphConvolutionNC` / `RelationalGraphConvolutionLP` keep the constructor arguments, parameter
+names and shapes, initialisation order, `forward` signatures and error behaviour of the reference classes
+(torch_rgcn/layers.py:101-308 and :311-565) so that torch_rgcn/models.py and the experiment scripts can use
+them unchanged.  What changes is everything inside `forward`: the sparse-adjacency construction, degree
+normalisation, weight decomposition and message passing run as CUDA kernels behind `rgcn_propagate`.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import Module, Parameter
+
+from . import _lib
+from .functional import rgcn_propagate
+from .graph import GraphPlan
+from .utils import select_b_init, select_w_init, schlichtkrull_normal_
+
+
+def _unpack_decomposition(decomposition):
+    d = decomposition if decomposition is not None else {}
+    return d.get('type'), d.get('num_bases'), d.get('num_blocks')
+
+
+def _check_blocks(num_blocks, in_dim, out_dim):
+    assert num_blocks > 0, \
+        'Number of blocks should be set to a value higher than zero for block diagonal decomposition!'
+    assert in_dim % num_blocks == 0 and out_dim % num_blocks == 0, \
+        f'For block diagonal decomposition, input dimensions ({in_dim}, {out_dim}) must be divisible ' \
+        f'by number of blocks ({num_blocks})'
+
+
+class RelationalGraphConvolutionNC(Module):
+    """Relational graph convolution for node classification (graph fixed at construction).
+
+    Mirrors reference torch_rgcn/layers.py:101-308.  The graph plan (sorted CSR + per-edge weights) is
+    built once per device on first use and cached, instead of per forward.
+    """
+
+    def __init__(self, triples=None, num_nodes=None, num_relations=None, in_features=None, out_features=None,
+                 edge_dropout=None, edge_dropout_self_loop=None, bias=True, decomposition=None,
+                 vertical_stacking=False, diag_weight_matrix=False, reset_mode='glorot_uniform'):
+        super().__init__()
+        assert (triples is not None or num_nodes is not None or num_relations is not None or
+                out_features is not None), \
+            "The following must be specified: triples, number of nodes, number of relations and output dimension!"
+        in_dim = in_features if in_features is not None else num_nodes     # featureless: one-hot input
+        weight_decomp, num_bases, num_blocks = _unpack_decomposition(decomposition)
+
+        self.triples = triples
+        self.num_nodes = num_nodes
+        self.num_relations = num_relations
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight_decomp = weight_decomp
+        self.num_bases = num_bases
+        self.num_blocks = num_blocks
+        self.vertical_stacking = vertical_stacking
+        self.diag_weight_matrix = diag_weight_matrix
+        self.edge_dropout = edge_dropout                       # stored, never applied (as in the reference)
+        self.edge_dropout_self_loop = edge_dropout_self_loop
+
+        if diag_weight_matrix:
+            self.weights = Parameter(torch.empty((num_relations, in_features)), requires_grad=True)
+            self.out_features = in_features
+            self.weight_decomp = None
+            bias = False
+        elif weight_decomp is None:
+            self.weights = Parameter(torch.FloatTensor(num_relations, in_dim, out_features))
+        elif weight_decomp == 'basis':
+            assert num_bases > 0, 'Number of bases should be set to higher than zero for basis decomposition!'
+            self.bases = Parameter(torch.FloatTensor(num_bases, in_dim, out_features))
+            self.comps = Parameter(torch.FloatTensor(num_relations, num_bases))
+        elif weight_decomp == 'block':
+            _check_blocks(num_blocks, in_dim, out_features)
+            self.blocks = Parameter(torch.FloatTensor(num_relations, num_blocks, in_dim // num_blocks,
+                                                      out_features // num_blocks))
+        else:
+            raise NotImplementedError(f'{weight_decomp} decomposition has not been implemented')
+
+        if bias:
+            self.bias = Parameter(torch.FloatTensor(out_features))
+        else:
+            self.register_parameter('bias', None)
+
+        self._plan_cache = None
+        self.validate_triples = True
+        self.reset_parameters(reset_mode)
+
+    def _decomposed(self):
+        if self.weight_decomp == 'block':
+            return [self.blocks]
+        if self.weight_decomp == 'basis':
+            return [self.bases, self.comps]
+        return [self.weights]
+
+    def reset_parameters(self, reset_mode='glorot_uniform'):
+        """Same draws, in the same order, as reference layers.py:182-220."""
+        if reset_mode in ('glorot_uniform', 'schlichtkrull'):
+            gain = nn.init.calculate_gain('relu')
+            for p in self._decomposed():
+                nn.init.xavier_uniform_(p, gain=gain)
+            if self.bias is not None:
+                nn.init.zeros_(self.bias)
+        elif reset_mode == 'uniform':
+            stdv = 1.0 / math.sqrt(self.weights.size(1))       # AttributeError for decomposed layers, as upstream
+            for p in self._decomposed():
+                p.data.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.data.uniform_(-stdv, stdv)
+        else:
+            raise NotImplementedError(f'{reset_mode} parameter initialisation method has not been implemented')
+
+    # -- graph plan -------------------------------------------------------------------------------------
+    def _plan(self, device):
+        t = self.triples
+        key = (str(device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking)
+        if self._plan_cache is None or self._plan_cache[0] != key:
+            nnz = t.size(0)
+            n_general = int((nnz - self.num_nodes) / 2)          # reference layers.py:235
+            norm = _lib.NORM_ROW if self.vertical_stacking else _lib.NORM_COL_SWAPPED
+            plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
+                             validate=self.validate_triples)
+            self._plan_cache = (key, plan)
+        return self._plan_cache[1]
+
+    def set_plan(self, plan):
+        """Install an externally built plan (e.g. a relation shard, see parallel.py)."""
+        t = self.triples
+        key = (str(plan.device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking)
+        self._plan_cache = (key, plan)
+
+    def forward(self, features=None):
+        """One pass of message propagation: (num_nodes, out_features) fp32."""
+        assert (features is None) == (self.in_features is None), "in_features not provided!"
+        lead = self._decomposed()[0]
+        _lib.require_cuda(lead, features)
+        if self.in_features is None and self.vertical_stacking:
+            # the reference reaches torch.mm with mismatched shapes here (layers.py:286-288)
+            raise RuntimeError('featureless message passing requires horizontal stacking (vertical_stacking=False)')
+        if self.diag_weight_matrix and self.vertical_stacking:
+            raise RuntimeError('diagonal weight matrices require horizontal stacking (vertical_stacking=False)')
+        plan = self._plan(lead.device)
+        in_dim = self.in_features if self.in_features is not None else self.num_nodes
+        if self.diag_weight_matrix:
+            assert self.weights.size() == (self.num_relations, in_dim)
+            return rgcn_propagate(plan, 'diag', in_dim, self.out_features, features, weights=self.weights)
+        if self.weight_decomp is None:
+            assert self.weights.size() == (self.num_relations, in_dim, self.out_features)
+            return rgcn_propagate(plan, 'dense', in_dim, self.out_features, features, weights=self.weights,
+                                  bias=self.bias)
+        if self.weight_decomp == 'basis':
+            return rgcn_propagate(plan, 'basis', in_dim, self.out_features, features, bases=self.bases,
+                                  comps=self.comps, bias=self.bias)
+        if self.weight_decomp == 'block':
+            return rgcn_propagate(plan, 'block', in_dim, self.out_features, features, blocks=self.blocks,
+                                  bias=self.bias)
+        raise NotImplementedError(f'{self.weight_decomp} decomposition has not been implemented')
+
+
+class RelationalGraphConvolutionLP(Module):
+    """Relational graph convolution for link prediction (graph passed per forward).
+
+    Mirrors reference torch_rgcn/layers.py:311-565, including its edge list [T; inverse(T); T; self-loops]
+    (the original triples appear twice, utils.py:124), the bernoulli self-loop dropout and the
+    'schlichtkrull-dropout' mask on the dense self-relation of the block decomposition.
+    """
+
+    def __init__(self, num_nodes=None, num_relations=None, in_features=None, out_features=None, edge_dropout=None,
+                 edge_dropout_self_loop=None, decomposition=None, vertical_stacking=False, w_init='glorot-normal',
+                 w_gain=False, b_init=None):
+        super().__init__()
+        assert (num_nodes is not None or num_relations is not None or out_features is not None), \
+            "The following must be specified: number of nodes, number of relations and output dimension!"
+        device = 'cuda' if torch.cuda.is_available() else 'cpu'      # reference layers.py:334
+        in_dim = in_features if in_features is not None else num_nodes
+        weight_decomp, num_bases, num_blocks = _unpack_decomposition(decomposition)
+
+        self.num_nodes = num_nodes
+        self.num_relations = num_relations
+        self.in_features = in_dim
+        self.out_features = out_features
+        self.weight_decomp = weight_decomp
+        self.num_bases = num_bases
+        self.num_blocks = num_blocks
+        self.vertical_stacking = vertical_stacking
+        self.edge_dropout = edge_dropout
+        self.edge_dropout_self_loop = edge_dropout_self_loop
+        self.w_init = w_init
+        self.w_gain = w_gain
+        self.b_init = b_init
+
+        if weight_decomp is None:
+            self.weights = Parameter(torch.FloatTensor(num_relations, in_dim, out_features).to(device))
+        elif weight_decomp == 'basis':
+            assert num_bases > 0, 'Number of bases should be set to higher than zero for basis decomposition!'
+            self.bases = Parameter(torch.FloatTensor(num_bases, in_dim, out_features).to(device))
+            self.comps = Parameter(torch.FloatTensor(num_relations, num_bases).to(device))
+        elif weight_decomp == 'block':
+            _check_blocks(num_blocks, in_dim, out_features)
+            self.blocks = Parameter(torch.FloatTensor(num_relations - 1, num_blocks, in_dim // num_blocks,
+                                                      out_features // num_blocks).to(device))
+            self.blocks_self = Parameter(torch.FloatTensor(in_dim, out_features).to(device))
+        else:
+            raise NotImplementedError(f'{weight_decomp} decomposition has not been implemented')
+
+        if b_init:
+            self.bias = Parameter(torch.FloatTensor(out_features))
+        else:
+            self.register_parameter('bias', None)
+
+        self.validate_triples = True
+        self._test_keep = None        # tests inject RNG outcomes here (CPU and CUDA generators differ)
+        self._test_self_mask = None
+        self.initialise_weights()
+        if self.bias is not None:
+            self.initialise_biases()
+
+    def initialise_biases(self):
+        select_b_init(self.b_init)(self.bias)
+
+    def initialise_weights(self):
+        """Same draws as reference layers.py:405-447."""
+        gain = nn.init.calculate_gain('relu') if self.w_gain else 1.0
+        init = select_w_init(self.w_init)
+        if self.weight_decomp == 'block':
+            shape = [(self.num_relations - 1) // 2, self.in_features // self.num_blocks]
+            schlichtkrull_normal_(self.blocks, shape=shape, gain=gain)
+            schlichtkrull_normal_(self.blocks_self, shape=shape, gain=gain)
+        elif self.weight_decomp == 'basis':
+            init(self.bases, gain=gain)
+            init(self.comps, gain=gain)
+        else:
+            init(self.weights, gain=gain)
+
+    def forward(self, triples, features=None):
+        """One pass of message propagation over `triples` (E, 3): (num_nodes, out_features) fp32."""
+        assert (features is None) == (self.in_features is None), "in_features not given"
+        lead = self.blocks if self.weight_decomp == 'block' else (
+            self.bases if self.weight_decomp == 'basis' else self.weights)
+        _lib.require_cuda(lead)
+        device = lead.device
+        triples = triples.to(device)
+        features = features.to(device)
+        N, Rp = self.num_nodes, self.num_relations
+        R = int((Rp - 1) / 2)                                          # reference layers.py:460
+        if self.weight_decomp == 'block' and self.vertical_stacking:
+            # reference layers.py:527-528 concatenates a 3-D and a 2-D tensor here
+            raise RuntimeError('block decomposition in the LP layer requires horizontal stacking')
+
+        schlichtkrull = self.training and self.edge_dropout["self_loop_type"] == 'schlichtkrull-dropout'
+        keep_prob = 1 - self.edge_dropout["self_loop"] if (self.training and not schlichtkrull) else 1
+        with torch.no_grad():
+            # same RNG draw as generate_self_loops (reference utils.py:120-121), even when keep_prob == 1
+            keep = torch.bernoulli(torch.empty(size=(N,), dtype=torch.float, device=device).fill_(keep_prob))
+            if self._test_keep is not None:
+                keep = self._test_keep.to(device)
+            nodes = torch.arange(N, device=device)
+            if keep_prob != 1 or self._test_keep is not None:
+                nodes = nodes[keep.to(torch.bool)]
+            t = triples.to(torch.long).contiguous()
+            E, n_self = t.size(0), nodes.numel()
+            triples_plus = torch.empty(3 * E + n_self, 3, dtype=torch.long, device=device)
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib.rgcn_lp_triples_plus(_lib.ptr(t), E, R, _lib.ptr(nodes), n_self,
+                                                         _lib.ptr(triples_plus), _lib.stream_ptr()))
+            norm = _lib.NORM_ROW if self.vertical_stacking else _lib.NORM_COL_SWAPPED
+            plan = GraphPlan(triples_plus, N, Rp, norm, E, E + n_self, validate=self.validate_triples)
+
+        if self.weight_decomp is None:
+            return rgcn_propagate(plan, 'dense', self.in_features, self.out_features, features,
+                                  weights=self.weights, bias=self.bias)
+        if self.weight_decomp == 'basis':
+            return rgcn_propagate(plan, 'basis', self.in_features, self.out_features, features, bases=self.bases,
+                                  comps=self.comps, bias=self.bias)
+        self_mask = None
+        if schlichtkrull:
+            # same draw as F.dropout on the (1, N, O) self-loop messages (reference layers.py:544-546)
+            self_mask = nn.functional.dropout(torch.ones(1, N, self.out_features, device=device),
+                                              p=self.edge_dropout["self_loop"], training=True)[0]
+            if self._test_self_mask is not None:
+                self_mask = self._test_self_mask.to(device)
+        return rgcn_propagate(plan, 'block', self.in_features, self.out_features, features, blocks=self.blocks,
+                              blocks_self=self.blocks_self, bias=self.bias, self_mask=self_mask)
