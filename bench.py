@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — RGCN-layer edges/sec (forward+backward) on synthetic graphs of BASELINE.json's shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload am64|am16|aifb|mutag|wn18|syn] [--impl reference]
+
+A "step" is ONE layer call: forward + backward of the RGCN layer over every edge of `triples_plus`
+(metric = nnz / (t_fwd + t_bwd)).  The default workload is the AM-shaped block-diagonal
+bf16 layer (BASELINE.json configs[2]) — the shape the north-star target is quoted on; the graph plan of a
+node-classification layer is built once and is outside the timed region, as it is a construction-time cost
+in this engine (the reference rebuilds it every forward; its port below pays that inside its timed region).
+
+Our arm:   value = device-resident throughput (CUDA events, max over ranks); e2e = the same step through the
+           layer with HOST (pinned) buffers, H2D of features + upstream gradient and D2H of output + gradients
+           inside the timed region; roofline = forward gather kernel vs the measured HBM peak.
+Reference: `--impl reference` times oracle/torch_sparse_port.py (a CPU port of the reference's torch.sparse
+           algorithm; the pure-Python reference checkout does not travel to the GPU box) on a bounded,
+           uniformly scaled-down sample of the same workload, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: shape key, layer kind, in, out, decomposition, feature dtype, vertical, config label
+    'am64': dict(shape='am', kind='nc', in_f=64, out_f=64, decomp={'type': 'block', 'num_blocks': 4}, dtype='bf16',
+                 vertical=False, label='AM-shaped nc rgcn layer (1,666,764 nodes, 133 rels -> R\'=267, nnz=13,643,406), '
+                                       'block-diagonal nb=4, 64->64, bf16 features / fp32 accumulate'),
+    'am16': dict(shape='am', kind='nc', in_f=16, out_f=16, decomp={'type': 'block', 'num_blocks': 2}, dtype='f32',
+                 vertical=False, label='AM-shaped nc rgcn layer, block-diagonal nb=2, 16->16, fp32'),
+    'aifb': dict(shape='aifb', kind='nc', in_f=16, out_f=4, decomp=None, dtype='f32', vertical=True,
+                 label='AIFB-shaped nc rgcn layer 2 (8,285 nodes, R\'=91, nnz=66,371), no decomposition, 16->4, fp32'),
+    'mutag': dict(shape='mutag', kind='nc', in_f=16, out_f=2, decomp={'type': 'basis', 'num_bases': 30}, dtype='f32',
+                  vertical=True, label='MUTAG-shaped nc rgcn layer 2 (23,644 nodes, R\'=47), basis B=30, 16->2, fp32'),
+    'wn18': dict(shape='wn18', kind='lp', in_f=16, out_f=16, decomp=None, dtype='f32', vertical=False,
+                 label='WN18-shaped lp rgcn layer (40,943 nodes, R\'=37, 70,721 sampled triples -> nnz=253,106), '
+                       '16->16, fp32; graph build inside the step'),
+    'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
+                vertical=True, raw=True,
+                label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
+}
+
+
+def dist_info():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload construction
+# ------------------------------------------------------------------------------------------------------
+def build_triples(wl, device, scale=1.0, seed=0):
+    from torch_rgcn_b200.synthetic import SHAPES, random_triples
+    N, R, E = SHAPES[wl['shape']]
+    if scale != 1.0:
+        N, E = max(int(N * scale), 64), max(int(E * scale), 64)
+    if wl.get('raw'):                                # arbitrary triples over 2R relation ids, no inverse/self structure
+        t = random_triples(N, 2 * R, 2 * E, seed=seed, device=device)
+        return t, N, 2 * R, t.size(0)
+    if wl['kind'] == 'lp':
+        t = random_triples(N, R, E // 2, seed=seed, device=device)     # 50 % edge dropout of the train triples
+        return t, N, 2 * R + 1, 3 * t.size(0) + N
+    t = random_triples(N, R, E, seed=seed, device=device)
+    return t, N, 2 * R + 1, 2 * E + N
+
+
+def algorithmic_bytes(wl, N, Rp, nnz):
+    """forward B_f and backward B_b in bytes (int32 indices, fp32 output/gradients, explicit val)."""
+    I, O = wl['in_f'], wl['out_f']
+    bx = 2 if wl['dtype'] == 'bf16' else 4
+    d = wl['decomp'] or {}
+    if d.get('type') == 'block':
+        w = Rp * I * O // d['num_blocks']
+    elif d.get('type') == 'basis':
+        w = d['num_bases'] * I * O + Rp * d['num_bases']
+    else:
+        w = Rp * I * O
+    b_f = nnz * (I * bx + 12) + 4 * (N + 1) + N * O * 4 + w * 4
+    b_b = nnz * (O * 4 + 12) + nnz * (I * bx + 8) + N * O * 4 + N * I * 4 + 2 * w * 4
+    return b_f, b_b, I * bx + 12
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {'sm_mhz': busy[len(busy) // 2] if busy else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from torch_rgcn_b200 import _lib
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP
+    from torch_rgcn_b200.parallel import RelationShardedNC
+    from torch_rgcn_b200.utils import add_inverse_and_self
+
+    rank, world, local = dist_info()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    wl = WORKLOADS[args.workload]
+    t, N, Rp, nnz = build_triples(wl, dev)
+    xdt = torch.bfloat16 if wl['dtype'] == 'bf16' else torch.float32
+    I, O = wl['in_f'], wl['out_f']
+    torch.manual_seed(2)
+    t_build = None
+    if wl['kind'] == 'nc':
+        tp = t if wl.get('raw') else add_inverse_and_self(t, N, (Rp - 1) // 2, device=dev)
+        layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
+                                             decomposition=wl['decomp'], vertical_stacking=wl['vertical']).to(dev)
+        if world > 1:
+            layer = RelationShardedNC(layer)
+        call = lambda x: layer(x)                                            # noqa: E731
+    else:
+        layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
+                                             decomposition=wl['decomp'], vertical_stacking=wl['vertical'],
+                                             b_init='zeros').to(dev).eval()
+        layer.validate_triples = False          # no per-forward host sync (the reference's asserts do sync)
+        call = lambda x: layer(t, x)                                         # noqa: E731
+    gen = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn(N, I, device=dev, generator=gen).to(xdt)
+    G = torch.randn(N, O, device=dev, generator=gen)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # 256 MB > 126 MB L2
+
+    def step(x_in, g_in, ev=None):
+        x = x_in.detach().requires_grad_(True)
+        if ev:
+            ev[0].record()
+        out = call(x)
+        if ev:
+            ev[1].record()
+        out.backward(g_in)
+        if ev:
+            ev[2].record()
+        return out, x.grad
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(X, G)                                   # first call builds (and caches) the NC graph plan
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    for _ in range(max(args.warmup - 1, 0)):
+        flush.zero_()
+        step(X, G)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timed region: exactly K steps, per-step events so the L2 flush is not counted
+    sampler = ClockSampler(local)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    launches0 = _lib.lib.rgcn_launch_count()
+    for k in range(args.steps):
+        flush.zero_()
+        step(X, G, evs[k])
+    barrier()
+    launches = _lib.lib.rgcn_launch_count() - launches0
+    t_fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    t_bwd = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    tt = torch.tensor([t_fwd + t_bwd, t_fwd, t_bwd], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step, ms_fwd, ms_bwd = tt.tolist()
+
+    # ---- end to end: host (pinned) buffers in and out, copies inside the timed region
+    params = [p for p in layer.parameters()]
+    hX = X.cpu().pin_memory(); hG = G.cpu().pin_memory()
+    hOut = torch.empty(N, O, dtype=torch.float32).pin_memory()
+    hGX = torch.empty(N, I, dtype=xdt).pin_memory()
+    hGP = [torch.empty_like(p, device='cpu').pin_memory() for p in params]
+    h2d = hX.numel() * hX.element_size() + hG.numel() * hG.element_size()
+    d2h = hOut.numel() * 4 + hGX.numel() * hGX.element_size() + sum(h.numel() * 4 for h in hGP)
+
+    def e2e_step():
+        for p in params:
+            p.grad = None
+        out, gx = step(hX.to(dev, non_blocking=True), hG.to(dev, non_blocking=True))
+        hOut.copy_(out.detach(), non_blocking=True)
+        hGX.copy_(gx, non_blocking=True)
+        for h, p in zip(hGP, params):
+            if p.grad is not None:
+                h.copy_(p.grad, non_blocking=True)
+
+    e2e_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    te = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    ms_e2e = te.item()
+
+    b_f, b_b, per_edge = algorithmic_bytes(wl, N, Rp, nnz)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
+    # per-rank bytes: a relation shard gathers nnz/world edges but still writes the full (N, O) partial output
+    bf_rank = (b_f - N * O * 4) / world + N * O * 4
+    bb_rank = (b_b - N * O * 4 - N * I * 4) / world + N * O * 4 + N * I * 4
+    ach_f = bf_rank / (ms_fwd * 1e-3) / 1e9
+    ach_b = bb_rank / (ms_bwd * 1e-3) / 1e9
+    line = {
+        'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': nnz / (ms_step * 1e-3), 'unit': 'edges/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': wl['dtype'], 'data': 'synthetic',
+        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'num_relations': Rp, 'nnz': nnz,
+                   'l2': 'L2 flushed (256 MB write) between timed steps; flush outside the event pairs',
+                   'parallelism': f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)'
+                   if world > 1 else 'single GPU',
+                   'graph_plan': 'built once at first call (outside timed region)' if wl['kind'] == 'nc'
+                   else 'rebuilt every step (inside timed region)'},
+        'ms_fwd': ms_fwd, 'ms_bwd': ms_bwd, 'first_call_s_incl_plan_build': t_build,
+        'e2e': {'value': nnz / (ms_e2e * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'forward gather+transform (rgcn_forward)', 'bound': 'hbm', 'achieved': ach_f,
+                     'peak': peak, 'unit': 'GB/s', 'frac': ach_f / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': bf_rank, 'bytes_per_edge': per_edge},
+        'roofline_bwd': {'kernel': 'backward (feature-gradient gather + weight-gradient walk + bias)', 'bound': 'hbm',
+                         'achieved': ach_b, 'peak': peak, 'unit': 'GB/s', 'frac': ach_b / peak,
+                         'algorithmic_bytes_per_step': bb_rank},
+        'clocks': clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_reference(args, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: CPU port of the reference's torch.sparse algorithm on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
+    from oracle import torch_sparse_port as port
+    from oracle import rgcn_oracle as orc
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from torch_rgcn_b200.synthetic import SHAPES
+    N0, R0, E0 = SHAPES[wl['shape']]
+    Rp = 2 * R0 if wl.get('raw') else 2 * R0 + 1
+    # the reference materialises dense (R', N, d) fp32 temporaries; bound the largest to ~1 GB
+    cap = 1e9 / (Rp * max(wl['in_f'], wl['out_f']) * 4)
+    scale = min(1.0, cap / N0)
+    t, N, Rp, nnz = build_triples(wl, 'cpu', scale=scale)
+    I, O = wl['in_f'], wl['out_f']
+    torch.manual_seed(2)
+    d = wl['decomp'] or {}
+    params = {}
+    if d.get('type') == 'block':
+        nb = d['num_blocks']
+        params['blocks'] = torch.randn(Rp - (1 if wl['kind'] == 'lp' else 0), nb, I // nb, O // nb)
+        if wl['kind'] == 'lp':
+            params['blocks_self'] = torch.randn(I, O)
+    elif d.get('type') == 'basis':
+        params['bases'] = torch.randn(d['num_bases'], I, O)
+        params['comps'] = torch.randn(Rp, d['num_bases'])
+    else:
+        params['weights'] = torch.randn(Rp, I, O)
+    params['bias'] = torch.zeros(O)
+    for p in params.values():
+        p.requires_grad_(True)
+    X = torch.randn(N, I)
+    G = torch.randn(N, O)
+    if wl['kind'] == 'nc':
+        tp = t if wl.get('raw') else torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, (Rp - 1) // 2))
+        fwd = lambda x: port.nc_forward(tp, N, Rp, params, x, wl['vertical'])        # noqa: E731
+    else:
+        fwd = lambda x: port.lp_forward(t, N, Rp, params, x, wl['vertical'])         # noqa: E731
+
+    def one():
+        x = X.clone().requires_grad_(True)
+        a = time.perf_counter()
+        out = fwd(x)
+        b = time.perf_counter()
+        out.backward(G)
+        c = time.perf_counter()
+        for p in params.values():
+            p.grad = None
+        return b - a, c - b
+
+    times = []
+    for _ in range(warmup):
+        one()
+    n = steps if steps is not None else 3
+    start = time.perf_counter()
+    for k in range(n):
+        times.append(one())
+        if steps is None and time.perf_counter() - start > budget_s:
+            break
+    tf = sum(a for a, _ in times) / len(times)
+    tb = sum(b for _, b in times) / len(times)
+    return {'value': nnz / (tf + tb), 'unit': 'edges/s', 'cores': cores, 'torch_threads': torch.get_num_threads(),
+            'kind': 'port', 's_fwd': tf, 's_bwd': tb, 'steps': len(times),
+            'sample': f'oracle/torch_sparse_port.py (op-for-op CPU port of the reference torch.sparse path) on a '
+                      f'uniformly scaled graph: scale={scale:.4f}, N={N}, R\'={Rp}, nnz={nnz}, {I}->{O}, fp32; '
+                      f'per-edge rate is scale-invariant because the reference cost is O(R\'*N*d) with N/nnz fixed'}
+
+
+def run_reference(args):
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    base = cpu_reference(args, steps=args.steps, warmup=args.warmup)
+    ms = (base['s_fwd'] + base['s_bwd']) * 1e3
+    line = {'impl': 'reference', 'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': base['value'], 'unit': 'edges/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['label'], 'name': args.workload},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='am64', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget', type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -86,3 +86,33 @@ def test_oracle_matches_reference_lp(name):
     out, og = orc.lp_layer(d['triples'], meta['N'], meta['num_relations'], params, d['features'],
                            meta['vertical'], d['G'], keep=d.get('keep'), self_mask=d.get('self_mask'))
     _check(meta, d, params, grads, out, og)
+
+
+# ---- the torch CPU port that bench.py times as the reference's CPU path ---------------------------------
+def _port_check(name, fwd):
+    import torch
+    meta, d, params, grads = load_golden(name)
+    tp = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    feats = torch.tensor(d['features'], requires_grad=True) if 'features' in d else None
+    out = fwd(meta, d, tp, feats)
+    out.backward(torch.tensor(d['G']))
+    np.testing.assert_allclose(out.detach().numpy(), d['out'], atol=1e-5, rtol=1e-5)
+    for k, g in grads.items():
+        got = feats.grad if k == 'features' else tp[k].grad
+        np.testing.assert_allclose(got.numpy(), g, atol=1e-5, rtol=1e-4, err_msg=k)
+
+
+@pytest.mark.parametrize('name', golden_names('nc_'))
+def test_port_matches_reference_nc(name):
+    import torch
+    from oracle import torch_sparse_port as port
+    _port_check(name, lambda meta, d, p, x: port.nc_forward(torch.tensor(d['triples_plus']), meta['N'],
+                                                            meta['num_relations'], p, x, meta['vertical']))
+
+
+@pytest.mark.parametrize('name', [n for n in golden_names('lp_') if 'train' not in n])
+def test_port_matches_reference_lp(name):
+    import torch
+    from oracle import torch_sparse_port as port
+    _port_check(name, lambda meta, d, p, x: port.lp_forward(torch.tensor(d['triples']), meta['N'],
+                                                            meta['num_relations'], p, x, meta['vertical']))

@@ -39,7 +39,7 @@ def _params_struct(form, featureless, in_dim, out_dim, weights, bases, comps, bl
 class _Propagate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, form, in_dim, out_dim, features, weights, bases, comps, blocks, blocks_self, bias,
-                self_mask):
+                self_mask, add_bias=True):
         featureless = features is None
         tensors = [_f32c(t) for t in (weights, bases, comps, blocks, blocks_self, bias, self_mask)]
         weights, bases, comps, blocks, blocks_self, bias, self_mask = tensors
@@ -51,8 +51,9 @@ class _Propagate(torch.autograd.Function):
                 f'features must be ({plan.num_nodes}, {in_dim}), got {tuple(features.shape)}'
         _lib.require_cuda(features, *tensors)
         dev = plan.device
-        p = _params_struct(form, featureless, in_dim, out_dim, weights, bases, comps, blocks, blocks_self, bias,
-                           self_mask)
+        # add_bias=False: the bias takes part in autograd but another relation shard adds it (parallel.py)
+        p = _params_struct(form, featureless, in_dim, out_dim, weights, bases, comps, blocks, blocks_self,
+                           bias if add_bias else None, self_mask)
         out = torch.empty(plan.num_nodes, out_dim, dtype=torch.float32, device=dev)
         ws_bytes = _lib.lib.rgcn_forward_workspace_bytes(C.byref(plan.c), C.byref(p))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -100,11 +101,11 @@ class _Propagate(torch.autograd.Function):
         if g_feat is not None and features.dtype != torch.float32:
             g_feat = g_feat.to(features.dtype)
         return (None, None, None, None, g_feat, g_w, g_bases if need[6] else None, g_comps if need[7] else None,
-                g_blocks, g_self, g_bias, None)
+                g_blocks, g_self, g_bias, None, None)
 
 
 def rgcn_propagate(plan, form, in_dim, out_dim, features=None, weights=None, bases=None, comps=None, blocks=None,
                    blocks_self=None, bias=None, self_mask=None):
     """out (N, out_dim) fp32.  `features=None` means the featureless (one-hot input) layer."""
     return _Propagate.apply(plan, form, in_dim, out_dim, features, weights, bases, comps, blocks, blocks_self, bias,
-                            self_mask)
+                            self_mask, True)
