@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 1
+#define RGCN_ABI_VERSION 2
+#define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 
 typedef void* rgcn_stream_t;
 
@@ -120,6 +121,9 @@ typedef struct rgcn_graph {
     int32_t* r_dst;         /* nnz */
     int32_t* r_src;         /* nnz */
     float* r_val;           /* nnz */
+    int32_t* r_dslot;       /* nnz: position of relation-major edge k in the destination-major list */
+    int32_t* r_sslot;       /* nnz: position of relation-major edge k in the source-major list */
+    int32_t* r_chunkptr;    /* R'+1: relation p owns chunks [r_chunkptr[p], r_chunkptr[p+1]) of RGCN_CHUNK_EDGES edges */
     float* val;             /* nnz, in the caller's edge order: the reference's `vals` (layers.py:273) */
     int32_t* status;        /* 4 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164) */
 } rgcn_graph;
@@ -163,11 +167,11 @@ typedef struct rgcn_grads { /* NULL = gradient not wanted; buffers are overwritt
     float* bias;
 } rgcn_grads;
 
-size_t rgcn_forward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params);
+size_t rgcn_forward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params, int feature_dtype);
 int rgcn_forward(const rgcn_graph* graph, const rgcn_params* params, const void* features, int feature_dtype,
                  float* out, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
-size_t rgcn_backward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params);
+size_t rgcn_backward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params, int feature_dtype);
 int rgcn_backward(const rgcn_graph* graph, const rgcn_params* params, const void* features, int feature_dtype,
                   const float* grad_out, const rgcn_grads* grads, void* workspace, size_t workspace_bytes,
                   rgcn_stream_t stream);

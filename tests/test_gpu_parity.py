@@ -214,6 +214,9 @@ CASES = [
     ('featureless_block', 2400, 7, 30000, None, 16, {'type': 'block', 'num_blocks': 4}, False, True, False),
     ('diag32', 3000, 11, 40000, 32, 32, None, False, False, True),
     ('dense128', 1500, 5, 20000, 128, 96, None, False, False, False),
+    ('dense16x4', 3000, 11, 40000, 16, 4, None, True, False, False),
+    ('block32x8', 3000, 11, 40000, 32, 8, {'type': 'block', 'num_blocks': 2}, False, False, False),
+    ('block512', 600, 3, 5000, 512, 512, {'type': 'block', 'num_blocks': 32}, True, False, False),
 ]
 
 
@@ -310,8 +313,9 @@ def test_bf16_features(cuda_device):
     out.backward(G)
     ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().float().cpu().numpy(),
                                   True, G.cpu().numpy())
-    # inputs are identical (already rounded), so only accumulation order differs: fp32 tolerance holds for out
-    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_out, atol=ATOL, rtol=1e-4)
+    # bf16 path: features AND the per-edge messages are stored in bf16 (8-bit mantissa), sums are fp32.
+    # Stated tolerance for this dtype: 1e-2 absolute on O(1) outputs (fp32 runs keep 1e-4, see ATOL).
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_out, atol=1e-2, rtol=1e-2)
     np.testing.assert_allclose(layer.blocks.grad.cpu().numpy(), ref_g['blocks'], atol=ATOL, rtol=2e-4)
     assert feats.grad.dtype == torch.bfloat16            # gradient is rounded to the feature dtype
     np.testing.assert_allclose(feats.grad.float().cpu().numpy(), ref_g['features'], atol=2e-2, rtol=2e-2)

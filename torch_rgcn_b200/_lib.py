@@ -25,6 +25,7 @@ class Graph(C.Structure):
                 ('d_rowptr', _p), ('d_src', _p), ('d_rel', _p), ('d_val', _p),
                 ('s_rowptr', _p), ('s_dst', _p), ('s_rel', _p), ('s_val', _p),
                 ('r_relptr', _p), ('r_dst', _p), ('r_src', _p), ('r_val', _p),
+                ('r_dslot', _p), ('r_sslot', _p), ('r_chunkptr', _p),
                 ('val', _p), ('status', _p)]
 
 
@@ -71,9 +72,9 @@ def _load():
         'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64]),
         'rgcn_graph_build': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _i64, _i64, _p, C.POINTER(Graph), _p,
                                        C.c_size_t, _p]),
-        'rgcn_forward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params)]),
+        'rgcn_forward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params), C.c_int]),
         'rgcn_forward': (C.c_int, [C.POINTER(Graph), C.POINTER(Params), _p, C.c_int, _p, _p, C.c_size_t, _p]),
-        'rgcn_backward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params)]),
+        'rgcn_backward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params), C.c_int]),
         'rgcn_backward': (C.c_int, [C.POINTER(Graph), C.POINTER(Params), _p, C.c_int, _p, C.POINTER(Grads), _p,
                                     C.c_size_t, _p]),
         'rgcn_shard_plan': (C.c_int, [_p, _i64, C.c_int32, _p]),

@@ -197,6 +197,33 @@ __global__ void k_edge_values(int64_t nnz, const int32_t* __restrict__ cnt, int 
     val[e] = __fdiv_rn(1.0f, (float)cnt[src]);
 }
 
+// inv[perm[e]] = e : position of every caller-order edge in the sorted list
+__global__ void k_invert_perm(int64_t nnz, const int32_t* __restrict__ perm, int32_t* __restrict__ inv) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < nnz) inv[perm[e]] = (int32_t)e;
+}
+
+__global__ void k_gather_slots(int64_t nnz, const int32_t* __restrict__ perm, const int32_t* __restrict__ inv_d,
+                               const int32_t* __restrict__ inv_s, int32_t* __restrict__ dslot,
+                               int32_t* __restrict__ sslot) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int32_t o = perm[e];
+    dslot[e] = inv_d[o];
+    sslot[e] = inv_s[o];
+}
+
+// chunkptr[p] = number of RGCN_CHUNK_EDGES-sized chunks of relations < p (R' is small: one thread scans)
+__global__ void k_chunkptr(const int32_t* __restrict__ relptr, int64_t Rp, int32_t* __restrict__ chunkptr) {
+    if (blockIdx.x || threadIdx.x) return;
+    int32_t acc = 0;
+    for (int64_t p = 0; p < Rp; ++p) {
+        chunkptr[p] = acc;
+        acc += (relptr[p + 1] - relptr[p] + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
+    }
+    chunkptr[Rp] = acc;
+}
+
 __global__ void k_gather_val(int64_t nnz, const int32_t* __restrict__ perm, const float* __restrict__ val,
                              float* __restrict__ out) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -211,7 +238,7 @@ int bits_for(unsigned __int128 maxkey) {
 
 struct BuildWs {
     uint64_t *k0, *k1;
-    int32_t *i0, *i1, *flag, *segid, *starts, *ends, *cnt;
+    int32_t *i0, *i1, *flag, *segid, *starts, *ends, *cnt, *inv_d, *inv_s;
     void* cub;
     size_t cub_bytes;
     size_t total;
@@ -230,6 +257,7 @@ BuildWs carve_build(void* ws, int64_t nnz) {
     b.flag = c.take<int32_t>(n); b.segid = c.take<int32_t>(n);
     b.starts = c.take<int32_t>(n); b.ends = c.take<int32_t>(n);
     b.cnt = c.take<int32_t>(n);
+    b.inv_d = c.take<int32_t>(n); b.inv_s = c.take<int32_t>(n);
     b.cub_bytes = align_up(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
     b.cub = c.take<char>(b.cub_bytes);
     b.total = c.off;
@@ -328,10 +356,11 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
                      "rgcn_graph_build: horizontal permutation needs 2n+i == nnz (n=%lld i=%lld nnz=%lld)",
                      (long long)n_general, (long long)n_self, (long long)nnz);
     if (norm == RGCN_NORM_EXPLICIT) RGCN_REQUIRE(val_in || nnz == 0, RGCN_ERR_ARG, "rgcn_graph_build: val_in is NULL");
-    RGCN_REQUIRE(g->d_rowptr && g->s_rowptr && g->r_relptr && g->status, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
+    RGCN_REQUIRE(g->d_rowptr && g->s_rowptr && g->r_relptr && g->r_chunkptr && g->status, RGCN_ERR_ARG,
+                 "rgcn_graph_build: NULL plan array");
     if (nnz > 0)
         RGCN_REQUIRE(triples && g->d_src && g->d_rel && g->d_val && g->s_dst && g->s_rel && g->s_val && g->r_dst &&
-                         g->r_src && g->r_val && g->val, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
+                         g->r_src && g->r_val && g->r_dslot && g->r_sslot && g->val, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
     BuildWs b = carve_build(ws, nnz);
     RGCN_REQUIRE(ws_bytes >= b.total && (ws || b.total == 0), RGCN_ERR_WORKSPACE,
                  "rgcn_graph_build: workspace %zu < %zu bytes", ws_bytes, b.total);
@@ -341,6 +370,7 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->d_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->s_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->r_relptr, 0, (size_t)(Rp + 1) * sizeof(int32_t), stream));
+        RGCN_CHECK_CUDA(cudaMemsetAsync(g->r_chunkptr, 0, (size_t)(Rp + 1) * sizeof(int32_t), stream));
         return RGCN_OK;
     }
     const int grid = grid_for(nnz, kBlock);
@@ -374,6 +404,12 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             RGCN_LAUNCH(k_edge_values, grid, kBlock, 0, stream, nnz, b.cnt, norm, n_general, n_self, g->val);
         }
         RGCN_LAUNCH(k_gather_val, grid, kBlock, 0, stream, nnz, b.i1, g->val, oval);
+        if (ord == ORD_DST) RGCN_LAUNCH(k_invert_perm, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d);
+        else if (ord == ORD_SRC) RGCN_LAUNCH(k_invert_perm, grid, kBlock, 0, stream, nnz, b.i1, b.inv_s);
+        else {
+            RGCN_LAUNCH(k_gather_slots, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d, b.inv_s, g->r_dslot, g->r_sslot);
+            RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr);
+        }
     }
     return RGCN_OK;
 }

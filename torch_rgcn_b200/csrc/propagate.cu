@@ -41,11 +41,7 @@ int launch_prop_generic(const PropArgs& A, const XT* X, cudaStream_t st) {
 }
 
 template <typename XT>
-int launch_prop(const PropArgs& A, const XT* X, cudaStream_t st) {
-    int rc = try_launch_prop_fast(A, X, st);       // > 0: no fast path for this shape
-    if (rc <= 0) return rc;
-    return launch_prop_generic(A, X, st);
-}
+int launch_prop(const PropArgs& A, const XT* X, cudaStream_t st) { return launch_prop_generic(A, X, st); }
 
 template <typename XT>
 int launch_wgrad_generic(WGradArgs A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
@@ -74,8 +70,6 @@ int launch_wgrad_generic(WGradArgs A, const XT* X, const float* G, int64_t nnz, 
 
 template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
-    int rc = try_launch_wgrad_fast(A, X, G, nnz, Rp, st);
-    if (rc <= 0) return rc;
     return launch_wgrad_generic(A, X, G, nnz, Rp, st);
 }
 
@@ -165,13 +159,38 @@ void fill_weights(PropArgs& A, const rgcn_params* p, const Shape& s) {
     A.bias = nullptr; A.out_mask = nullptr; A.in_mask = nullptr; A.mask_rel = (int)s.Rp - 1;
 }
 
+// Relation-batched path (propagate_fast.cuh): featured, dense or pure block-diagonal weights with an
+// instantiated block shape, no dropout mask, and a message buffer that stays within kMaxMsgBytes.
+constexpr size_t kMaxMsgBytes = (size_t)24 << 30;
+
+bool rel_path(const rgcn_params* p, const Shape& s, bool bf16, bool transposed, RelShape* rs, size_t* msg_bytes) {
+    if (p->featureless || p->self_mask || p->blocks_self || s.nnz == 0) return false;
+    if (p->form == RGCN_W_DIAG) return false;
+    int nb = 1, bi = s.I, bo = s.O;
+    if (p->form == RGCN_W_BLOCK) { nb = s.nb; bi = s.bi; bo = s.bo; }
+    if (transposed) { int t = bi; bi = bo; bo = t; }
+    if (!rel_shape_supported(nb, bi, bo, bf16)) return false;
+    const int ti = bi < 8 ? bi : 8, tj = bo < 8 ? bo : 8;
+    if (nb * (bi / ti) * (bo / tj) > 256) return false;
+    size_t bytes = (size_t)s.nnz * nb * bo * (bf16 ? 2 : 4);
+    if (bytes > kMaxMsgBytes) return false;
+    rs->nb = nb; rs->bi = bi; rs->bo = bo;
+    *msg_bytes = align_up(bytes);
+    return true;
+}
+
+int max_chunks(const Shape& s) { return (int)(s.nnz / RGCN_CHUNK_EDGES + s.Rp); }
+
 }  // namespace
 
-extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p) {
-    if (!g || !p) return 0;
-    if (p->form == RGCN_W_BASIS && !p->featureless)
-        return align_up((size_t)g->num_rels * p->in_dim * p->out_dim * sizeof(float));
-    return 0;
+extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p, int x_dtype) {
+    Shape s;
+    if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
+    size_t bytes = 0;
+    if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
+    RelShape rs; size_t msg = 0;
+    if (rel_path(p, s, x_dtype == RGCN_BF16, false, &rs, &msg)) bytes += msg;
+    return bytes;
 }
 
 extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const void* X, int x_dtype, float* out,
@@ -183,8 +202,9 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     RGCN_REQUIRE(out, RGCN_ERR_ARG, "rgcn_forward: out is NULL");
     RGCN_REQUIRE(p->featureless || X, RGCN_ERR_ARG, "rgcn_forward: features is NULL");
     RGCN_REQUIRE(x_dtype == RGCN_F32 || x_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_forward: unknown dtype %d", x_dtype);
-    size_t need = rgcn_forward_workspace_bytes(g, p);
+    size_t need = rgcn_forward_workspace_bytes(g, p, x_dtype);
     RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_forward: workspace %zu < %zu", ws_bytes, need);
+    Carver carve(ws);
 
     PropArgs A{};
     A.rowptr = g->d_rowptr; A.col = g->d_src; A.rel = g->d_rel; A.val = g->d_val;
@@ -192,29 +212,51 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     fill_weights(A, p, s);
     A.bias = p->bias; A.out_mask = p->self_mask; A.out = out;
     if (p->form == RGCN_W_BASIS && !p->featureless) {      // materialise the small (R', I, O) table only
-        float* weff = static_cast<float*>(ws);
+        float* weff = carve.take<float>(s.w_elems);
         int64_t IO = (int64_t)s.I * s.O;
         dim3 grid(grid_for(IO, 256), (unsigned)s.Rp);
         RGCN_LAUNCH(k_basis_combine, grid, 256, 0, st, p->comps, p->bases, (int)s.Rp, s.B, IO, weff);
         A.form = RGCN_W_DENSE; A.W = weff;
     }
-    if (x_dtype == RGCN_BF16 && !p->featureless) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
+    const bool bf16 = x_dtype == RGCN_BF16 && !p->featureless;
+    RelShape rs; size_t msg_bytes = 0;
+    if (rel_path(p, s, bf16, false, &rs, &msg_bytes)) {
+        RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, nullptr, g->r_dslot, g->r_val,
+                  A.form == RGCN_W_BLOCK ? A.blocks : A.W, rs.nb};
+        void* msg = carve.take<char>(msg_bytes);
+        if (bf16) {
+            rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const __nv_bfloat16*>(X),
+                                      static_cast<__nv_bfloat16*>(msg), max_chunks(s), st);
+            if (rc) return rc;
+            return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const __nv_bfloat16*>(msg), p->bias, out, st);
+        }
+        rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const float*>(X), static_cast<float*>(msg),
+                                  max_chunks(s), st);
+        if (rc) return rc;
+        return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const float*>(msg), p->bias, out, st);
+    }
+    if (bf16) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
     return launch_prop(A, static_cast<const float*>(X), st);
 }
 
-extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p) {
-    if (!g || !p || p->featureless) return 0;
-    size_t w = align_up((size_t)g->num_rels * p->in_dim * p->out_dim * sizeof(float));
+extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p, int x_dtype) {
+    (void)x_dtype;
+    Shape s;
+    if (check_common(g, p, &s, "rgcn_backward_workspace_bytes") || p->featureless) return 0;
+    size_t w = align_up(s.w_elems * sizeof(float));
+    size_t bytes = 0;
     switch (p->form) {
-        case RGCN_W_DENSE: return w;                       // W^T
-        case RGCN_W_BASIS: return 3 * w;                   // W_eff, W_eff^T, gW_eff
-        case RGCN_W_BLOCK: {
-            size_t nb = (size_t)p->num_blocks;
-            size_t blocks = align_up((size_t)p->num_block_rels * nb * (p->in_dim / nb) * (p->out_dim / nb) * sizeof(float));
-            return blocks + (p->blocks_self ? align_up((size_t)p->in_dim * p->out_dim * sizeof(float)) : 0);
-        }
-        default: return 0;
+        case RGCN_W_DENSE: bytes = w; break;                       // W^T
+        case RGCN_W_BASIS: bytes = 3 * w; break;                   // W_eff, W_eff^T, gW_eff
+        case RGCN_W_BLOCK:
+            bytes = align_up(s.blocks_elems * sizeof(float)) +
+                    (p->blocks_self ? align_up((size_t)s.I * s.O * sizeof(float)) : 0);
+            break;
+        default: break;
     }
+    RelShape rs; size_t msg = 0;
+    if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32)
+    return bytes;
 }
 
 extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const void* X, int x_dtype,
@@ -226,7 +268,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     RGCN_REQUIRE(G && gr, RGCN_ERR_ARG, "rgcn_backward: grad_out or grads is NULL");
     RGCN_REQUIRE(p->featureless || X, RGCN_ERR_ARG, "rgcn_backward: features is NULL");
     RGCN_REQUIRE(x_dtype == RGCN_F32 || x_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_backward: unknown dtype %d", x_dtype);
-    size_t need = rgcn_backward_workspace_bytes(g, p);
+    size_t need = rgcn_backward_workspace_bytes(g, p, x_dtype);
     RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_backward: workspace %zu < %zu", ws_bytes, need);
     Carver carve(ws);
     const int64_t IO = (int64_t)s.I * s.O;
@@ -292,7 +334,18 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
                 A.blocks_self = stp;
             }
         }
-        rc = launch_prop(A, G, st);
+        RelShape rs; size_t msg_bytes = 0;
+        if (rel_path(p, s, false, true, &rs, &msg_bytes)) {
+            // same two kernels as the forward: gather G[dst], transposed weights, slots in source-major order
+            RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, nullptr, g->r_sslot, g->r_val,
+                      A.form == RGCN_W_BLOCK ? A.blocks : A.W, rs.nb};
+            float* msg = reinterpret_cast<float*>(carve.take<char>(msg_bytes));
+            rc = launch_rel_transform(R, rs.bi, rs.bo, G, msg, max_chunks(s), st);
+            if (rc) return rc;
+            rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
+        } else {
+            rc = launch_prop(A, G, st);
+        }
         if (rc) return rc;
     } else if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
         carve.take<float>((size_t)s.Rp * IO);            // keep the layout identical to the query
@@ -331,8 +384,20 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         }
         return RGCN_OK;
     }
-    if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
-    else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+    RelShape ws_shape; size_t unused = 0;
+    if (rel_path(p, s, x_dtype == RGCN_BF16, false, &ws_shape, &unused)) {
+        RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, nullptr, g->r_val, nullptr, ws_shape.nb};
+        float* target = (p->form == RGCN_W_BLOCK) ? gr->blocks : Wg.gW;
+        if (x_dtype == RGCN_BF16)
+            rc = launch_rel_wgrad(R, ws_shape.bi, ws_shape.bo, static_cast<const __nv_bfloat16*>(X), G, target,
+                                  max_chunks(s), st);
+        else
+            rc = launch_rel_wgrad(R, ws_shape.bi, ws_shape.bo, static_cast<const float*>(X), G, target, max_chunks(s), st);
+    } else if (x_dtype == RGCN_BF16) {
+        rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
+    } else {
+        rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+    }
     if (rc) return rc;
     if (p->form == RGCN_W_BASIS) {
         if (gr->comps) {

@@ -1,21 +1,412 @@
-// Specialised propagation kernels for the aligned shapes the benchmark configs use.
-// Return convention of the try_* dispatchers: 0 = launched, < 0 = error, > 0 = no fast path (use generic).
+// Relation-batched propagation kernels for aligned block-diagonal / small dense weights.
+//
+// Why relation-major: with one (s, p) segment per edge (typical of sparse multi-relational graphs) a
+// destination-major walk has to fetch a different W_p for every edge, and that weight traffic (L1/L2),
+// not the feature gather, bounds the kernel.  Here edges are walked in relation order, so a CTA stages
+// W_p once per 1024-edge chunk and every weight element is reused across the whole chunk:
+//
+//   k_rel_transform : msg[slot(e)] = val_e * X[src_e] @ W_p        (gather rows, per-block FMA, scatter rows)
+//   k_row_sum       : out[row] = bias + sum of the row's messages  (slot order == row-major order, so this is
+//                                                                   a contiguous streaming segmented sum)
+//   k_rel_wgrad     : gW_p += sum_e val_e X[src_e]^T G[dst_e]      (cp.async-staged rows, 8x8 register tiles)
+//
+// The same two kernels serve the feature gradient: walk with (gather = dst, slot = source-major position),
+// transposed weights and the upstream gradient as the feature matrix.
+//
+// Return convention of the try_* dispatchers: 0 = launched, < 0 = error, > 0 = shape not served here.
 #pragma once
 #include "common.cuh"
 #include "propagate_generic.cuh"
 
 namespace rgcn {
 
-template <typename XT>
-int try_launch_prop_fast(const PropArgs& A, const XT* X, cudaStream_t st) {
-    (void)A; (void)X; (void)st;
-    return 1;
+struct RelArgs {
+    const int32_t* relptr; const int32_t* chunkptr; int num_rels;
+    const int32_t* gather;    // per edge: row of the feature matrix to read
+    const int32_t* other;     // per edge: the other endpoint (weight gradient only)
+    const int32_t* slot;      // per edge: message row to write
+    const float* val;
+    const float* W;           // per relation: nb contiguous (BI, BO) blocks
+    int nb;
+};
+
+__device__ __forceinline__ void chunk_lookup(const RelArgs& A, int c, int& p, int& e0, int& e1) {
+    int lo = 0, hi = A.num_rels;              // chunkptr[lo] <= c < chunkptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    p = lo;
+    e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+}
+
+// ---- vector row-slice loads / stores -----------------------------------------------------------------
+template <int n>
+__device__ __forceinline__ void load_slice(const float* __restrict__ p, float (&x)[n], float scale) {
+    static_assert(n % 4 == 0, "slice must be a multiple of 4 floats");
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p) + k);
+        x[4 * k] = v.x * scale; x[4 * k + 1] = v.y * scale; x[4 * k + 2] = v.z * scale; x[4 * k + 3] = v.w * scale;
+    }
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+}
+template <int n>
+__device__ __forceinline__ void load_slice(const __nv_bfloat16* __restrict__ p, float (&x)[n], float scale) {
+    static_assert(n % 4 == 0, "slice must be a multiple of 4 elements");
+    if constexpr (n % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < n / 8; ++k) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + k);
+            unpack_bf16x2(v.x, x[8 * k], x[8 * k + 1]); unpack_bf16x2(v.y, x[8 * k + 2], x[8 * k + 3]);
+            unpack_bf16x2(v.z, x[8 * k + 4], x[8 * k + 5]); unpack_bf16x2(v.w, x[8 * k + 6], x[8 * k + 7]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < n / 4; ++k) {
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + k);
+            unpack_bf16x2(v.x, x[4 * k], x[4 * k + 1]); unpack_bf16x2(v.y, x[4 * k + 2], x[4 * k + 3]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < n; ++k) x[k] *= scale;
+}
+template <int n>
+__device__ __forceinline__ void store_slice(float* __restrict__ p, const float (&y)[n]) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k)
+        reinterpret_cast<float4*>(p)[k] = make_float4(y[4 * k], y[4 * k + 1], y[4 * k + 2], y[4 * k + 3]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int n>
+__device__ __forceinline__ void store_slice(__nv_bfloat16* __restrict__ p, const float (&y)[n]) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k)
+        reinterpret_cast<uint2*>(p)[k] = make_uint2(pack_bf16x2(y[4 * k], y[4 * k + 1]), pack_bf16x2(y[4 * k + 2], y[4 * k + 3]));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// phase 1: one thread per (edge, block); W_p broadcast from shared memory
+// ------------------------------------------------------------------------------------------------------
+template <typename XT, typename MT, int BI, int BO, int EPT>
+__global__ void __launch_bounds__(256) k_rel_transform(RelArgs A, const XT* __restrict__ X, MT* __restrict__ msg) {
+    extern __shared__ float Ws[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int p, e0, e1;
+    chunk_lookup(A, c, p, e0, e1);
+    constexpr int WB = BI * BO + 4;            // padded block stride: blocks start 4 banks apart
+    const int nb = A.nb;
+    const float* wp = A.W + (size_t)p * nb * BI * BO;
+    for (int i = threadIdx.x; i < nb * BI * BO; i += blockDim.x) {
+        int b = i / (BI * BO);
+        Ws[b * WB + (i - b * BI * BO)] = wp[i];
+    }
+    __syncthreads();
+    const int groups = blockDim.x / nb;
+    const int blk = threadIdx.x % nb, grp = threadIdx.x / nb;
+    if (grp >= groups) return;
+    const size_t I = (size_t)nb * BI, O = (size_t)nb * BO;
+    const float* w = Ws + blk * WB;
+    for (int base = e0; base < e1; base += groups * EPT) {
+        float x[EPT][BI], y[EPT][BO];
+        int slot[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            const int e = base + u * groups + grp;
+            slot[u] = -1;
+            if (e < e1) {
+                slot[u] = A.slot[e];
+                load_slice<BI>(X + (size_t)A.gather[e] * I + blk * BI, x[u], A.val[e]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < BI; ++i) x[u][i] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < BO; ++j) y[u][j] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < BI; ++i) {
+#pragma unroll
+            for (int j4 = 0; j4 < BO / 4; ++j4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + i * BO + 4 * j4);
+#pragma unroll
+                for (int u = 0; u < EPT; ++u) {
+                    y[u][4 * j4] += x[u][i] * w4.x; y[u][4 * j4 + 1] += x[u][i] * w4.y;
+                    y[u][4 * j4 + 2] += x[u][i] * w4.z; y[u][4 * j4 + 3] += x[u][i] * w4.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EPT; ++u)
+            if (slot[u] >= 0) store_slice<BO>(msg + (size_t)slot[u] * O + blk * BO, y[u]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// phase 2: out[row, 4q..4q+3] = bias + sum_{e in row} msg[e, 4q..4q+3]   (thread per (row, 4 columns))
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    float4 r;
+    unpack_bf16x2(v.x, r.x, r.y); unpack_bf16x2(v.y, r.z, r.w);
+    return r;
+}
+
+template <typename MT>
+__global__ void __launch_bounds__(256) k_row_sum(const int32_t* __restrict__ rowptr, int64_t nrows, int O,
+                                                 const MT* __restrict__ msg, const float* __restrict__ bias,
+                                                 float* __restrict__ out) {
+    const int cg = O >> 2;
+    const int64_t total = nrows * cg;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / cg;
+        const int q = (int)(idx - row * cg);
+        const int e0 = rowptr[row], e1 = rowptr[row + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const MT* m = msg + (size_t)e0 * O + 4 * q;
+        int e = e0;
+        for (; e + 1 < e1; e += 2, m += 2 * (size_t)O) {
+            float4 a = load4(m), b = load4(m + O);
+            acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+        }
+        if (e < e1) {
+            float4 a = load4(m);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        if (bias) {
+            float4 b = load4(bias + 4 * q);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)row * O + 4 * q) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight gradient: rows of X and G staged through shared memory with cp.async (3-stage ring), then
+// TI x TJ register tiles of gW_p accumulated with FMAs; one atomic flush per chunk
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;                        // src-size 0 -> the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int n>
+__device__ __forceinline__ void lds_slice(const float* p, float (&x)[n]) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k) {
+        float4 v = reinterpret_cast<const float4*>(p)[k];
+        x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+    }
+}
+template <int n>
+__device__ __forceinline__ void lds_slice(const __nv_bfloat16* p, float (&x)[n]) {
+    if constexpr (n % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < n / 8; ++k) {
+            uint4 v = reinterpret_cast<const uint4*>(p)[k];
+            unpack_bf16x2(v.x, x[8 * k], x[8 * k + 1]); unpack_bf16x2(v.y, x[8 * k + 2], x[8 * k + 3]);
+            unpack_bf16x2(v.z, x[8 * k + 4], x[8 * k + 5]); unpack_bf16x2(v.w, x[8 * k + 6], x[8 * k + 7]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < n / 4; ++k) {
+            uint2 v = reinterpret_cast<const uint2*>(p)[k];
+            unpack_bf16x2(v.x, x[4 * k], x[4 * k + 1]); unpack_bf16x2(v.y, x[4 * k + 2], x[4 * k + 3]);
+        }
+    }
+}
+
+constexpr int kWgStages = 3;
+
+template <typename XT, int BI, int BO>
+__global__ void __launch_bounds__(256) k_rel_wgrad(RelArgs A, const XT* __restrict__ X, const float* __restrict__ G,
+                                                   float* __restrict__ gW, int TE) {
+    constexpr int TI = BI < 8 ? BI : 8, TJ = BO < 8 ? BO : 8;
+    constexpr int TPB = (BI / TI) * (BO / TJ);       // threads covering one (BI, BO) block
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int p, e0, e1;
+    chunk_lookup(A, c, p, e0, e1);
+    const int nb = A.nb;
+    const int I = nb * BI, O = nb * BO;
+    const int RX = I * (int)sizeof(XT), RG = O * 4;   // row bytes
+    const int NZ = nb * BI * BO;
+    // smem carve: indices of the whole chunk, then the stage ring
+    int32_t* s_src = reinterpret_cast<int32_t*>(smem_raw);
+    int32_t* s_dst = s_src + RGCN_CHUNK_EDGES;
+    float* s_val = reinterpret_cast<float*>(s_dst + RGCN_CHUNK_EDGES);
+    unsigned char* ring = reinterpret_cast<unsigned char*>(s_val + RGCN_CHUNK_EDGES);
+    const int stage_bytes = TE * (RX + RG);
+    const int n = e1 - e0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_src[i] = A.gather[e0 + i]; s_dst[i] = A.other[e0 + i]; s_val[i] = A.val[e0 + i];
+    }
+    __syncthreads();
+    const int ntiles = (n + TE - 1) / TE;
+    const int ops = (RX + RG) / 16;                   // 16-byte copies per edge
+    auto issue = [&](int tile) {
+        if (tile < ntiles) {
+            unsigned char* st = ring + (size_t)(tile % kWgStages) * stage_bytes;
+            for (int k = threadIdx.x; k < TE * ops; k += blockDim.x) {
+                const int t = k / ops, piece = k - t * ops, le = tile * TE + t;
+                const bool ok = le < n;
+                const int li = ok ? le : 0;
+                if (piece * 16 < RX)
+                    cp_async16(st + (size_t)t * RX + piece * 16,
+                               reinterpret_cast<const unsigned char*>(X) + (size_t)s_src[li] * RX + piece * 16, ok);
+                else
+                    cp_async16(st + (size_t)TE * RX + (size_t)t * RG + (piece * 16 - RX),
+                               reinterpret_cast<const unsigned char*>(G) + (size_t)s_dst[li] * RG + (piece * 16 - RX), ok);
+            }
+        }
+        cp_async_commit();
+    };
+    const int TC = nb * TPB;                          // threads covering the whole relation weight
+    const int sets = blockDim.x / TC;                 // split-K groups
+    const int set = threadIdx.x / TC, r = threadIdx.x % TC;
+    const int blk = r / TPB, q = r % TPB, ti = q / (BO / TJ), tj = q % (BO / TJ);
+    const bool active = set < sets;
+    float acc[TI][TJ];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
+
+    issue(0);
+    issue(1);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        issue(tile + 2);
+        cp_async_wait<2>();                           // tile's group has landed (two younger groups may be in flight)
+        __syncthreads();
+        const unsigned char* st = ring + (size_t)(tile % kWgStages) * stage_bytes;
+        if (active) {
+            for (int t = set; t < TE; t += sets) {
+                const int le = tile * TE + t;
+                if (le >= n) break;
+                float x[TI], g[TJ];
+                lds_slice<TI>(reinterpret_cast<const XT*>(st + (size_t)t * RX) + blk * BI + ti * TI, x);
+                lds_slice<TJ>(reinterpret_cast<const float*>(st + (size_t)TE * RX + (size_t)t * RG) + blk * BO + tj * TJ, g);
+                const float v = s_val[le];
+#pragma unroll
+                for (int i = 0; i < TI; ++i) {
+                    const float xv = x[i] * v;
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) acc[i][j] += xv * g[j];
+                }
+            }
+        }
+        __syncthreads();                              // everyone is done with this stage before it is refilled
+    }
+    cp_async_wait<0>();
+    // reduce the split-K partials through shared memory (reusing the ring), one set per round
+    float* red = reinterpret_cast<float*>(ring);
+    for (int s = 0; s < sets; ++s) {
+        if (active && set == s) {
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) {
+                    const int idx = blk * BI * BO + (ti * TI + i) * BO + tj * TJ + j;
+                    red[idx] = (s == 0) ? acc[i][j] : red[idx] + acc[i][j];
+                }
+        }
+        __syncthreads();
+    }
+    float* dst = gW + (size_t)p * NZ;
+    for (int i = threadIdx.x; i < NZ; i += blockDim.x) {
+        const float v = red[i];
+        if (v != 0.f) atomicAdd(dst + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------------
+struct RelShape { int nb, bi, bo; };
+
+// which (XT, BI, BO) the relation-batched kernels are instantiated for
+inline bool rel_shape_supported(int nb, int bi, int bo, bool bf16) {
+    if (nb < 1 || nb > 256) return false;
+    bool pair = (bi == 8 && bo == 8) || (bi == 16 && bo == 16) || (bi == 16 && bo == 4) || (bi == 4 && bo == 16);
+    if (!pair) return false;
+    if (bf16 && bi % 8 != 0) return false;
+    return true;
+}
+
+template <typename XT, typename MT, int BI, int BO>
+int launch_rel_transform_t(const RelArgs& A, const XT* X, MT* msg, int max_chunks, cudaStream_t st) {
+    constexpr int EPT = 2;
+    const size_t smem = (size_t)A.nb * (BI * BO + 4) * sizeof(float);
+    auto kern = k_rel_transform<XT, MT, BI, BO, EPT>;
+    if (smem > 48 * 1024) RGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RGCN_LAUNCH(kern, max_chunks, 256, smem, st, A, X, msg);
+    return RGCN_OK;
+}
+
+template <typename XT, typename MT>
+int launch_rel_transform(const RelArgs& A, int bi, int bo, const XT* X, MT* msg, int max_chunks, cudaStream_t st) {
+    if (bi == 8 && bo == 8) return launch_rel_transform_t<XT, MT, 8, 8>(A, X, msg, max_chunks, st);
+    if (bi == 16 && bo == 16) return launch_rel_transform_t<XT, MT, 16, 16>(A, X, msg, max_chunks, st);
+    if (bi == 16 && bo == 4) return launch_rel_transform_t<XT, MT, 16, 4>(A, X, msg, max_chunks, st);
+    if constexpr (sizeof(XT) == 4) {
+        if (bi == 4 && bo == 16) return launch_rel_transform_t<XT, MT, 4, 16>(A, X, msg, max_chunks, st);
+    }
+    set_error("relation-batched transform: unsupported block %dx%d", bi, bo);
+    return RGCN_ERR_UNSUPPORTED;
+}
+
+template <typename MT>
+int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
+                   cudaStream_t st) {
+    int64_t total = nrows * (O / 4);
+    int64_t want = (total + 255) / 256;
+    int grid = (int)(want < (int64_t)kNumSMs * 32 ? want : (int64_t)kNumSMs * 32);
+    if (grid < 1) grid = 1;
+    RGCN_LAUNCH(k_row_sum<MT>, grid, 256, 0, st, rowptr, nrows, O, msg, bias, out);
+    return RGCN_OK;
+}
+
+template <typename XT, int BI, int BO>
+int launch_rel_wgrad_t(const RelArgs& A, const XT* X, const float* G, float* gW, int max_chunks, cudaStream_t st) {
+    const int I = A.nb * BI, O = A.nb * BO;
+    const int row_bytes = I * (int)sizeof(XT) + O * 4;
+    int TE = (36 * 1024) / (kWgStages * row_bytes);       // ~36 KB of ring per CTA
+    TE = TE < 2 ? 2 : (TE > 64 ? 64 : TE);
+    size_t ring = (size_t)kWgStages * TE * row_bytes;
+    size_t red = (size_t)A.nb * BI * BO * sizeof(float);
+    if (ring < red) ring = red;
+    const size_t smem = 3 * RGCN_CHUNK_EDGES * sizeof(int32_t) + ring;
+    auto kern = k_rel_wgrad<XT, BI, BO>;
+    if (smem > 48 * 1024) RGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RGCN_LAUNCH(kern, max_chunks, 256, smem, st, A, X, G, gW, TE);
+    return RGCN_OK;
 }
 
 template <typename XT>
-int try_launch_wgrad_fast(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
-    (void)A; (void)X; (void)G; (void)nnz; (void)Rp; (void)st;
-    return 1;
+int launch_rel_wgrad(const RelArgs& A, int bi, int bo, const XT* X, const float* G, float* gW, int max_chunks,
+                     cudaStream_t st) {
+    if (bi == 8 && bo == 8) return launch_rel_wgrad_t<XT, 8, 8>(A, X, G, gW, max_chunks, st);
+    if (bi == 16 && bo == 16) return launch_rel_wgrad_t<XT, 16, 16>(A, X, G, gW, max_chunks, st);
+    if (bi == 16 && bo == 4) return launch_rel_wgrad_t<XT, 16, 4>(A, X, G, gW, max_chunks, st);
+    if constexpr (sizeof(XT) == 4) {
+        if (bi == 4 && bo == 16) return launch_rel_wgrad_t<XT, 4, 16>(A, X, G, gW, max_chunks, st);
+    }
+    set_error("relation-batched weight gradient: unsupported block %dx%d", bi, bo);
+    return RGCN_ERR_UNSUPPORTED;
 }
 
 }  // namespace rgcn

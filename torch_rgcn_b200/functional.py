@@ -55,9 +55,9 @@ class _Propagate(torch.autograd.Function):
         p = _params_struct(form, featureless, in_dim, out_dim, weights, bases, comps, blocks, blocks_self,
                            bias if add_bias else None, self_mask)
         out = torch.empty(plan.num_nodes, out_dim, dtype=torch.float32, device=dev)
-        ws_bytes = _lib.lib.rgcn_forward_workspace_bytes(C.byref(plan.c), C.byref(p))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         dt = _lib.BF16 if (features is not None and features.dtype == torch.bfloat16) else _lib.F32
+        ws_bytes = _lib.lib.rgcn_forward_workspace_bytes(C.byref(plan.c), C.byref(p), dt)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.rgcn_forward(C.byref(plan.c), C.byref(p), _lib.ptr(features), dt, _lib.ptr(out),
                                              _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
@@ -91,9 +91,9 @@ class _Propagate(torch.autograd.Function):
         for name, t in (('features', g_feat), ('weights', g_w), ('bases', g_bases), ('comps', g_comps),
                         ('blocks', g_blocks), ('blocks_self', g_self), ('bias', g_bias)):
             setattr(gr, name, t.data_ptr() if t is not None else None)
-        ws_bytes = _lib.lib.rgcn_backward_workspace_bytes(C.byref(plan.c), C.byref(p))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         dt = _lib.BF16 if (features is not None and features.dtype == torch.bfloat16) else _lib.F32
+        ws_bytes = _lib.lib.rgcn_backward_workspace_bytes(C.byref(plan.c), C.byref(p), dt)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.rgcn_backward(C.byref(plan.c), C.byref(p), _lib.ptr(features), dt,
                                               _lib.ptr(grad_out), C.byref(gr), _lib.ptr(ws), ws_bytes,

@@ -32,15 +32,17 @@ class GraphPlan:
         self.s_rowptr = torch.empty(num_nodes + 1, **i32)
         self.r_relptr = torch.empty(num_rels + 1, **i32)
         # one allocation each for the int and float edge arrays
-        self._ints = torch.empty(6, n1, **i32)
+        self._ints = torch.empty(8, n1, **i32)
         self._floats = torch.empty(4, n1, **f32)
-        self.d_src, self.d_rel, self.s_dst, self.s_rel, self.r_dst, self.r_src = self._ints.unbind(0)
+        (self.d_src, self.d_rel, self.s_dst, self.s_rel, self.r_dst, self.r_src, self.r_dslot,
+         self.r_sslot) = self._ints.unbind(0)
+        self.r_chunkptr = torch.empty(num_rels + 1, **i32)
         self.d_val, self.s_val, self.r_val, self.val = self._floats.unbind(0)
         self.status = torch.zeros(4, **i32)
         g = _lib.Graph()
         g.num_nodes, g.num_rels, g.nnz = num_nodes, num_rels, nnz
         for name in ('d_rowptr', 'd_src', 'd_rel', 'd_val', 's_rowptr', 's_dst', 's_rel', 's_val',
-                     'r_relptr', 'r_dst', 'r_src', 'r_val', 'val', 'status'):
+                     'r_relptr', 'r_dst', 'r_src', 'r_val', 'r_dslot', 'r_sslot', 'r_chunkptr', 'val', 'status'):
             setattr(g, name, getattr(self, name).data_ptr())
         self.c = g
         if val is not None:
