@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "propagate_generic.cuh"
 #include "propagate_fast.cuh"
+#include "propagate_mma.cuh"
 
 using namespace rgcn;
 
@@ -225,8 +226,12 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
                   A.form == RGCN_W_BLOCK ? A.blocks : A.W, rs.nb};
         void* msg = carve.take<char>(msg_bytes);
         if (bf16) {
-            rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const __nv_bfloat16*>(X),
-                                      static_cast<__nv_bfloat16*>(msg), max_chunks(s), st);
+            if (mma_shape_supported(rs.nb, rs.bi, rs.bo))
+                rc = launch_rel_mma_fwd(R, static_cast<const __nv_bfloat16*>(X), static_cast<__nv_bfloat16*>(msg),
+                                        max_chunks(s), st);
+            else
+                rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const __nv_bfloat16*>(X),
+                                          static_cast<__nv_bfloat16*>(msg), max_chunks(s), st);
             if (rc) return rc;
             return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const __nv_bfloat16*>(msg), p->bias, out, st);
         }
@@ -301,6 +306,21 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             RGCN_CHECK_CUDA(cudaMemsetAsync(gr->comps, 0, (size_t)s.Rp * s.B * sizeof(float), st));
         }
         return launch_featureless_grad(F, G, st);
+    }
+
+    // ---- bf16 features + 16x16 blocks: one fused tensor-core pass for feature and weight gradients
+    if (x_dtype == RGCN_BF16 && p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 &&
+        mma_shape_supported(s.nb, s.bi, s.bo) && (gr->features || gr->blocks) &&
+        align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes) {
+        RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
+        __nv_bfloat16* msg = nullptr;
+        if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
+        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), G, msg, gr->blocks, max_chunks(s), st);
+        if (rc) return rc;
+        if (gr->features)
+            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
+        return RGCN_OK;
     }
 
     // ---- effective / transposed weights for the feature gradient
