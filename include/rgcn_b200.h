@@ -31,8 +31,10 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 2
+#define RGCN_ABI_VERSION 3
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
+#define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
+#define RGCN_RING_DEPTH 3             /* message tiles kept in flight by the tiled kernels */
 
 typedef void* rgcn_stream_t;
 
@@ -102,6 +104,21 @@ int rgcn_block_diag(const float* blocks, int64_t num_rels, int64_t num_blocks, i
  * Replaces stack_matrices + sum_sparse + the COO constructor on every forward
  * (layers.py:255-279 / :490-516).  All arrays are caller-allocated device memory.
  * ---------------------------------------------------------------------------------------- */
+/* Optional super-tiling of the rows (destination rows for the forward, source rows for the backward) so that
+ * the per-edge messages of one tile fit an L2-resident ring.  Tile of row r = rowptr[r] / tile_edges.
+ * Edges are sorted by (tile, relation, row); "group" g = tile * R' + relation. */
+typedef struct rgcn_tiling {
+    int32_t* tilerow;       /* T+1: first row of every tile (tilerow[T] = N) */
+    int32_t* grpptr;        /* T*R'+1: edge range of every group */
+    int32_t* chunkptr;      /* T*R'+1: chunk range of every group (RGCN_CHUNK_EDGES edges per chunk) */
+    int32_t* row;           /* nnz: tile-side endpoint (forward: subject s, backward: object o) */
+    int32_t* col;           /* nnz: the other endpoint */
+    int32_t* slot;          /* nnz: position of the edge in the row-major CSR of the tile side */
+    float* val;             /* nnz */
+    int32_t* stepptr;       /* T+2: work-queue prefix: step j = chunks of tile j, then row blocks of tile j-1 */
+    int32_t* slotneed;      /* T: row blocks of the earlier tiles that share ring slot k % RGCN_RING_DEPTH */
+} rgcn_tiling;
+
 typedef struct rgcn_graph {
     int64_t num_nodes;
     int64_t num_rels;       /* R' = number of relation ids the layer sees */
@@ -125,16 +142,23 @@ typedef struct rgcn_graph {
     int32_t* r_sslot;       /* nnz: position of relation-major edge k in the source-major list */
     int32_t* r_chunkptr;    /* R'+1: relation p owns chunks [r_chunkptr[p], r_chunkptr[p+1]) of RGCN_CHUNK_EDGES edges */
     float* val;             /* nnz, in the caller's edge order: the reference's `vals` (layers.py:273) */
-    int32_t* status;        /* 4 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164) */
+    int32_t* status;        /* 4 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164),
+                               [1] / [2] = largest destination / source tile in edges, [3] = kernel watchdog flag */
+    int64_t tile_edges;     /* 0: no tiling (ft / bt unused) */
+    int64_t num_tiles;      /* T = (nnz - 1) / tile_edges + 1 (trailing tiles may be empty) */
+    int64_t tile_capacity;  /* host copy of max(status[1], status[2]), filled by the caller after the build */
+    rgcn_tiling ft;         /* forward tiling (destination rows) */
+    rgcn_tiling bt;         /* backward tiling (source rows) */
 } rgcn_graph;
 
-size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels);
+size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges);
 
 /* n_general / n_self are the (n, i) of the horizontal permutation: NC ((nnz-N)/2, N), LP (|T|, |T|+|self|).
  * val_in (nnz floats, caller order) is read only for RGCN_NORM_EXPLICIT. */
 int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t num_nodes, int64_t num_rels,
                      int norm, int64_t n_general, int64_t n_self, const float* val_in,
                      rgcn_graph* graph, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+/* graph->tile_edges > 0 asks rgcn_graph_build to also fill graph->ft / graph->bt (arrays caller-allocated). */
 
 /* ------------------------------------------------------------------------------------------
  * Propagation: out[s] = bias + sum_e val_e * T_{p_e}(X[o_e]) and its gradients.

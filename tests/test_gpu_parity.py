@@ -297,7 +297,8 @@ def test_lp_empty_graph_and_isolated_nodes(cuda_device):
 
 @pytest.mark.parametrize('width,nb', [(64, 4), (128, 8), (512, 32)])
 @pytest.mark.parametrize('grads', ['all', 'weights_only', 'features_only'])
-def test_bf16_features(cuda_device, width, nb, grads):
+@pytest.mark.parametrize('tile_mb', ['16', '0.5', '0'])      # one tile / many row super-tiles / untiled kernels
+def test_bf16_features(cuda_device, monkeypatch, width, nb, grads, tile_mb):
     """bf16 path (tensor-core kernels): features, per-edge messages and the MMA operands are bf16, all sums fp32.
 
     Compared with the fp64 oracle on the already-rounded features.  Stated tolerance for this dtype: 1e-2 of the
@@ -305,8 +306,9 @@ def test_bf16_features(cuda_device, width, nb, grads):
     """
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
     from torch_rgcn_b200.synthetic import random_triples
+    monkeypatch.setenv('RGCN_TILE_MB', tile_mb)
     N, R, E = 3000, 9, 40000
-    t = random_triples(N, R, E, seed=4, rel_dist='zipf')
+    t = random_triples(N, R, E, seed=4, rel_dist='zipf', node_skew=(tile_mb == '0.5'))
     tp = torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, R))
     torch.manual_seed(8)
     layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=width,
@@ -322,6 +324,11 @@ def test_bf16_features(cuda_device, width, nb, grads):
     assert out.dtype == torch.float32
     G = torch.randn_like(out)
     out.backward(G)
+    plan = layer._plan_cache[1]
+    assert (plan.tile_edges > 0) == (tile_mb != '0')
+    if tile_mb == '0.5':
+        assert plan.c.num_tiles > 4
+    assert plan.status.tolist()[3] == 0, 'tiled kernel watchdog fired'
     ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().float().cpu().numpy(),
                                   True, G.cpu().numpy())
 

@@ -20,13 +20,19 @@ _p = C.c_void_p
 _i64 = C.c_int64
 
 
+class Tiling(C.Structure):
+    _fields_ = [('tilerow', _p), ('grpptr', _p), ('chunkptr', _p), ('row', _p), ('col', _p), ('slot', _p),
+                ('val', _p), ('stepptr', _p), ('slotneed', _p)]
+
+
 class Graph(C.Structure):
     _fields_ = [('num_nodes', _i64), ('num_rels', _i64), ('nnz', _i64),
                 ('d_rowptr', _p), ('d_src', _p), ('d_rel', _p), ('d_val', _p),
                 ('s_rowptr', _p), ('s_dst', _p), ('s_rel', _p), ('s_val', _p),
                 ('r_relptr', _p), ('r_dst', _p), ('r_src', _p), ('r_val', _p),
                 ('r_dslot', _p), ('r_sslot', _p), ('r_chunkptr', _p),
-                ('val', _p), ('status', _p)]
+                ('val', _p), ('status', _p),
+                ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ft', Tiling), ('bt', Tiling)]
 
 
 class Params(C.Structure):
@@ -69,7 +75,7 @@ def _load():
         'rgcn_stack_matrices': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _p, _p, _p]),
         'rgcn_sum_sparse': (C.c_int, [_p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p]),
         'rgcn_block_diag': (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
-        'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64]),
+        'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64, _i64]),
         'rgcn_graph_build': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _i64, _i64, _p, C.POINTER(Graph), _p,
                                        C.c_size_t, _p]),
         'rgcn_forward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params), C.c_int]),

@@ -230,6 +230,92 @@ __global__ void k_gather_val(int64_t nnz, const int32_t* __restrict__ perm, cons
     if (e < nnz) out[e] = val[perm[e]];
 }
 
+
+// ---- super-tiling (L2-resident message ring) ----------------------------------------------------------
+// key = (tile * R' + p) * N + a,  a = tile-side endpoint, tile = rowptr[a] / tile_edges
+__global__ void k_make_tile_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
+                                 const int32_t* __restrict__ rowptr, int64_t tile_edges,
+                                 uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int64_t s = t[3 * e], p = t[3 * e + 1], o = t[3 * e + 2];
+    if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
+    const int64_t a = backward ? o : s;
+    const uint64_t tile = (uint64_t)(rowptr[a] / tile_edges);
+    keys[e] = (tile * Rp + p) * N + a;
+    idx[e] = (int32_t)e;
+}
+
+__global__ void k_decode_tiles(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
+                               const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
+                               int64_t ngroups, const int32_t* __restrict__ inv, const float* __restrict__ val,
+                               int32_t* __restrict__ grpptr, int32_t* __restrict__ row, int32_t* __restrict__ col,
+                               int32_t* __restrict__ slot, float* __restrict__ oval) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const uint64_t k = keys[e];
+    const int64_t grp = (int64_t)(k / N);
+    const int32_t orig = perm[e];
+    int64_t s = t[3 * (int64_t)orig], p = t[3 * (int64_t)orig + 1], o = t[3 * (int64_t)orig + 2];
+    if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
+    row[e] = (int32_t)(k % N);
+    col[e] = (int32_t)(backward ? s : o);
+    slot[e] = inv[orig];
+    oval[e] = val[orig];
+    const int64_t prev = e ? (int64_t)(keys[e - 1] / N) : -1;
+    for (int64_t g = prev + 1; g <= grp; ++g) grpptr[g] = (int32_t)e;
+    if (e == nnz - 1)
+        for (int64_t g = grp + 1; g <= ngroups; ++g) grpptr[g] = (int32_t)nnz;
+}
+
+// tilerow[k] = first row whose tile id is >= k; tilerow[T] = N
+__global__ void k_tile_rows(const int32_t* __restrict__ rowptr, int64_t N, int64_t tile_edges, int64_t T,
+                            int32_t* __restrict__ tilerow) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    auto tile_of = [&](int64_t x) { int64_t k = rowptr[x] / tile_edges; return k < T ? k : T - 1; };   // trailing empty rows
+    const int64_t tile = tile_of(r);
+    const int64_t prev = r ? tile_of(r - 1) : -1;
+    for (int64_t k = prev + 1; k <= tile; ++k) tilerow[k] = (int32_t)r;
+    if (r == N - 1)
+        for (int64_t k = tile + 1; k <= T; ++k) tilerow[k] = (int32_t)N;
+}
+
+__global__ void k_group_chunks(const int32_t* __restrict__ grpptr, int64_t ngroups, int32_t* __restrict__ cnt) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < ngroups) cnt[g] = (grpptr[g + 1] - grpptr[g] + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
+    else if (g == ngroups) cnt[g] = 0;
+}
+
+// per-tile capacity (atomicMax) and the work-queue prefix over steps: step j = chunks of tile j + row blocks of tile j-1
+__global__ void k_tile_steps(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tilerow,
+                             const int32_t* __restrict__ chunkptr, int64_t T, int64_t Rp,
+                             int32_t* __restrict__ stepcnt, int32_t* cap) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j > T + 1) return;
+    int32_t n = 0;
+    if (j < T) {
+        n += chunkptr[(j + 1) * Rp] - chunkptr[j * Rp];
+        atomicMax(cap, rowptr[tilerow[j + 1]] - rowptr[tilerow[j]]);
+    }
+    if (j >= 1 && j <= T) {
+        const int32_t rows = tilerow[j] - tilerow[j - 1];
+        n += (rows + RGCN_TILE_ROWS_PER_ITEM - 1) / RGCN_TILE_ROWS_PER_ITEM;
+    }
+    stepcnt[j] = (j <= T) ? n : 0;
+}
+
+// slotneed[k] = row blocks of all tiles k' < k with k' % depth == k % depth (one thread per ring slot)
+__global__ void k_slot_need(const int32_t* __restrict__ tilerow, int64_t T, int32_t* __restrict__ slotneed) {
+    const int s = threadIdx.x;
+    if (blockIdx.x || s >= RGCN_RING_DEPTH) return;
+    int32_t acc = 0;
+    for (int64_t k = s; k < T; k += RGCN_RING_DEPTH) {
+        slotneed[k] = acc;
+        acc += (tilerow[k + 1] - tilerow[k] + RGCN_TILE_ROWS_PER_ITEM - 1) / RGCN_TILE_ROWS_PER_ITEM;
+    }
+}
+
 int bits_for(unsigned __int128 maxkey) {
     int b = 1;
     while (b < 64 && (maxkey >> b) != 0) ++b;
@@ -244,9 +330,10 @@ struct BuildWs {
     size_t total;
 };
 
-BuildWs carve_build(void* ws, int64_t nnz) {
+BuildWs carve_build(void* ws, int64_t nnz, int64_t ngroups = 0) {
     BuildWs b;
     size_t n = (size_t)(nnz > 0 ? nnz : 1);
+    if ((size_t)ngroups + 2 > n) n = (size_t)ngroups + 2;     // the scans over groups reuse the int scratch arrays
     size_t sort_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)n);
@@ -332,9 +419,14 @@ extern "C" int rgcn_block_diag(const float* blocks, int64_t R, int64_t nb, int64
     return RGCN_OK;
 }
 
-extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp) {
-    (void)N; (void)Rp;
-    return carve_build(nullptr, nnz).total;
+static int64_t tile_groups(int64_t nnz, int64_t Rp, int64_t tile_edges) {
+    if (tile_edges <= 0 || nnz <= 0) return 0;
+    return ((nnz - 1) / tile_edges + 1) * Rp;
+}
+
+extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges) {
+    (void)N;
+    return carve_build(nullptr, nnz, tile_groups(nnz, Rp, tile_edges)).total;
 }
 
 extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, int64_t Rp, int norm,
@@ -361,10 +453,12 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
     if (nnz > 0)
         RGCN_REQUIRE(triples && g->d_src && g->d_rel && g->d_val && g->s_dst && g->s_rel && g->s_val && g->r_dst &&
                          g->r_src && g->r_val && g->r_dslot && g->r_sslot && g->val, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
-    BuildWs b = carve_build(ws, nnz);
+    BuildWs b = carve_build(ws, nnz, tile_groups(nnz, Rp, g->tile_edges));
     RGCN_REQUIRE(ws_bytes >= b.total && (ws || b.total == 0), RGCN_ERR_WORKSPACE,
                  "rgcn_graph_build: workspace %zu < %zu bytes", ws_bytes, b.total);
     g->num_nodes = N; g->num_rels = Rp; g->nnz = nnz;
+    g->num_tiles = 0; g->tile_capacity = 0;
+    RGCN_REQUIRE(g->tile_edges >= 0, RGCN_ERR_ARG, "rgcn_graph_build: negative tile_edges");
     RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 4 * sizeof(int32_t), stream));
     if (nnz == 0) {
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->d_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
@@ -409,6 +503,37 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         else {
             RGCN_LAUNCH(k_gather_slots, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d, b.inv_s, g->r_dslot, g->r_sslot);
             RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr);
+        }
+    }
+    if (g->tile_edges > 0) {
+        const int64_t te = g->tile_edges;
+        const int64_t T = (nnz - 1) / te + 1;
+        const int64_t ngroups = T * Rp;
+        RGCN_REQUIRE(ngroups < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: too many (tile, relation) groups");
+        g->num_tiles = T;
+        const int tbits = bits_for((unsigned __int128)ngroups * (unsigned __int128)N);
+        RGCN_REQUIRE(tbits <= 63, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: tile key does not fit 64 bits");
+        for (int backward = 0; backward < 2; ++backward) {
+            rgcn_tiling& tl = backward ? g->bt : g->ft;
+            RGCN_REQUIRE(tl.tilerow && tl.grpptr && tl.chunkptr && tl.row && tl.col && tl.slot && tl.val && tl.stepptr && tl.slotneed,
+                         RGCN_ERR_ARG, "rgcn_graph_build: NULL tiling array");
+            const int32_t* rowptr = backward ? g->s_rowptr : g->d_rowptr;
+            RGCN_LAUNCH(k_make_tile_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, rowptr, te, b.k0, b.i0);
+            size_t cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, tbits, stream));
+            rgcn::g_launches.fetch_add((tbits + 7) / 8 + 1, std::memory_order_relaxed);
+            RGCN_LAUNCH(k_decode_tiles, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, ngroups,
+                        backward ? b.inv_s : b.inv_d, g->val, tl.grpptr, tl.row, tl.col, tl.slot, tl.val);
+            RGCN_LAUNCH(k_tile_rows, grid_for(N, kBlock), kBlock, 0, stream, rowptr, N, te, T, tl.tilerow);
+            RGCN_LAUNCH(k_slot_need, 1, 32, 0, stream, tl.tilerow, T, tl.slotneed);
+            RGCN_LAUNCH(k_group_chunks, grid_for(ngroups + 1, kBlock), kBlock, 0, stream, tl.grpptr, ngroups, b.flag);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.flag, tl.chunkptr, (int)(ngroups + 1), stream));
+            RGCN_LAUNCH(k_tile_steps, grid_for(T + 2, kBlock), kBlock, 0, stream, rowptr, tl.tilerow, tl.chunkptr, T, Rp,
+                        b.segid, g->status + 1 + backward);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.segid, tl.stepptr, (int)(T + 2), stream));
+            rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
         }
     }
     return RGCN_OK;

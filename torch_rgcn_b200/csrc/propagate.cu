@@ -180,6 +180,17 @@ bool rel_path(const rgcn_params* p, const Shape& s, bool bf16, bool transposed, 
     return true;
 }
 
+// Tiled tensor-core path: bf16 features, 16x16 blocks, and a plan built with tile_edges > 0.
+bool tiled_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool bf16) {
+    return bf16 && g->tile_edges > 0 && g->num_tiles > 0 && g->tile_capacity > 0 && !p->featureless &&
+           p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 &&
+           mma_shape_supported(s.nb, s.bi, s.bo);
+}
+
+size_t tiled_ring_bytes(const rgcn_graph* g, int width) {
+    return align_up((size_t)kRingDepth * (size_t)g->tile_capacity * width * 2);
+}
+
 int max_chunks(const Shape& s) { return (int)(s.nnz / RGCN_CHUNK_EDGES + s.Rp); }
 
 }  // namespace
@@ -189,6 +200,7 @@ extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_p
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
     size_t bytes = 0;
     if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O);
     RelShape rs; size_t msg = 0;
     if (rel_path(p, s, x_dtype == RGCN_BF16, false, &rs, &msg)) bytes += msg;
     return bytes;
@@ -220,6 +232,13 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         A.form = RGCN_W_DENSE; A.W = weff;
     }
     const bool bf16 = x_dtype == RGCN_BF16 && !p->featureless;
+    if (tiled_path(g, p, s, bf16)) {
+        int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
+        __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.O)));
+        RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
+        TiledArgs T = make_tiled_args(g, false, s.nb, p->blocks, p->bias, counters);
+        return launch_tiled_mma_fwd(T, static_cast<const __nv_bfloat16*>(X), ring, out, st);
+    }
     RelShape rs; size_t msg_bytes = 0;
     if (rel_path(p, s, bf16, false, &rs, &msg_bytes)) {
         RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, nullptr, g->r_dslot, g->r_val,
@@ -259,6 +278,7 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
             break;
         default: break;
     }
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I);
     RelShape rs; size_t msg = 0;
     if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32)
     return bytes;
@@ -306,6 +326,16 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             RGCN_CHECK_CUDA(cudaMemsetAsync(gr->comps, 0, (size_t)s.Rp * s.B * sizeof(float), st));
         }
         return launch_featureless_grad(F, G, st);
+    }
+
+    // ---- tiled variant of the fused pass: feature-gradient messages stay in an L2-resident ring
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16) && gr->features) {
+        int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
+        __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.I)));
+        RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
+        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        TiledArgs T = make_tiled_args(g, true, s.nb, p->blocks, nullptr, counters);
+        return launch_tiled_mma_bwd(T, static_cast<const __nv_bfloat16*>(X), G, ring, gr->features, gr->blocks, st);
     }
 
     // ---- bf16 features + 16x16 blocks: one fused tensor-core pass for feature and weight gradients

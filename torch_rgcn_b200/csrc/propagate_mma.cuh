@@ -1,16 +1,21 @@
 // Tensor-core relation-batched kernels for bf16 features and 16x16 weight blocks (AM / SYN shapes).
 //
-// A CTA owns one 1024-edge chunk of one relation.  Each warp keeps the bf16 fragments of "its" four 16x16
-// weight blocks in registers for the whole chunk and streams 16-edge tiles through a private 3-stage
-// cp.async ring: the 16 gathered feature-row slices (16 x 128 B) land in shared memory with a 16-byte XOR
-// swizzle, ldmatrix feeds them to mma.sync.m16n8k16 (bf16 x bf16 -> fp32), the result is scaled by the
-// per-edge weight, packed to bf16, bounced through the same tile buffer and written to the message rows
-// with coalesced 16-byte stores.  No CTA-wide barrier after the index prologue: warps are independent.
+// Work unit: one <=1024-edge chunk of one relation (or of one (tile, relation) group).  Each warp keeps the bf16
+// fragments of "its" four 16x16 weight blocks in registers for the whole chunk and streams 16-edge tiles through a
+// private 3-stage cp.async ring: the 16 gathered row slices (16 x 128 B) land in shared memory with a 16-byte XOR
+// swizzle, ldmatrix feeds them to mma.sync.m16n8k16 (bf16 x bf16 -> fp32), the result is scaled by the per-edge
+// weight, packed to bf16, bounced through the same tile buffer and written to the message rows with coalesced
+// 16-byte stores.  After the index prologue the warps of a CTA are independent (no CTA-wide barriers).
 //
-// Each block is a true dense 16x16 GEMM tile shared by all edges of the relation, which is the one place the
-// path is GEMM-shaped; everything else stays a gather/scatter.  mma.sync (HMMA) rather than tcgen05: the
-// tiles are 16 edges x 16 x 16, far below the 128-row UMMA atom, and the kernel is gather-bound, not
-// tensor-bound.
+// Two drivers use the chunk bodies:
+//   k_rel_mma_fwd / k_rel_mma_bwd      one CTA per chunk, messages go to an nnz-sized buffer in HBM
+//   k_tiled_mma_fwd / k_tiled_mma_bwd  persistent CTAs pull work from an in-order queue over row super-tiles:
+//                                      messages of a tile live in a small ring that stays in L2, and the row sums of
+//                                      tile k overlap the transform of tile k+1
+//
+// Each block is a true dense 16x16 GEMM tile shared by all edges of the relation, the one place the path is
+// GEMM-shaped.  mma.sync (HMMA) rather than tcgen05: tiles are 16 edges x 16 x 16, far below the 128-row UMMA atom,
+// and the kernels are gather-bound, not tensor-bound.
 #pragma once
 #include "common.cuh"
 #include "propagate_fast.cuh"
@@ -39,33 +44,40 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // byte offset of 16-byte chunk `chunk` of row `row` inside a swizzled 16 x 128 B tile
 __device__ __forceinline__ int tile_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-// msg[slot(e), bg*64 .. bg*64+63] = bf16( val_e * X[src_e, bg*64 ..] @ blockdiag(W_p[4bg .. 4bg+3]) )
-__global__ void __launch_bounds__(256) k_rel_mma_fwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
-                                                     __nv_bfloat16* __restrict__ msg) {
-    extern __shared__ __align__(128) unsigned char smem_mma[];
-    unsigned char* smem = smem_mma;
-    const int c = blockIdx.x;
-    if (c >= A.chunkptr[A.num_rels]) return;
-    int p, e0, e1;
-    chunk_lookup(A, c, p, e0, e1);
-    const int n = e1 - e0;
+// One chunk of edges of relation p, described by global index arrays already offset to the chunk's first edge.
+struct Chunk {
+    int p, n;                 // relation, edges in the chunk (<= RGCN_CHUNK_EDGES)
+    const int32_t* gather;    // rows of the bf16 matrix (X)
+    const int32_t* other;     // rows of the fp32 matrix (G), backward only
+    const int32_t* slot;      // message row ids
+    const float* val;
+    int slot_bias;            // subtracted from slot (first slot of the tile when messages go to a ring)
+};
+
+constexpr size_t kFwdSmemBytes = 3 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kMmaStages * kTileBytes;
+
+// msg[slot(e) - bias, bg*64 .. bg*64+63] = bf16( val_e * X[src_e, bg*64 ..] @ blockdiag(W_p[4bg .. 4bg+3]) )
+__device__ __forceinline__ void mma_fwd_chunk(const Chunk& C, const float* __restrict__ W, int nb,
+                                              const __nv_bfloat16* __restrict__ X, __nv_bfloat16* __restrict__ msg,
+                                              unsigned char* smem) {
+    const int n = C.n;
     int32_t* s_src = reinterpret_cast<int32_t*>(smem);
     int32_t* s_slot = s_src + RGCN_CHUNK_EDGES;
     float* s_val = reinterpret_cast<float*>(s_slot + RGCN_CHUNK_EDGES);
     unsigned char* rings = reinterpret_cast<unsigned char*>(s_val + RGCN_CHUNK_EDGES);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        s_src[i] = A.gather[e0 + i]; s_slot[i] = A.slot[e0 + i]; s_val[i] = A.val[e0 + i];
+        s_src[i] = C.gather[i]; s_slot[i] = C.slot[i] - C.slot_bias; s_val[i] = C.val[i];
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int NG = A.nb >> 2;                       // block groups of four 16x16 blocks (128 B of every row)
+    const int NG = nb >> 2;                         // block groups of four 16x16 blocks (128 B of every row)
     const int bg = warp % NG, wsub = warp / NG, nsub = 8 / NG;
-    const size_t row_bytes = (size_t)A.nb * 32;     // I == O == nb * 16 bf16
+    const size_t row_bytes = (size_t)nb * 32;       // I == O == nb * 16 bf16
 
     // weight fragments (col-major B operand): b0 = W[2t..2t+1][n], b1 = W[2t+8..2t+9][n], n = 8h + g
     uint32_t bfrag[4][2][2];
     {
-        const float* wp = A.W + ((size_t)p * A.nb + (size_t)bg * 4) * 256;
+        const float* wp = W + ((size_t)C.p * nb + (size_t)bg * 4) * 256;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -142,48 +154,43 @@ __global__ void __launch_bounds__(256) k_rel_mma_fwd(RelArgs A, const __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Fused backward for the same shapes.  One relation-major pass reads X[src] (bf16) and G[dst] (fp32) once and
-// produces BOTH
-//   msg'[sslot(e)] = bf16( (val_e G[dst_e]) @ blockdiag(W_p)^T )      -> summed per source row by k_row_sum
-//   gW_p          += X[src]^T (val_e G[dst_e])                         -> fp32 fragments kept in registers for
-//                                                                         the whole chunk, one atomic flush
+// Fused backward chunk.  One relation-major pass reads X[gather] (bf16) and G[other] (fp32) once and produces BOTH
+//   msg'[slot(e) - bias] = bf16( (val_e G[other_e]) @ blockdiag(W_p)^T )   -> summed per source row afterwards
+//   gW_p                += X[gather]^T (val_e G[other_e])                   -> fp32 fragments kept in registers for the
+//                                                                              whole chunk, one atomic flush
 // G rows are staged as fp32, scaled by val and rounded to bf16 in shared memory (fp32 accumulation in the MMA).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kBwdStages = 3;
 constexpr int kGTileBytes = 16 * 256;              // 16 edges x 64 fp32 outputs
 constexpr int kBwdStageBytes = kTileBytes + kGTileBytes;
 constexpr int kBwdWarpBytes = kBwdStages * kBwdStageBytes + kTileBytes;   // ring + bf16 G tile
+constexpr size_t kBwdSmemBytes = 4 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kBwdWarpBytes;
 
-__global__ void __launch_bounds__(256, 1) k_rel_mma_bwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
-                                                        const float* __restrict__ G, __nv_bfloat16* __restrict__ msg,
-                                                        float* __restrict__ gW) {
-    extern __shared__ __align__(128) unsigned char smem_bwd[];
-    unsigned char* smem = smem_bwd;
-    const int c = blockIdx.x;
-    if (c >= A.chunkptr[A.num_rels]) return;
-    int p, e0, e1;
-    chunk_lookup(A, c, p, e0, e1);
-    const int n = e1 - e0;
+__device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __restrict__ W, int nb,
+                                              const __nv_bfloat16* __restrict__ X, const float* __restrict__ G,
+                                              __nv_bfloat16* __restrict__ msg, float* __restrict__ gW,
+                                              unsigned char* smem) {
+    const int n = C.n;
     int32_t* s_src = reinterpret_cast<int32_t*>(smem);
     int32_t* s_dst = s_src + RGCN_CHUNK_EDGES;
     int32_t* s_slot = s_dst + RGCN_CHUNK_EDGES;
     float* s_val = reinterpret_cast<float*>(s_slot + RGCN_CHUNK_EDGES);
     unsigned char* rings = reinterpret_cast<unsigned char*>(s_val + RGCN_CHUNK_EDGES);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        s_src[i] = A.gather[e0 + i]; s_dst[i] = A.other[e0 + i]; s_val[i] = A.val[e0 + i];
-        if (msg) s_slot[i] = A.slot[e0 + i];
+        s_src[i] = C.gather[i]; s_dst[i] = C.other[i]; s_val[i] = C.val[i];
+        if (msg) s_slot[i] = C.slot[i] - C.slot_bias;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int NG = A.nb >> 2;
+    const int NG = nb >> 2;
     const int bg = warp % NG, wsub = warp / NG, nsub = 8 / NG;
-    const size_t xrow_bytes = (size_t)A.nb * 32;    // bf16 rows of X and msg'
-    const size_t grow_bytes = (size_t)A.nb * 64;    // fp32 rows of G
+    const size_t xrow_bytes = (size_t)nb * 32;      // bf16 rows of X and msg'
+    const size_t grow_bytes = (size_t)nb * 64;      // fp32 rows of G
 
     // W^T fragments for msg' = Gb @ W^T:  B[k = j][n = i] = W[i][j];  b0 = W[n][2t..2t+1], b1 = W[n][2t+8..2t+9]
     uint32_t wt[4][2][2];
     if (msg) {
-        const float* wp = A.W + ((size_t)p * A.nb + (size_t)bg * 4) * 256;
+        const float* wp = W + ((size_t)C.p * nb + (size_t)bg * 4) * 256;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(256, 1) k_rel_mma_bwd(RelArgs A, const __nv_bf
             }
     }
     __syncthreads();
-    float* dst = gW + (size_t)p * A.nb * 256;
+    float* dst = gW + (size_t)C.p * nb * 256;
     for (int i = threadIdx.x; i < NG * 1024; i += blockDim.x) {
         const int grp = i >> 10, el = i & 1023;
         float s = 0.f;
@@ -319,6 +326,214 @@ __global__ void __launch_bounds__(256, 1) k_rel_mma_bwd(RelArgs A, const __nv_bf
     }
 }
 
+// ---- one CTA per chunk --------------------------------------------------------------------------------
+__device__ __forceinline__ Chunk rel_chunk(const RelArgs& A, int c) {
+    int p, e0, e1;
+    chunk_lookup(A, c, p, e0, e1);
+    Chunk C;
+    C.p = p; C.n = e1 - e0;
+    C.gather = A.gather + e0; C.other = A.other ? A.other + e0 : nullptr;
+    C.slot = A.slot ? A.slot + e0 : nullptr; C.val = A.val + e0; C.slot_bias = 0;
+    return C;
+}
+
+__global__ void __launch_bounds__(256) k_rel_mma_fwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
+                                                     __nv_bfloat16* __restrict__ msg) {
+    extern __shared__ __align__(128) unsigned char smem_mma_fwd[];
+    if ((int)blockIdx.x >= A.chunkptr[A.num_rels]) return;
+    mma_fwd_chunk(rel_chunk(A, blockIdx.x), A.W, A.nb, X, msg, smem_mma_fwd);
+}
+
+__global__ void __launch_bounds__(256, 1) k_rel_mma_bwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
+                                                        const float* __restrict__ G, __nv_bfloat16* __restrict__ msg,
+                                                        float* __restrict__ gW) {
+    extern __shared__ __align__(128) unsigned char smem_mma_bwd[];
+    if ((int)blockIdx.x >= A.chunkptr[A.num_rels]) return;
+    mma_bwd_chunk(rel_chunk(A, blockIdx.x), A.W, A.nb, X, G, msg, gW, smem_mma_bwd);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Persistent tiled drivers: in-order work queue over row super-tiles, messages in an L2-resident ring.
+//   step j of the queue = [transform chunks of tile j] then [row-sum blocks of tile j-1]
+//   a row-sum block of tile k waits until all chunks of tile k are done (done1[k]);
+//   a chunk of tile k waits until every earlier tile that used ring slot k % depth has been summed: per-slot
+//   counter slot_done[k % depth] >= slotneed[k] (a per-tile "tile k-depth is done" test is NOT enough: empty
+//   tiles in between break the chain).
+// Items are claimed in order, so a waiting CTA only ever waits for items held by running CTAs: no deadlock.
+// ------------------------------------------------------------------------------------------------------
+struct TiledArgs {
+    rgcn_tiling tl;
+    const int32_t* rowptr;     // CSR of the tile side (d_rowptr forward, s_rowptr backward)
+    int T, Rp, nb, depth;
+    long long capacity;        // message rows per ring slot
+    int32_t* queue;            // [0]: next item
+    int32_t* done1;            // [T] finished chunks per tile
+    int32_t* slot_done;        // [depth] finished row blocks per ring slot
+    int32_t* status;           // [3] set if a wait gave up (watchdog)
+    const float* W;
+    const float* bias;
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void wait_count(const int32_t* counter, int need, int32_t* status) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire(counter) < need) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) { atomicExch(status + 3, 1); break; }   // ~1 s: report instead of hanging
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void signal_done(int32_t* counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1);
+    }
+}
+
+__device__ __forceinline__ float4 ldcg4(const __nv_bfloat16* p) {     // L2-only load: the ring is rewritten in-kernel
+    uint2 v = __ldcg(reinterpret_cast<const uint2*>(p));
+    float4 r;
+    unpack_bf16x2(v.x, r.x, r.y); unpack_bf16x2(v.y, r.z, r.w);
+    return r;
+}
+
+// rows [r0, r1): out[row, :] = bias + sum of the row's messages (contiguous in the ring slot)
+__device__ __forceinline__ void row_sum_block(const int32_t* __restrict__ rowptr, int r0, int r1, int width,
+                                              const __nv_bfloat16* __restrict__ ring_slot, int slot_bias,
+                                              const float* __restrict__ bias, float* __restrict__ out) {
+    const int cg = width >> 2;
+    const int total = (r1 - r0) * cg;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int row = r0 + idx / cg, q = idx % cg;
+        const int e0 = rowptr[row] - slot_bias, e1 = rowptr[row + 1] - slot_bias;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const __nv_bfloat16* m = ring_slot + (size_t)e0 * width + 4 * q;
+        int e = e0;
+        for (; e + 1 < e1; e += 2, m += 2 * (size_t)width) {
+            float4 a = ldcg4(m), b = ldcg4(m + width);
+            acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+        }
+        if (e < e1) {
+            float4 a = ldcg4(m);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        if (bias) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)row * width + 4 * q) = acc;
+    }
+}
+
+struct TiledItem { bool transform; int tile; int local; };
+
+// claim the next queue item (all threads get the same answer); false when the queue is exhausted
+__device__ __forceinline__ bool next_item(const TiledArgs& A, int* s_item, TiledItem& it) {
+    if (threadIdx.x == 0) *s_item = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int item = *s_item;
+    __syncthreads();
+    const int32_t* stepptr = A.tl.stepptr;
+    if (item >= stepptr[A.T + 1]) return false;
+    int lo = 0, hi = A.T + 1;                       // stepptr[lo] <= item < stepptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (stepptr[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int local = item - stepptr[lo];
+    const int n1 = lo < A.T ? A.tl.chunkptr[(lo + 1) * A.Rp] - A.tl.chunkptr[lo * A.Rp] : 0;
+    it.transform = local < n1;
+    it.tile = it.transform ? lo : lo - 1;
+    it.local = it.transform ? local : local - n1;
+    return true;
+}
+
+// chunk `local` of tile k -> Chunk over the tiling's arrays
+__device__ __forceinline__ Chunk tile_chunk(const TiledArgs& A, int k, int local) {
+    const int32_t* cp = A.tl.chunkptr;
+    const int c = cp[k * A.Rp] + local;
+    int lo = k * A.Rp, hi = (k + 1) * A.Rp;         // cp[lo] <= c < cp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (cp[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int e0 = A.tl.grpptr[lo] + (c - cp[lo]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.tl.grpptr[lo + 1], e0 + RGCN_CHUNK_EDGES);
+    Chunk C;
+    C.p = lo - k * A.Rp; C.n = e1 - e0;
+    C.gather = nullptr; C.other = nullptr;
+    C.slot = A.tl.slot + e0; C.val = A.tl.val + e0;
+    C.slot_bias = A.rowptr[A.tl.tilerow[k]];
+    // caller fills gather / other from tl.row / tl.col (+ e0)
+    C.gather = A.tl.row + e0; C.other = A.tl.col + e0;
+    return C;
+}
+
+// forward: rows = destinations; gather X[col] (sources)
+__global__ void __launch_bounds__(256) k_tiled_mma_fwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
+                                                       __nv_bfloat16* __restrict__ ring, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_tiled_fwd[];
+    __shared__ int s_item;
+    const size_t width = (size_t)A.nb * 16;
+    TiledItem it;
+    while (next_item(A, &s_item, it)) {
+        const int k = it.tile;
+        __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
+        if (it.transform) {
+            Chunk C = tile_chunk(A, k, it.local);
+            C.gather = C.other;                      // forward gathers the source endpoint (tl.col)
+            C.other = nullptr;
+            wait_count(A.slot_done + (k % A.depth), A.tl.slotneed[k], A.status);
+            mma_fwd_chunk(C, A.W, A.nb, X, slot_base, smem_tiled_fwd);
+            signal_done(A.done1 + k);
+        } else {
+            const int r0 = A.tl.tilerow[k] + it.local * RGCN_TILE_ROWS_PER_ITEM;
+            const int r1 = min(A.tl.tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM);
+            wait_count(A.done1 + k, A.tl.chunkptr[(k + 1) * A.Rp] - A.tl.chunkptr[k * A.Rp], A.status);
+            row_sum_block(A.rowptr, r0, r1, (int)width, slot_base, A.rowptr[A.tl.tilerow[k]], A.bias, out);
+            signal_done(A.slot_done + (k % A.depth));
+        }
+    }
+}
+
+// backward: rows = sources; gather X[row] (bf16) and G[col] (fp32); messages summed into the feature gradient
+__global__ void __launch_bounds__(256, 1) k_tiled_mma_bwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
+                                                          const float* __restrict__ G, __nv_bfloat16* __restrict__ ring,
+                                                          float* __restrict__ gX, float* __restrict__ gW) {
+    extern __shared__ __align__(128) unsigned char smem_tiled_bwd[];
+    __shared__ int s_item;
+    const size_t width = (size_t)A.nb * 16;
+    TiledItem it;
+    while (next_item(A, &s_item, it)) {
+        const int k = it.tile;
+        __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
+        if (it.transform) {
+            Chunk C = tile_chunk(A, k, it.local);   // gather = tl.row (source, X rows), other = tl.col (G rows)
+            wait_count(A.slot_done + (k % A.depth), A.tl.slotneed[k], A.status);
+            mma_bwd_chunk(C, A.W, A.nb, X, G, slot_base, gW, smem_tiled_bwd);
+            signal_done(A.done1 + k);
+        } else {
+            const int r0 = A.tl.tilerow[k] + it.local * RGCN_TILE_ROWS_PER_ITEM;
+            const int r1 = min(A.tl.tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM);
+            wait_count(A.done1 + k, A.tl.chunkptr[(k + 1) * A.Rp] - A.tl.chunkptr[k * A.Rp], A.status);
+            row_sum_block(A.rowptr, r0, r1, (int)width, slot_base, A.rowptr[A.tl.tilerow[k]], nullptr, gX);
+            signal_done(A.slot_done + (k % A.depth));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
 inline bool mma_shape_supported(int nb, int bi, int bo) {
     if (bi != 16 || bo != 16 || nb % 4 != 0) return false;
     int ng = nb / 4;
@@ -327,29 +542,67 @@ inline bool mma_shape_supported(int nb, int bi, int bo) {
 
 inline int launch_rel_mma_fwd(const RelArgs& A, const __nv_bfloat16* X, __nv_bfloat16* msg, int max_chunks,
                               cudaStream_t st) {
-    const size_t smem = 3 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kMmaStages * kTileBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
         attr_set = true;
     }
-    RGCN_LAUNCH(k_rel_mma_fwd, max_chunks, 256, smem, st, A, X, msg);
+    RGCN_LAUNCH(k_rel_mma_fwd, max_chunks, 256, kFwdSmemBytes, st, A, X, msg);
     return RGCN_OK;
 }
 
-}  // namespace rgcn
-
-namespace rgcn {
 // msg == nullptr: weight gradient only; gW == nullptr: feature-gradient messages only
 inline int launch_rel_mma_bwd(const RelArgs& A, const __nv_bfloat16* X, const float* G, __nv_bfloat16* msg, float* gW,
                               int max_chunks, cudaStream_t st) {
-    const size_t smem = 4 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kBwdWarpBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
         attr_set = true;
     }
-    RGCN_LAUNCH(k_rel_mma_bwd, max_chunks, 256, smem, st, A, X, G, msg, gW);
+    RGCN_LAUNCH(k_rel_mma_bwd, max_chunks, 256, kBwdSmemBytes, st, A, X, G, msg, gW);
     return RGCN_OK;
 }
+
+constexpr int kRingDepth = RGCN_RING_DEPTH;
+
+inline size_t tiled_counter_bytes(int64_t T) { return align_up((size_t)(T + 4 + 4) * sizeof(int32_t)); }
+
+inline TiledArgs make_tiled_args(const rgcn_graph* g, bool backward, int nb, const float* W, const float* bias,
+                                 int32_t* counters) {
+    TiledArgs A{};
+    A.tl = backward ? g->bt : g->ft;
+    A.rowptr = backward ? g->s_rowptr : g->d_rowptr;
+    A.T = (int)g->num_tiles; A.Rp = (int)g->num_rels; A.nb = nb; A.depth = kRingDepth;
+    A.capacity = (long long)g->tile_capacity;
+    A.queue = counters; A.slot_done = counters + 4; A.done1 = counters + 8;
+    A.status = g->status; A.W = W; A.bias = bias;
+    return A;
+}
+
+inline int launch_tiled_mma_fwd(const TiledArgs& A, const __nv_bfloat16* X, __nv_bfloat16* ring, float* out,
+                                cudaStream_t st) {
+    static int grid = 0;
+    if (!grid) {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
+        int per_sm = 0;
+        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_fwd, 256, kFwdSmemBytes));
+        grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
+    }
+    RGCN_LAUNCH(k_tiled_mma_fwd, grid, 256, kFwdSmemBytes, st, A, X, ring, out);
+    return RGCN_OK;
+}
+
+inline int launch_tiled_mma_bwd(const TiledArgs& A, const __nv_bfloat16* X, const float* G, __nv_bfloat16* ring,
+                                float* gX, float* gW, cudaStream_t st) {
+    static int grid = 0;
+    if (!grid) {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+        int per_sm = 0;
+        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, kBwdSmemBytes));
+        grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
+    }
+    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, kBwdSmemBytes, st, A, X, G, ring, gX, gW);
+    return RGCN_OK;
+}
+
 }  // namespace rgcn

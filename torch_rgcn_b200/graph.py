@@ -18,7 +18,8 @@ class GraphPlan:
     reference's (n, i) = (n_general, n_self)) or _lib.NORM_EXPLICIT (caller-provided `val`).
     """
 
-    def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True):
+    def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True,
+                 tile_edges=0):
         _lib.require_cuda(triples_plus)
         assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
         t = triples_plus.contiguous()
@@ -44,17 +45,38 @@ class GraphPlan:
         for name in ('d_rowptr', 'd_src', 'd_rel', 'd_val', 's_rowptr', 's_dst', 's_rel', 's_val',
                      'r_relptr', 'r_dst', 'r_src', 'r_val', 'r_dslot', 'r_sslot', 'r_chunkptr', 'val', 'status'):
             setattr(g, name, getattr(self, name).data_ptr())
+        # optional super-tiling for the L2-resident message ring (see include/rgcn_b200.h: rgcn_tiling)
+        self.tile_edges = int(tile_edges) if nnz > 0 else 0
+        g.tile_edges = self.tile_edges
+        self._tiling = []
+        if self.tile_edges > 0:
+            T = (nnz - 1) // self.tile_edges + 1
+            groups = T * num_rels
+            for tl in (g.ft, g.bt):
+                arrs = dict(tilerow=torch.empty(T + 1, **i32), grpptr=torch.empty(groups + 1, **i32),
+                            chunkptr=torch.empty(groups + 1, **i32), row=torch.empty(n1, **i32),
+                            col=torch.empty(n1, **i32), slot=torch.empty(n1, **i32), val=torch.empty(n1, **f32),
+                            stepptr=torch.empty(T + 2, **i32), slotneed=torch.empty(T, **i32))
+                self._tiling.append(arrs)
+                for k, v in arrs.items():
+                    setattr(tl, k, v.data_ptr())
         self.c = g
         if val is not None:
             val = val.to(device=dev, dtype=torch.float32).contiguous()
             assert val.numel() == nnz
-        ws_bytes = _lib.lib.rgcn_graph_workspace_bytes(nnz, num_nodes, num_rels)
+        ws_bytes = _lib.lib.rgcn_graph_workspace_bytes(nnz, num_nodes, num_rels, self.tile_edges)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.rgcn_graph_build(_lib.ptr(t), nnz, num_nodes, num_rels, norm, int(n_general),
                                                  int(n_self), _lib.ptr(val), C.byref(g), _lib.ptr(ws), ws_bytes,
                                                  _lib.stream_ptr()))
-        if validate:
+        if self.tile_edges > 0:
+            st = self.status.tolist()
+            g.tile_capacity = self.tile_capacity = max(st[1], st[2])
+            bad = st[0]
+            assert bad == 0 or not validate, f'{bad} triples have a node or relation id out of range ' \
+                                             f'(num_nodes={num_nodes}, num_relations={num_rels})'
+        elif validate:
             bad = int(self.status[0].item())
             # the reference asserts index bounds in stack_matrices (utils.py:163-164)
             assert bad == 0, f'{bad} triples have a node or relation id out of range ' \

@@ -7,6 +7,7 @@ them unchanged.  What changes is everything inside `forward`: the sparse-adjacen
 normalisation, weight decomposition and message passing run as CUDA kernels behind `rgcn_propagate`.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -113,22 +114,42 @@ class RelationalGraphConvolutionNC(Module):
             raise NotImplementedError(f'{reset_mode} parameter initialisation method has not been implemented')
 
     # -- graph plan -------------------------------------------------------------------------------------
-    def _plan(self, device):
+    def _tile_edges(self, features):
+        """Edges per row super-tile for the L2-resident message ring (bf16 features, 16x16 blocks only)."""
+        if (features is None or features.dtype != torch.bfloat16 or self.weight_decomp != 'block' or
+                self.in_features != self.out_features or self.in_features // self.num_blocks != 16 or
+                self.num_blocks % 4 != 0 or self.num_blocks // 4 not in (1, 2, 4, 8)):
+            return 0
+        # RGCN_TILE_MB: message bytes per row super-tile.  Default: tiling only when the untiled message buffer
+        # (nnz rows of bf16 messages) would exceed 8 GB, e.g. the 200 M-edge / 512-wide synthetic config.
+        env = os.environ.get('RGCN_TILE_MB')
+        row_bytes = self.out_features * 2
+        if env is None:
+            nnz = self.triples.size(0)
+            if nnz * row_bytes <= (8 << 30):
+                return 0
+            tile_bytes = 256 << 20
+        else:
+            tile_bytes = int(float(env) * (1 << 20))
+        return max(tile_bytes // row_bytes, 4096) if tile_bytes > 0 else 0
+
+    def _plan(self, device, features=None):
         t = self.triples
-        key = (str(device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking)
+        tile_edges = self._tile_edges(features)
+        key = (str(device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, tile_edges)
         if self._plan_cache is None or self._plan_cache[0] != key:
             nnz = t.size(0)
             n_general = int((nnz - self.num_nodes) / 2)          # reference layers.py:235
             norm = _lib.NORM_ROW if self.vertical_stacking else _lib.NORM_COL_SWAPPED
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
-                             validate=self.validate_triples)
+                             validate=self.validate_triples, tile_edges=tile_edges)
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 
     def set_plan(self, plan):
         """Install an externally built plan (e.g. a relation shard, see parallel.py)."""
         t = self.triples
-        key = (str(plan.device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking)
+        key = (str(plan.device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, plan.tile_edges)
         self._plan_cache = (key, plan)
 
     def forward(self, features=None):
@@ -141,7 +162,7 @@ class RelationalGraphConvolutionNC(Module):
             raise RuntimeError('featureless message passing requires horizontal stacking (vertical_stacking=False)')
         if self.diag_weight_matrix and self.vertical_stacking:
             raise RuntimeError('diagonal weight matrices require horizontal stacking (vertical_stacking=False)')
-        plan = self._plan(lead.device)
+        plan = self._plan(lead.device, features)
         in_dim = self.in_features if self.in_features is not None else self.num_nodes
         if self.diag_weight_matrix:
             assert self.weights.size() == (self.num_relations, in_dim)

@@ -80,8 +80,9 @@ class RelationShardedNC(torch.nn.Module):
         self.world = dist.get_world_size(group)
         self._local = None
 
-    def _local_plan(self, device):
-        if self._local is None or self._local.device != device:
+    def _local_plan(self, device, features=None):
+        tile_edges = self.layer._tile_edges(features)
+        if self._local is None or self._local.device != device or self._local.tile_edges != tile_edges:
             L = self.layer
             tp = L.triples.to(device)
             counts = torch.bincount(tp[:, 1], minlength=L.num_relations).cpu()
@@ -90,13 +91,13 @@ class RelationShardedNC(torch.nn.Module):
             if L.vertical_stacking:
                 # (p, s) segment counts are relation-local: normalise the shard directly
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_ROW,
-                                        validate=L.validate_triples)
+                                        validate=L.validate_triples, tile_edges=tile_edges)
             else:
                 # the horizontal permutation pairs each edge with its inverse in another relation: take the
                 # per-edge weights from the full graph, then keep this rank's rows
                 full = L._plan(device)
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT,
-                                        val=full.val[:full.nnz][mask], validate=False)
+                                        val=full.val[:full.nnz][mask], validate=False, tile_edges=tile_edges)
                 L._plan_cache = None
         return self._local
 
@@ -104,7 +105,7 @@ class RelationShardedNC(torch.nn.Module):
         L = self.layer
         assert (features is None) == (L.in_features is None), "in_features not provided!"
         lead = L._decomposed()[0]
-        plan = self._local_plan(lead.device)
+        plan = self._local_plan(lead.device, features)
         in_dim = L.in_features if L.in_features is not None else L.num_nodes
         if features is not None:
             features = _CopyToShards.apply(features, self.group)
