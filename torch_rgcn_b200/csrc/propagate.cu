@@ -279,8 +279,9 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
         default: break;
     }
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I);
+    if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
     RelShape rs; size_t msg = 0;
-    if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32)
+    if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32 upper bound)
     return bytes;
 }
 
@@ -297,6 +298,28 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_backward: workspace %zu < %zu", ws_bytes, need);
     Carver carve(ws);
     const int64_t IO = (int64_t)s.I * s.O;
+
+    // ---- bf16 features + 16x16 blocks (untiled): G is rounded to bf16 once, fused with the bias gradient, then ONE
+    //      tensor-core pass produces the feature-gradient messages and the weight gradient
+    const bool mma_bwd = x_dtype == RGCN_BF16 && !p->featureless && p->form == RGCN_W_BLOCK && !p->blocks_self &&
+                         !p->self_mask && s.nnz > 0 && mma_shape_supported(s.nb, s.bi, s.bo) &&
+                         (gr->features || gr->blocks) && !(tiled_path(g, p, s, true) && gr->features) &&
+                         align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes;
+    if (mma_bwd) {
+        __nv_bfloat16* gb16 = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
+        if (gr->bias) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->bias, 0, (size_t)s.O * sizeof(float), st));
+        rc = launch_cast_colsum(G, s.N, s.O, gb16, gr->bias, st);
+        if (rc) return rc;
+        RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
+        __nv_bfloat16* msg = nullptr;
+        if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
+        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), gb16, msg, gr->blocks, max_chunks(s), st);
+        if (rc) return rc;
+        if (gr->features)
+            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
+        return RGCN_OK;
+    }
 
     // ---- gbias
     if (gr->bias) {
@@ -336,21 +359,6 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
         TiledArgs T = make_tiled_args(g, true, s.nb, p->blocks, nullptr, counters);
         return launch_tiled_mma_bwd(T, static_cast<const __nv_bfloat16*>(X), G, ring, gr->features, gr->blocks, st);
-    }
-
-    // ---- bf16 features + 16x16 blocks: one fused tensor-core pass for feature and weight gradients
-    if (x_dtype == RGCN_BF16 && p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 &&
-        mma_shape_supported(s.nb, s.bi, s.bo) && (gr->features || gr->blocks) &&
-        align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes) {
-        RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
-        __nv_bfloat16* msg = nullptr;
-        if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
-        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
-        rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), G, msg, gr->blocks, max_chunks(s), st);
-        if (rc) return rc;
-        if (gr->features)
-            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
-        return RGCN_OK;
     }
 
     // ---- effective / transposed weights for the feature gradient

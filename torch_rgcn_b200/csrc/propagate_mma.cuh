@@ -162,14 +162,21 @@ __device__ __forceinline__ void mma_fwd_chunk(const Chunk& C, const float* __res
 // ------------------------------------------------------------------------------------------------------
 constexpr int kBwdStages = 3;
 constexpr int kGTileBytes = 16 * 256;              // 16 edges x 64 fp32 outputs
-constexpr int kBwdStageBytes = kTileBytes + kGTileBytes;
-constexpr int kBwdWarpBytes = kBwdStages * kBwdStageBytes + kTileBytes;   // ring + bf16 G tile
-constexpr size_t kBwdSmemBytes = 4 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kBwdWarpBytes;
+// fp32 G: per stage an X tile + an fp32 G tile, plus one bf16 G tile per warp; bf16 G: X tile + bf16 G tile
+template <bool GBF16> struct BwdSmem {
+    static constexpr int kStageBytes = GBF16 ? 2 * kTileBytes : kTileBytes + kGTileBytes;
+    static constexpr int kWarpBytes = kBwdStages * kStageBytes + (GBF16 ? 0 : kTileBytes);
+    static constexpr size_t kBytes = 4 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)8 * kWarpBytes;
+};
 
+// GBF16 = true: G was pre-rounded to bf16 by k_cast_colsum, so its rows are gathered straight into a swizzled
+// tile (128 B per edge instead of 256 B); val is applied to the message in fp32 and to the X tile in place.
+template <bool GBF16>
 __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __restrict__ W, int nb,
-                                              const __nv_bfloat16* __restrict__ X, const float* __restrict__ G,
+                                              const __nv_bfloat16* __restrict__ X, const void* __restrict__ Gv,
                                               __nv_bfloat16* __restrict__ msg, float* __restrict__ gW,
                                               unsigned char* smem) {
+    using L = BwdSmem<GBF16>;
     const int n = C.n;
     int32_t* s_src = reinterpret_cast<int32_t*>(smem);
     int32_t* s_dst = s_src + RGCN_CHUNK_EDGES;
@@ -184,8 +191,8 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int NG = nb >> 2;
     const int bg = warp % NG, wsub = warp / NG, nsub = 8 / NG;
-    const size_t xrow_bytes = (size_t)nb * 32;      // bf16 rows of X and msg'
-    const size_t grow_bytes = (size_t)nb * 64;      // fp32 rows of G
+    const size_t xrow_bytes = (size_t)nb * 32;                      // bf16 rows of X, msg' (and bf16 G)
+    const size_t grow_bytes = (size_t)nb * (GBF16 ? 32 : 64);
 
     // W^T fragments for msg' = Gb @ W^T:  B[k = j][n = i] = W[i][j];  b0 = W[n][2t..2t+1], b1 = W[n][2t+8..2t+9]
     uint32_t wt[4][2][2];
@@ -208,30 +215,33 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
 #pragma unroll
             for (int q = 0; q < 4; ++q) gacc[kb][h][q] = 0.f;
 
-    unsigned char* ring = rings + (size_t)warp * kBwdWarpBytes;
-    unsigned char* gb = ring + kBwdStages * kBwdStageBytes;          // bf16 (val * G) tile, swizzled
+    unsigned char* ring = rings + (size_t)warp * L::kWarpBytes;
+    unsigned char* gb_shared = ring + kBwdStages * L::kStageBytes;  // fp32-G variant: single bf16 (val * G) tile
     const int ntiles = (n + 15) >> 4;
     const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X) + (size_t)bg * 128;
-    const unsigned char* Gp = reinterpret_cast<const unsigned char*>(G) + (size_t)bg * 256;
+    const unsigned char* Gp = reinterpret_cast<const unsigned char*>(Gv) + (size_t)bg * (GBF16 ? 128 : 256);
     unsigned char* Mb = reinterpret_cast<unsigned char*>(msg) + (size_t)bg * 128;
 
     auto issue = [&](int k) {
         const int tile = wsub + k * nsub;
         if (tile < ntiles) {
-            unsigned char* st = ring + (k % kBwdStages) * kBwdStageBytes;
-            if (gW) {
+            unsigned char* st = ring + (k % kBwdStages) * L::kStageBytes;
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
-                    const bool ok = le < n;
-                    cp_async16(st + tile_off(row, chunk), Xb + (size_t)s_src[ok ? le : 0] * xrow_bytes + chunk * 16, ok);
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int row = (lane >> 4) + 2 * it, c16 = lane & 15, le = tile * 16 + row;
+            for (int it = 0; it < 4; ++it) {
+                const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
                 const bool ok = le < n;
-                cp_async16(st + kTileBytes + row * 256 + c16 * 16, Gp + (size_t)s_dst[ok ? le : 0] * grow_bytes + c16 * 16, ok);
+                if (gW) cp_async16(st + tile_off(row, chunk), Xb + (size_t)s_src[ok ? le : 0] * xrow_bytes + chunk * 16, ok);
+                if constexpr (GBF16)
+                    cp_async16(st + kTileBytes + tile_off(row, chunk),
+                               Gp + (size_t)s_dst[ok ? le : 0] * grow_bytes + chunk * 16, ok);
+            }
+            if constexpr (!GBF16) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = (lane >> 4) + 2 * it, c16 = lane & 15, le = tile * 16 + row;
+                    const bool ok = le < n;
+                    cp_async16(st + kTileBytes + row * 256 + c16 * 16, Gp + (size_t)s_dst[ok ? le : 0] * grow_bytes + c16 * 16, ok);
+                }
             }
         }
         cp_async_commit();
@@ -242,16 +252,35 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
         issue(k + 2);
         cp_async_wait<2>();
         __syncwarp();
-        unsigned char* st = ring + (k % kBwdStages) * kBwdStageBytes;
+        unsigned char* st = ring + (k % kBwdStages) * L::kStageBytes;
         const int tile = wsub + k * nsub;
-        // ---- fp32 G rows -> val-scaled bf16 tile (each lane: 4 floats of one row per step)
+        unsigned char* gb;
+        if constexpr (GBF16) {
+            gb = st + kTileBytes;                       // already bf16 and swizzled
+            if (gW) {                                   // X'[e] = val_e * X[e] in place (operand of the weight gradient)
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = (lane >> 4) + 2 * it, c4 = lane & 15, le = tile * 16 + row;
-            const float v = le < n ? s_val[le] : 0.f;
-            const float4 f = *reinterpret_cast<const float4*>(st + kTileBytes + row * 256 + c4 * 16);
-            *reinterpret_cast<uint2*>(gb + tile_off(row, c4 >> 1) + (c4 & 1) * 8) =
-                make_uint2(pack_bf16x2(f.x * v, f.y * v), pack_bf16x2(f.z * v, f.w * v));
+                for (int it = 0; it < 4; ++it) {
+                    const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
+                    const float v = le < n ? s_val[le] : 0.f;
+                    uint4* px = reinterpret_cast<uint4*>(st + tile_off(row, chunk));
+                    uint4 x = *px;
+                    float f[8];
+                    unpack_bf16x2(x.x, f[0], f[1]); unpack_bf16x2(x.y, f[2], f[3]);
+                    unpack_bf16x2(x.z, f[4], f[5]); unpack_bf16x2(x.w, f[6], f[7]);
+                    *px = make_uint4(pack_bf16x2(f[0] * v, f[1] * v), pack_bf16x2(f[2] * v, f[3] * v),
+                                     pack_bf16x2(f[4] * v, f[5] * v), pack_bf16x2(f[6] * v, f[7] * v));
+                }
+            }
+        } else {
+            gb = gb_shared;                             // fp32 G rows -> val-scaled bf16 tile
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = (lane >> 4) + 2 * it, c4 = lane & 15, le = tile * 16 + row;
+                const float v = le < n ? s_val[le] : 0.f;
+                const float4 f = *reinterpret_cast<const float4*>(st + kTileBytes + row * 256 + c4 * 16);
+                *reinterpret_cast<uint2*>(gb + tile_off(row, c4 >> 1) + (c4 & 1) * 8) =
+                    make_uint2(pack_bf16x2(f.x * v, f.y * v), pack_bf16x2(f.z * v, f.w * v));
+            }
         }
         __syncwarp();
         float macc[4][2][4];
@@ -280,13 +309,20 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
         }
         __syncwarp();                                   // X tile consumed: reuse it to transpose msg'
         if (msg) {
+            float v0 = 1.f, v1 = 1.f;                   // fp32-G variant folded val into the G tile already
+            if constexpr (GBF16) {
+                const int le0 = tile * 16 + g, le1 = le0 + 8;
+                v0 = le0 < n ? s_val[le0] : 0.f; v1 = le1 < n ? s_val[le1] : 0.f;
+            }
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int chunk = kb * 2 + h;
-                    *reinterpret_cast<uint32_t*>(st + tile_off(g, chunk) + t * 4) = pack_bf16x2(macc[kb][h][0], macc[kb][h][1]);
-                    *reinterpret_cast<uint32_t*>(st + tile_off(g + 8, chunk) + t * 4) = pack_bf16x2(macc[kb][h][2], macc[kb][h][3]);
+                    *reinterpret_cast<uint32_t*>(st + tile_off(g, chunk) + t * 4) =
+                        pack_bf16x2(macc[kb][h][0] * v0, macc[kb][h][1] * v0);
+                    *reinterpret_cast<uint32_t*>(st + tile_off(g + 8, chunk) + t * 4) =
+                        pack_bf16x2(macc[kb][h][2] * v1, macc[kb][h][3] * v1);
                 }
             __syncwarp();
 #pragma unroll
@@ -326,6 +362,38 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
     }
 }
 
+// G (N, O) fp32 -> bf16 copy, fused with the bias gradient (column sums): one streaming pass over G.
+// Thread = 8 consecutive columns of a strided set of rows; block-level smem reduction, then atomics.
+__global__ void __launch_bounds__(256) k_cast_colsum(const float* __restrict__ G, long long N, int O,
+                                                     long long rows_per_block, __nv_bfloat16* __restrict__ Gb,
+                                                     float* __restrict__ gbias) {
+    extern __shared__ float sums[];
+    const int cg = O >> 3;                               // 8-column groups per row
+    for (int j = threadIdx.x; j < O; j += blockDim.x) sums[j] = 0.f;
+    __syncthreads();
+    const int lanes = blockDim.x / cg;                   // rows handled concurrently
+    const int q = threadIdx.x % cg, rl = threadIdx.x / cg;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rl < lanes) {
+        const long long r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+        for (long long r = r0 + rl; r < r1; r += lanes) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * O + 8 * q));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * O + 8 * q) + 1);
+            *reinterpret_cast<uint4*>(Gb + (size_t)r * O + 8 * q) =
+                make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        if (gbias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sums[8 * q + j], acc[j]);
+        }
+    }
+    if (!gbias) return;
+    __syncthreads();
+    for (int j = threadIdx.x; j < O; j += blockDim.x) atomicAdd(gbias + j, sums[j]);
+}
+
 // ---- one CTA per chunk --------------------------------------------------------------------------------
 __device__ __forceinline__ Chunk rel_chunk(const RelArgs& A, int c) {
     int p, e0, e1;
@@ -344,12 +412,14 @@ __global__ void __launch_bounds__(256) k_rel_mma_fwd(RelArgs A, const __nv_bfloa
     mma_fwd_chunk(rel_chunk(A, blockIdx.x), A.W, A.nb, X, msg, smem_mma_fwd);
 }
 
-__global__ void __launch_bounds__(256, 1) k_rel_mma_bwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
-                                                        const float* __restrict__ G, __nv_bfloat16* __restrict__ msg,
-                                                        float* __restrict__ gW) {
+template <bool GBF16>
+__global__ void __launch_bounds__(256, GBF16 ? 2 : 1) k_rel_mma_bwd(RelArgs A, const __nv_bfloat16* __restrict__ X,
+                                                                    const void* __restrict__ G,
+                                                                    __nv_bfloat16* __restrict__ msg,
+                                                                    float* __restrict__ gW) {
     extern __shared__ __align__(128) unsigned char smem_mma_bwd[];
     if ((int)blockIdx.x >= A.chunkptr[A.num_rels]) return;
-    mma_bwd_chunk(rel_chunk(A, blockIdx.x), A.W, A.nb, X, G, msg, gW, smem_mma_bwd);
+    mma_bwd_chunk<GBF16>(rel_chunk(A, blockIdx.x), A.W, A.nb, X, G, msg, gW, smem_mma_bwd);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -519,7 +589,7 @@ __global__ void __launch_bounds__(256, 1) k_tiled_mma_bwd(TiledArgs A, const __n
         if (it.transform) {
             Chunk C = tile_chunk(A, k, it.local);   // gather = tl.row (source, X rows), other = tl.col (G rows)
             wait_count(A.slot_done + (k % A.depth), A.tl.slotneed[k], A.status);
-            mma_bwd_chunk(C, A.W, A.nb, X, G, slot_base, gW, smem_tiled_bwd);
+            mma_bwd_chunk<false>(C, A.W, A.nb, X, G, slot_base, gW, smem_tiled_bwd);
             signal_done(A.done1 + k);
         } else {
             const int r0 = A.tl.tilerow[k] + it.local * RGCN_TILE_ROWS_PER_ITEM;
@@ -551,15 +621,24 @@ inline int launch_rel_mma_fwd(const RelArgs& A, const __nv_bfloat16* X, __nv_bfl
     return RGCN_OK;
 }
 
-// msg == nullptr: weight gradient only; gW == nullptr: feature-gradient messages only
-inline int launch_rel_mma_bwd(const RelArgs& A, const __nv_bfloat16* X, const float* G, __nv_bfloat16* msg, float* gW,
-                              int max_chunks, cudaStream_t st) {
+// msg == nullptr: weight gradient only; gW == nullptr: feature-gradient messages only.  G is the bf16 copy.
+inline int launch_rel_mma_bwd(const RelArgs& A, const __nv_bfloat16* X, const __nv_bfloat16* Gb, __nv_bfloat16* msg,
+                              float* gW, int max_chunks, cudaStream_t st) {
+    constexpr size_t smem = BwdSmem<true>::kBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    RGCN_LAUNCH(k_rel_mma_bwd, max_chunks, 256, kBwdSmemBytes, st, A, X, G, msg, gW);
+    RGCN_LAUNCH(k_rel_mma_bwd<true>, max_chunks, 256, smem, st, A, X, static_cast<const void*>(Gb), msg, gW);
+    return RGCN_OK;
+}
+
+inline int launch_cast_colsum(const float* G, int64_t N, int O, __nv_bfloat16* Gb, float* gbias, cudaStream_t st) {
+    int64_t rows_per_block = (N + kNumSMs * 8 - 1) / (kNumSMs * 8);
+    if (rows_per_block < 64) rows_per_block = 64;
+    const int grid = (int)((N + rows_per_block - 1) / rows_per_block);
+    RGCN_LAUNCH(k_cast_colsum, grid, 256, (size_t)O * sizeof(float), st, G, (long long)N, O, (long long)rows_per_block, Gb, gbias);
     return RGCN_OK;
 }
 
@@ -596,12 +675,12 @@ inline int launch_tiled_mma_bwd(const TiledArgs& A, const __nv_bfloat16* X, cons
                                 float* gX, float* gW, cudaStream_t st) {
     static int grid = 0;
     if (!grid) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<false>::kBytes));
         int per_sm = 0;
-        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, kBwdSmemBytes));
+        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, BwdSmem<false>::kBytes));
         grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
     }
-    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, kBwdSmemBytes, st, A, X, G, ring, gX, gW);
+    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, BwdSmem<false>::kBytes, st, A, X, G, ring, gX, gW);
     return RGCN_OK;
 }
 
