@@ -443,6 +443,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         return RGCN_OK;
     }
     RelShape ws_shape; size_t unused = 0;
+    rc = 1;                                   // > 0: not served by the relation-batched kernel
     if (rel_path(p, s, x_dtype == RGCN_BF16, false, &ws_shape, &unused)) {
         RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, nullptr, g->r_val, nullptr, ws_shape.nb};
         float* target = (p->form == RGCN_W_BLOCK) ? gr->blocks : Wg.gW;
@@ -451,10 +452,10 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
                                   max_chunks(s), st);
         else
             rc = launch_rel_wgrad(R, ws_shape.bi, ws_shape.bo, static_cast<const float*>(X), G, target, max_chunks(s), st);
-    } else if (x_dtype == RGCN_BF16) {
-        rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
-    } else {
-        rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+    }
+    if (rc > 0) {
+        if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
+        else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
     }
     if (rc) return rc;
     if (p->form == RGCN_W_BASIS) {

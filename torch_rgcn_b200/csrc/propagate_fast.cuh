@@ -231,55 +231,61 @@ __device__ __forceinline__ void lds_slice(const __nv_bfloat16* p, float (&x)[n])
 
 constexpr int kWgStages = 3;
 
-template <typename XT, int BI, int BO>
+// All shape parameters are compile-time so that the staging and tile addressing reduce to constants
+// (the first version of this kernel spent 3/4 of its instructions on index arithmetic).
+template <typename XT, int BI, int BO, int NB>
 __global__ void __launch_bounds__(256) k_rel_wgrad(RelArgs A, const XT* __restrict__ X, const float* __restrict__ G,
-                                                   float* __restrict__ gW, int TE) {
+                                                   float* __restrict__ gW) {
     constexpr int TI = BI < 8 ? BI : 8, TJ = BO < 8 ? BO : 8;
-    constexpr int TPB = (BI / TI) * (BO / TJ);       // threads covering one (BI, BO) block
+    constexpr int TPB = (BI / TI) * (BO / TJ);        // threads covering one (BI, BO) block
+    constexpr int TC = NB * TPB;                       // threads covering the whole relation weight
+    constexpr int SETS = 256 / TC;                     // split-K groups
+    static_assert(TC <= 256 && SETS >= 1, "weight does not fit one CTA");
+    constexpr int I = NB * BI, O = NB * BO;
+    constexpr int RX = I * (int)sizeof(XT), RG = O * 4;   // row bytes
+    constexpr int NZ = NB * BI * BO;
+    constexpr int OPS = (RX + RG) / 16;                // 16-byte copies per edge
+    constexpr int TE_RAW = (36 * 1024) / (kWgStages * (RX + RG));
+    constexpr int TE_CAP = TE_RAW > 64 ? 64 : TE_RAW;
+    constexpr int TE = TE_CAP < SETS ? SETS : (TE_CAP / SETS) * SETS;                     // multiple of SETS
+    constexpr int STAGE = TE * (RX + RG);
+    static_assert(kWgStages * STAGE >= NZ * 4, "ring too small for the split-K reduction");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x;
     if (c >= A.chunkptr[A.num_rels]) return;
     int p, e0, e1;
     chunk_lookup(A, c, p, e0, e1);
-    const int nb = A.nb;
-    const int I = nb * BI, O = nb * BO;
-    const int RX = I * (int)sizeof(XT), RG = O * 4;   // row bytes
-    const int NZ = nb * BI * BO;
-    // smem carve: indices of the whole chunk, then the stage ring
     int32_t* s_src = reinterpret_cast<int32_t*>(smem_raw);
     int32_t* s_dst = s_src + RGCN_CHUNK_EDGES;
     float* s_val = reinterpret_cast<float*>(s_dst + RGCN_CHUNK_EDGES);
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_val + RGCN_CHUNK_EDGES);
-    const int stage_bytes = TE * (RX + RG);
     const int n = e1 - e0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         s_src[i] = A.gather[e0 + i]; s_dst[i] = A.other[e0 + i]; s_val[i] = A.val[e0 + i];
     }
     __syncthreads();
     const int ntiles = (n + TE - 1) / TE;
-    const int ops = (RX + RG) / 16;                   // 16-byte copies per edge
+    const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X);
+    const unsigned char* Gb = reinterpret_cast<const unsigned char*>(G);
     auto issue = [&](int tile) {
         if (tile < ntiles) {
-            unsigned char* st = ring + (size_t)(tile % kWgStages) * stage_bytes;
-            for (int k = threadIdx.x; k < TE * ops; k += blockDim.x) {
-                const int t = k / ops, piece = k - t * ops, le = tile * TE + t;
+            unsigned char* st = ring + (tile % kWgStages) * STAGE;
+#pragma unroll
+            for (int k = threadIdx.x; k < TE * OPS; k += 256) {
+                const int t = k / OPS, piece = k - t * OPS, le = tile * TE + t;      // OPS is a constant
                 const bool ok = le < n;
                 const int li = ok ? le : 0;
                 if (piece * 16 < RX)
-                    cp_async16(st + (size_t)t * RX + piece * 16,
-                               reinterpret_cast<const unsigned char*>(X) + (size_t)s_src[li] * RX + piece * 16, ok);
+                    cp_async16(st + t * RX + piece * 16, Xb + (size_t)s_src[li] * RX + piece * 16, ok);
                 else
-                    cp_async16(st + (size_t)TE * RX + (size_t)t * RG + (piece * 16 - RX),
-                               reinterpret_cast<const unsigned char*>(G) + (size_t)s_dst[li] * RG + (piece * 16 - RX), ok);
+                    cp_async16(st + TE * RX + t * RG + (piece * 16 - RX), Gb + (size_t)s_dst[li] * RG + (piece * 16 - RX), ok);
             }
         }
         cp_async_commit();
     };
-    const int TC = nb * TPB;                          // threads covering the whole relation weight
-    const int sets = blockDim.x / TC;                 // split-K groups
     const int set = threadIdx.x / TC, r = threadIdx.x % TC;
     const int blk = r / TPB, q = r % TPB, ti = q / (BO / TJ), tj = q % (BO / TJ);
-    const bool active = set < sets;
+    const bool active = set < SETS;
     float acc[TI][TJ];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
@@ -290,17 +296,19 @@ __global__ void __launch_bounds__(256) k_rel_wgrad(RelArgs A, const XT* __restri
     issue(1);
     for (int tile = 0; tile < ntiles; ++tile) {
         issue(tile + 2);
-        cp_async_wait<2>();                           // tile's group has landed (two younger groups may be in flight)
+        cp_async_wait<2>();                           // this tile has landed (two younger groups may be in flight)
         __syncthreads();
-        const unsigned char* st = ring + (size_t)(tile % kWgStages) * stage_bytes;
+        const unsigned char* st = ring + (tile % kWgStages) * STAGE;
         if (active) {
-            for (int t = set; t < TE; t += sets) {
-                const int le = tile * TE + t;
-                if (le >= n) break;
+            const XT* xs = reinterpret_cast<const XT*>(st) + blk * BI + ti * TI;
+            const float* gs = reinterpret_cast<const float*>(st + TE * RX) + blk * BO + tj * TJ;
+            const float* vs = s_val + tile * TE;
+#pragma unroll 4
+            for (int t = set; t < TE; t += SETS) {    // rows past the chunk end were zero-filled by cp.async
                 float x[TI], g[TJ];
-                lds_slice<TI>(reinterpret_cast<const XT*>(st + (size_t)t * RX) + blk * BI + ti * TI, x);
-                lds_slice<TJ>(reinterpret_cast<const float*>(st + (size_t)TE * RX + (size_t)t * RG) + blk * BO + tj * TJ, g);
-                const float v = s_val[le];
+                lds_slice<TI>(xs + t * I, x);
+                lds_slice<TJ>(gs + t * O, g);
+                const float v = (tile * TE + t < n) ? vs[t] : 0.f;
 #pragma unroll
                 for (int i = 0; i < TI; ++i) {
                     const float xv = x[i] * v;
@@ -312,10 +320,23 @@ __global__ void __launch_bounds__(256) k_rel_wgrad(RelArgs A, const XT* __restri
         __syncthreads();                              // everyone is done with this stage before it is refilled
     }
     cp_async_wait<0>();
-    // reduce the split-K partials through shared memory (reusing the ring), one set per round
+    // reduce the split-K partials: first across the sets that live in the same warp (shuffles), then across warps
+    // through shared memory (reusing the ring) in at most 8 rounds
+    if constexpr (TC < 32) {
+#pragma unroll
+        for (int off = TC; off < 32; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], off);
+    }
+    constexpr int ROUNDS = TC < 32 ? 8 : SETS;
+    const int my_round = TC < 32 ? (int)(threadIdx.x >> 5) : set;
+    const bool writer = TC < 32 ? ((threadIdx.x & 31) < TC) : active;
     float* red = reinterpret_cast<float*>(ring);
-    for (int s = 0; s < sets; ++s) {
-        if (active && set == s) {
+#pragma unroll 1
+    for (int s = 0; s < ROUNDS; ++s) {
+        if (writer && my_round == s) {
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
@@ -380,33 +401,43 @@ int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, c
     return RGCN_OK;
 }
 
-template <typename XT, int BI, int BO>
+template <typename XT, int BI, int BO, int NB>
 int launch_rel_wgrad_t(const RelArgs& A, const XT* X, const float* G, float* gW, int max_chunks, cudaStream_t st) {
-    const int I = A.nb * BI, O = A.nb * BO;
-    const int row_bytes = I * (int)sizeof(XT) + O * 4;
-    int TE = (36 * 1024) / (kWgStages * row_bytes);       // ~36 KB of ring per CTA
-    TE = TE < 2 ? 2 : (TE > 64 ? 64 : TE);
-    size_t ring = (size_t)kWgStages * TE * row_bytes;
-    size_t red = (size_t)A.nb * BI * BO * sizeof(float);
-    if (ring < red) ring = red;
-    const size_t smem = 3 * RGCN_CHUNK_EDGES * sizeof(int32_t) + ring;
-    auto kern = k_rel_wgrad<XT, BI, BO>;
+    constexpr int row_bytes = NB * BI * (int)sizeof(XT) + NB * BO * 4;
+    constexpr int TI = BI < 8 ? BI : 8, TJ = BO < 8 ? BO : 8;
+    constexpr int SETS = 256 / (NB * (BI / TI) * (BO / TJ));
+    constexpr int TE_RAW = (36 * 1024) / (kWgStages * row_bytes);
+    constexpr int TE_CAP = TE_RAW > 64 ? 64 : TE_RAW;
+    constexpr int TE = TE_CAP < SETS ? SETS : (TE_CAP / SETS) * SETS;
+    const size_t smem = 3 * RGCN_CHUNK_EDGES * sizeof(int32_t) + (size_t)kWgStages * TE * row_bytes;
+    auto kern = k_rel_wgrad<XT, BI, BO, NB>;
     if (smem > 48 * 1024) RGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RGCN_LAUNCH(kern, max_chunks, 256, smem, st, A, X, G, gW, TE);
+    RGCN_LAUNCH(kern, max_chunks, 256, smem, st, A, X, G, gW);
     return RGCN_OK;
 }
 
+template <typename XT, int BI, int BO>
+int launch_rel_wgrad_b(const RelArgs& A, const XT* X, const float* G, float* gW, int max_chunks, cudaStream_t st) {
+    switch (A.nb) {
+        case 1: return launch_rel_wgrad_t<XT, BI, BO, 1>(A, X, G, gW, max_chunks, st);
+        case 2: return launch_rel_wgrad_t<XT, BI, BO, 2>(A, X, G, gW, max_chunks, st);
+        case 4: return launch_rel_wgrad_t<XT, BI, BO, 4>(A, X, G, gW, max_chunks, st);
+        case 8: return launch_rel_wgrad_t<XT, BI, BO, 8>(A, X, G, gW, max_chunks, st);
+        default: return 1;   // not instantiated: caller falls back to the generic kernel
+    }
+}
+
+// returns > 0 when this (block shape, block count) is not instantiated
 template <typename XT>
 int launch_rel_wgrad(const RelArgs& A, int bi, int bo, const XT* X, const float* G, float* gW, int max_chunks,
                      cudaStream_t st) {
-    if (bi == 8 && bo == 8) return launch_rel_wgrad_t<XT, 8, 8>(A, X, G, gW, max_chunks, st);
-    if (bi == 16 && bo == 16) return launch_rel_wgrad_t<XT, 16, 16>(A, X, G, gW, max_chunks, st);
-    if (bi == 16 && bo == 4) return launch_rel_wgrad_t<XT, 16, 4>(A, X, G, gW, max_chunks, st);
+    if (bi == 8 && bo == 8) return launch_rel_wgrad_b<XT, 8, 8>(A, X, G, gW, max_chunks, st);
+    if (bi == 16 && bo == 16) return launch_rel_wgrad_b<XT, 16, 16>(A, X, G, gW, max_chunks, st);
+    if (bi == 16 && bo == 4) return launch_rel_wgrad_b<XT, 16, 4>(A, X, G, gW, max_chunks, st);
     if constexpr (sizeof(XT) == 4) {
-        if (bi == 4 && bo == 16) return launch_rel_wgrad_t<XT, 4, 16>(A, X, G, gW, max_chunks, st);
+        if (bi == 4 && bo == 16) return launch_rel_wgrad_b<XT, 4, 16>(A, X, G, gW, max_chunks, st);
     }
-    set_error("relation-batched weight gradient: unsupported block %dx%d", bi, bo);
-    return RGCN_ERR_UNSUPPORTED;
+    return 1;
 }
 
 }  // namespace rgcn
