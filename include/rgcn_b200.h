@@ -31,10 +31,10 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 3
+#define RGCN_ABI_VERSION 5
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
-#define RGCN_RING_DEPTH 3             /* message tiles kept in flight by the tiled kernels */
+#define RGCN_MAX_RING_DEPTH 64        /* upper bound on rgcn_graph.ring_depth */
 
 typedef void* rgcn_stream_t;
 
@@ -115,9 +115,23 @@ typedef struct rgcn_tiling {
     int32_t* col;           /* nnz: the other endpoint */
     int32_t* slot;          /* nnz: position of the edge in the row-major CSR of the tile side */
     float* val;             /* nnz */
-    int32_t* stepptr;       /* T+2: work-queue prefix: step j = chunks of tile j, then row blocks of tile j-1 */
-    int32_t* slotneed;      /* T: row blocks of the earlier tiles that share ring slot k % RGCN_RING_DEPTH */
+    int32_t* stepptr;       /* T+lag+1: work-queue prefix: step j = chunks of tile j, then row blocks of tile j-lag,
+                               lag = ring_depth / 2 (a tile is summed only after `lag` later tiles were queued) */
+    int32_t* slotneed;      /* T: row blocks of the earlier tiles that share ring slot k % ring_depth */
+    int32_t* items;         /* 8 x int32 per work-queue item (see rgcn_tile_item), capacity = rgcn_tile_items_bound() */
 } rgcn_tiling;
+
+/* one entry of the tiled kernels' in-order work queue */
+typedef struct rgcn_tile_item {
+    int32_t kind;           /* 0 = transform chunk, 1 = row-sum block */
+    int32_t tile;
+    int32_t a;              /* chunk: relation        | row block: first row */
+    int32_t b;              /* chunk: first edge      | row block: end row   */
+    int32_t c;              /* chunk: number of edges | row block: unused    */
+    int32_t slot_bias;      /* first CSR position of the tile (message row 0 of its ring slot) */
+    int32_t need;           /* counter value to wait for before starting */
+    int32_t pad;
+} rgcn_tile_item;
 
 typedef struct rgcn_graph {
     int64_t num_nodes;
@@ -147,11 +161,16 @@ typedef struct rgcn_graph {
     int64_t tile_edges;     /* 0: no tiling (ft / bt unused) */
     int64_t num_tiles;      /* T = (nnz - 1) / tile_edges + 1 (trailing tiles may be empty) */
     int64_t tile_capacity;  /* host copy of max(status[1], status[2]), filled by the caller after the build */
+    int64_t ring_depth;     /* message tiles in flight (2 .. RGCN_MAX_RING_DEPTH); set by the caller with tile_edges */
     rgcn_tiling ft;         /* forward tiling (destination rows) */
     rgcn_tiling bt;         /* backward tiling (source rows) */
 } rgcn_graph;
 
 size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges);
+/* upper bound on the number of work-queue items of one tiling (host-side sizing of rgcn_tiling.items) */
+int64_t rgcn_tile_items_bound(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges);
+/* length of rgcn_tiling.stepptr for a given tiling */
+int64_t rgcn_tile_steps_len(int64_t nnz, int64_t tile_edges, int64_t ring_depth);
 
 /* n_general / n_self are the (n, i) of the horizontal permutation: NC ((nnz-N)/2, N), LP (|T|, |T|+|self|).
  * val_in (nnz floats, caller order) is read only for RGCN_NORM_EXPLICIT. */

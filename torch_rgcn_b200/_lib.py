@@ -22,7 +22,7 @@ _i64 = C.c_int64
 
 class Tiling(C.Structure):
     _fields_ = [('tilerow', _p), ('grpptr', _p), ('chunkptr', _p), ('row', _p), ('col', _p), ('slot', _p),
-                ('val', _p), ('stepptr', _p), ('slotneed', _p)]
+                ('val', _p), ('stepptr', _p), ('slotneed', _p), ('items', _p)]
 
 
 class Graph(C.Structure):
@@ -32,7 +32,8 @@ class Graph(C.Structure):
                 ('r_relptr', _p), ('r_dst', _p), ('r_src', _p), ('r_val', _p),
                 ('r_dslot', _p), ('r_sslot', _p), ('r_chunkptr', _p),
                 ('val', _p), ('status', _p),
-                ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ft', Tiling), ('bt', Tiling)]
+                ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ring_depth', _i64),
+                ('ft', Tiling), ('bt', Tiling)]
 
 
 class Params(C.Structure):
@@ -76,6 +77,8 @@ def _load():
         'rgcn_sum_sparse': (C.c_int, [_p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p]),
         'rgcn_block_diag': (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
         'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64, _i64]),
+        'rgcn_tile_items_bound': (_i64, [_i64, _i64, _i64, _i64]),
+        'rgcn_tile_steps_len': (_i64, [_i64, _i64, _i64]),
         'rgcn_graph_build': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _i64, _i64, _p, C.POINTER(Graph), _p,
                                        C.c_size_t, _p]),
         'rgcn_forward_workspace_bytes': (C.c_size_t, [C.POINTER(Graph), C.POINTER(Params), C.c_int]),
@@ -95,7 +98,7 @@ def _load():
 lib = _load()
 EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add_inverse_and_self',
            'rgcn_generate_inverses', 'rgcn_lp_triples_plus', 'rgcn_stack_matrices', 'rgcn_sum_sparse',
-           'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
+           'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
            'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan']
 
 

@@ -287,33 +287,73 @@ __global__ void k_group_chunks(const int32_t* __restrict__ grpptr, int64_t ngrou
     else if (g == ngroups) cnt[g] = 0;
 }
 
-// per-tile capacity (atomicMax) and the work-queue prefix over steps: step j = chunks of tile j + row blocks of tile j-1
+// per-tile capacity (atomicMax) and the work-queue prefix over steps:
+// step j = chunks of tile j (j < T) + row blocks of tile j - lag (lag <= j < T + lag)
 __global__ void k_tile_steps(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tilerow,
-                             const int32_t* __restrict__ chunkptr, int64_t T, int64_t Rp,
+                             const int32_t* __restrict__ chunkptr, int64_t T, int64_t Rp, int64_t lag,
                              int32_t* __restrict__ stepcnt, int32_t* cap) {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j > T + 1) return;
+    if (j > T + lag) return;
     int32_t n = 0;
     if (j < T) {
         n += chunkptr[(j + 1) * Rp] - chunkptr[j * Rp];
         atomicMax(cap, rowptr[tilerow[j + 1]] - rowptr[tilerow[j]]);
     }
-    if (j >= 1 && j <= T) {
-        const int32_t rows = tilerow[j] - tilerow[j - 1];
+    if (j >= lag && j < T + lag) {
+        const int32_t rows = tilerow[j - lag + 1] - tilerow[j - lag];
         n += (rows + RGCN_TILE_ROWS_PER_ITEM - 1) / RGCN_TILE_ROWS_PER_ITEM;
     }
-    stepcnt[j] = (j <= T) ? n : 0;
+    stepcnt[j] = (j < T + lag) ? n : 0;
 }
 
 // slotneed[k] = row blocks of all tiles k' < k with k' % depth == k % depth (one thread per ring slot)
-__global__ void k_slot_need(const int32_t* __restrict__ tilerow, int64_t T, int32_t* __restrict__ slotneed) {
+__global__ void k_slot_need(const int32_t* __restrict__ tilerow, int64_t T, int depth, int32_t* __restrict__ slotneed) {
     const int s = threadIdx.x;
-    if (blockIdx.x || s >= RGCN_RING_DEPTH) return;
+    if (blockIdx.x || s >= depth) return;
     int32_t acc = 0;
-    for (int64_t k = s; k < T; k += RGCN_RING_DEPTH) {
+    for (int64_t k = s; k < T; k += depth) {
         slotneed[k] = acc;
         acc += (tilerow[k + 1] - tilerow[k] + RGCN_TILE_ROWS_PER_ITEM - 1) / RGCN_TILE_ROWS_PER_ITEM;
     }
+}
+
+// work-queue item table: item q of step j is a transform chunk of tile j (first) or a row block of tile j-1
+__global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t* __restrict__ chunkptr,
+                             const int32_t* __restrict__ grpptr, const int32_t* __restrict__ tilerow,
+                             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slotneed,
+                             int64_t T, int64_t Rp, int64_t lag, int64_t bound, rgcn_tile_item* __restrict__ items) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= bound || q >= stepptr[T + lag]) return;
+    int64_t lo = 0, hi = T + lag;                   // stepptr[lo] <= q < stepptr[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (stepptr[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int local = (int)(q - stepptr[lo]);
+    const int n1 = lo < T ? chunkptr[(lo + 1) * Rp] - chunkptr[lo * Rp] : 0;
+    rgcn_tile_item it;
+    it.pad = 0;
+    if (local < n1) {
+        const int64_t k = lo;
+        const int c = chunkptr[k * Rp] + local;
+        int64_t glo = k * Rp, ghi = (k + 1) * Rp;   // chunkptr[glo] <= c < chunkptr[ghi]
+        while (ghi - glo > 1) {
+            int64_t mid = (glo + ghi) >> 1;
+            if (chunkptr[mid] <= c) glo = mid; else ghi = mid;
+        }
+        const int e0 = grpptr[glo] + (c - chunkptr[glo]) * RGCN_CHUNK_EDGES;
+        const int e1 = min(grpptr[glo + 1], e0 + RGCN_CHUNK_EDGES);
+        it.kind = 0; it.tile = (int)k; it.a = (int)(glo - k * Rp); it.b = e0; it.c = e1 - e0;
+        it.slot_bias = rowptr[tilerow[k]];
+        it.need = slotneed[k];
+    } else {
+        const int64_t k = lo - lag;
+        const int r0 = tilerow[k] + (local - n1) * RGCN_TILE_ROWS_PER_ITEM;
+        it.kind = 1; it.tile = (int)k; it.a = r0; it.b = min(tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM); it.c = 0;
+        it.slot_bias = rowptr[tilerow[k]];
+        it.need = chunkptr[(k + 1) * Rp] - chunkptr[k * Rp];
+    }
+    items[q] = it;
 }
 
 int bits_for(unsigned __int128 maxkey) {
@@ -333,7 +373,7 @@ struct BuildWs {
 BuildWs carve_build(void* ws, int64_t nnz, int64_t ngroups = 0) {
     BuildWs b;
     size_t n = (size_t)(nnz > 0 ? nnz : 1);
-    if ((size_t)ngroups + 2 > n) n = (size_t)ngroups + 2;     // the scans over groups reuse the int scratch arrays
+    if ((size_t)ngroups + RGCN_MAX_RING_DEPTH + 2 > n) n = (size_t)ngroups + RGCN_MAX_RING_DEPTH + 2;   // scans over groups / steps reuse the int scratch
     size_t sort_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)n);
@@ -424,6 +464,17 @@ static int64_t tile_groups(int64_t nnz, int64_t Rp, int64_t tile_edges) {
     return ((nnz - 1) / tile_edges + 1) * Rp;
 }
 
+extern "C" int64_t rgcn_tile_items_bound(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges) {
+    if (tile_edges <= 0 || nnz <= 0) return 0;
+    const int64_t T = (nnz - 1) / tile_edges + 1;
+    return nnz / RGCN_CHUNK_EDGES + T * Rp + N / RGCN_TILE_ROWS_PER_ITEM + T + 2;
+}
+
+extern "C" int64_t rgcn_tile_steps_len(int64_t nnz, int64_t tile_edges, int64_t ring_depth) {
+    if (tile_edges <= 0 || nnz <= 0) return 0;
+    return (nnz - 1) / tile_edges + 1 + ring_depth / 2 + 1;
+}
+
 extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges) {
     (void)N;
     return carve_build(nullptr, nnz, tile_groups(nnz, Rp, tile_edges)).total;
@@ -509,13 +560,16 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         const int64_t te = g->tile_edges;
         const int64_t T = (nnz - 1) / te + 1;
         const int64_t ngroups = T * Rp;
+        const int64_t depth = g->ring_depth, lag = depth / 2;
+        RGCN_REQUIRE(depth >= 2 && depth <= RGCN_MAX_RING_DEPTH, RGCN_ERR_ARG, "rgcn_graph_build: ring_depth %lld out of range",
+                     (long long)depth);
         RGCN_REQUIRE(ngroups < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: too many (tile, relation) groups");
         g->num_tiles = T;
         const int tbits = bits_for((unsigned __int128)ngroups * (unsigned __int128)N);
         RGCN_REQUIRE(tbits <= 63, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: tile key does not fit 64 bits");
         for (int backward = 0; backward < 2; ++backward) {
             rgcn_tiling& tl = backward ? g->bt : g->ft;
-            RGCN_REQUIRE(tl.tilerow && tl.grpptr && tl.chunkptr && tl.row && tl.col && tl.slot && tl.val && tl.stepptr && tl.slotneed,
+            RGCN_REQUIRE(tl.tilerow && tl.grpptr && tl.chunkptr && tl.row && tl.col && tl.slot && tl.val && tl.stepptr && tl.slotneed && tl.items,
                          RGCN_ERR_ARG, "rgcn_graph_build: NULL tiling array");
             const int32_t* rowptr = backward ? g->s_rowptr : g->d_rowptr;
             RGCN_LAUNCH(k_make_tile_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, rowptr, te, b.k0, b.i0);
@@ -525,15 +579,18 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             RGCN_LAUNCH(k_decode_tiles, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, ngroups,
                         backward ? b.inv_s : b.inv_d, g->val, tl.grpptr, tl.row, tl.col, tl.slot, tl.val);
             RGCN_LAUNCH(k_tile_rows, grid_for(N, kBlock), kBlock, 0, stream, rowptr, N, te, T, tl.tilerow);
-            RGCN_LAUNCH(k_slot_need, 1, 32, 0, stream, tl.tilerow, T, tl.slotneed);
+            RGCN_LAUNCH(k_slot_need, 1, 64, 0, stream, tl.tilerow, T, (int)depth, tl.slotneed);
             RGCN_LAUNCH(k_group_chunks, grid_for(ngroups + 1, kBlock), kBlock, 0, stream, tl.grpptr, ngroups, b.flag);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.flag, tl.chunkptr, (int)(ngroups + 1), stream));
-            RGCN_LAUNCH(k_tile_steps, grid_for(T + 2, kBlock), kBlock, 0, stream, rowptr, tl.tilerow, tl.chunkptr, T, Rp,
-                        b.segid, g->status + 1 + backward);
+            RGCN_LAUNCH(k_tile_steps, grid_for(T + lag + 1, kBlock), kBlock, 0, stream, rowptr, tl.tilerow, tl.chunkptr, T,
+                        Rp, lag, b.segid, g->status + 1 + backward);
             cub_bytes = b.cub_bytes;
-            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.segid, tl.stepptr, (int)(T + 2), stream));
+            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.segid, tl.stepptr, (int)(T + lag + 1), stream));
             rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
+            const int64_t bound = rgcn_tile_items_bound(nnz, N, Rp, te);
+            RGCN_LAUNCH(k_fill_items, grid_for(bound, kBlock), kBlock, 0, stream, tl.stepptr, tl.chunkptr, tl.grpptr,
+                        tl.tilerow, rowptr, tl.slotneed, T, Rp, lag, bound, reinterpret_cast<rgcn_tile_item*>(tl.items));
         }
     }
     return RGCN_OK;

@@ -188,7 +188,7 @@ bool tiled_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool 
 }
 
 size_t tiled_ring_bytes(const rgcn_graph* g, int width) {
-    return align_up((size_t)kRingDepth * (size_t)g->tile_capacity * width * 2);
+    return align_up((size_t)g->ring_depth * (size_t)g->tile_capacity * width * 2);
 }
 
 int max_chunks(const Shape& s) { return (int)(s.nnz / RGCN_CHUNK_EDGES + s.Rp); }
@@ -278,8 +278,8 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
             break;
         default: break;
     }
-    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I);
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I);
     RelShape rs; size_t msg = 0;
     if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32 upper bound)
     return bytes;
@@ -303,17 +303,26 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     //      tensor-core pass produces the feature-gradient messages and the weight gradient
     const bool mma_bwd = x_dtype == RGCN_BF16 && !p->featureless && p->form == RGCN_W_BLOCK && !p->blocks_self &&
                          !p->self_mask && s.nnz > 0 && mma_shape_supported(s.nb, s.bi, s.bo) &&
-                         (gr->features || gr->blocks) && !(tiled_path(g, p, s, true) && gr->features) &&
-                         align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes;
+                         (gr->features || gr->blocks);
+    const bool tiled_bwd = mma_bwd && gr->features && tiled_path(g, p, s, true);
+    RGCN_REQUIRE(!mma_bwd || tiled_bwd || !gr->features || align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes,
+                 RGCN_ERR_UNSUPPORTED, "rgcn_backward: message buffer too large; build the plan with tile_edges > 0");
     if (mma_bwd) {
         __nv_bfloat16* gb16 = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
         if (gr->bias) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->bias, 0, (size_t)s.O * sizeof(float), st));
         rc = launch_cast_colsum(G, s.N, s.O, gb16, gr->bias, st);
         if (rc) return rc;
+        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        if (tiled_bwd) {      // feature-gradient messages stay in an L2-resident ring
+            int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
+            __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.I)));
+            RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
+            TiledArgs T = make_tiled_args(g, true, s.nb, p->blocks, nullptr, counters);
+            return launch_tiled_mma_bwd(T, static_cast<const __nv_bfloat16*>(X), gb16, ring, gr->features, gr->blocks, st);
+        }
         RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
         __nv_bfloat16* msg = nullptr;
         if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
-        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
         rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), gb16, msg, gr->blocks, max_chunks(s), st);
         if (rc) return rc;
         if (gr->features)
@@ -349,16 +358,6 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             RGCN_CHECK_CUDA(cudaMemsetAsync(gr->comps, 0, (size_t)s.Rp * s.B * sizeof(float), st));
         }
         return launch_featureless_grad(F, G, st);
-    }
-
-    // ---- tiled variant of the fused pass: feature-gradient messages stay in an L2-resident ring
-    if (tiled_path(g, p, s, x_dtype == RGCN_BF16) && gr->features) {
-        int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
-        __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.I)));
-        RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
-        if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
-        TiledArgs T = make_tiled_args(g, true, s.nb, p->blocks, nullptr, counters);
-        return launch_tiled_mma_bwd(T, static_cast<const __nv_bfloat16*>(X), G, ring, gr->features, gr->blocks, st);
     }
 
     // ---- effective / transposed weights for the feature gradient

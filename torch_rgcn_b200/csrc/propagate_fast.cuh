@@ -370,7 +370,7 @@ inline bool rel_shape_supported(int nb, int bi, int bo, bool bf16) {
 
 template <typename XT, typename MT, int BI, int BO>
 int launch_rel_transform_t(const RelArgs& A, const XT* X, MT* msg, int max_chunks, cudaStream_t st) {
-    constexpr int EPT = 2;
+    constexpr int EPT = 2;                           // 4 edges/thread was measured slower (am16: 0.73 -> 0.91 ms)
     const size_t smem = (size_t)A.nb * (BI * BO + 4) * sizeof(float);
     auto kern = k_rel_transform<XT, MT, BI, BO, EPT>;
     if (smem > 48 * 1024) RGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -435,6 +435,7 @@ struct TiledArgs {
     rgcn_tiling tl;
     const int32_t* rowptr;     // CSR of the tile side (d_rowptr forward, s_rowptr backward)
     int T, Rp, nb, depth;
+    int total_items;           // filled in-kernel from stepptr[T + 1]
     long long capacity;        // message rows per ring slot
     int32_t* queue;            // [0]: next item
     int32_t* done1;            // [T] finished chunks per tile
@@ -469,82 +470,70 @@ __device__ __forceinline__ void signal_done(int32_t* counter) {
     }
 }
 
-__device__ __forceinline__ float4 ldcg4(const __nv_bfloat16* p) {     // L2-only load: the ring is rewritten in-kernel
-    uint2 v = __ldcg(reinterpret_cast<const uint2*>(p));
-    float4 r;
-    unpack_bf16x2(v.x, r.x, r.y); unpack_bf16x2(v.y, r.z, r.w);
-    return r;
+// L2-only 16-byte load (the ring is rewritten inside the kernel, so L1 must not serve it)
+__device__ __forceinline__ void ldcg8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+    unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
 }
 
-// rows [r0, r1): out[row, :] = bias + sum of the row's messages (contiguous in the ring slot)
+// rows [r0, r1): out[row, :] = bias + sum of the row's messages (contiguous in the ring slot).
+// Thread = 8 columns of one row; 4 independent 16-byte loads in flight per thread.
 __device__ __forceinline__ void row_sum_block(const int32_t* __restrict__ rowptr, int r0, int r1, int width,
                                               const __nv_bfloat16* __restrict__ ring_slot, int slot_bias,
                                               const float* __restrict__ bias, float* __restrict__ out) {
-    const int cg = width >> 2;
+    const int cg = width >> 3;
     const int total = (r1 - r0) * cg;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int row = r0 + idx / cg, q = idx % cg;
         const int e0 = rowptr[row] - slot_bias, e1 = rowptr[row + 1] - slot_bias;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const __nv_bfloat16* m = ring_slot + (size_t)e0 * width + 4 * q;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* m = ring_slot + (size_t)e0 * width + 8 * q;
         int e = e0;
-        for (; e + 1 < e1; e += 2, m += 2 * (size_t)width) {
-            float4 a = ldcg4(m), b = ldcg4(m + width);
-            acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+        for (; e + 3 < e1; e += 4, m += 4 * (size_t)width) {
+            float a[8], b[8], c[8], d[8];
+            ldcg8(m, a); ldcg8(m + width, b); ldcg8(m + 2 * (size_t)width, c); ldcg8(m + 3 * (size_t)width, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += (a[j] + b[j]) + (c[j] + d[j]);
         }
-        if (e < e1) {
-            float4 a = ldcg4(m);
-            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        for (; e < e1; ++e, m += width) {
+            float a[8];
+            ldcg8(m, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += a[j];
         }
         if (bias) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
-            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q + 1);
+            acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+            acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
         }
-        *reinterpret_cast<float4*>(out + (size_t)row * width + 4 * q) = acc;
+        float4* o = reinterpret_cast<float4*>(out + (size_t)row * width + 8 * q);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
 }
 
-struct TiledItem { bool transform; int tile; int local; };
-
-// claim the next queue item (all threads get the same answer); false when the queue is exhausted
-__device__ __forceinline__ bool next_item(const TiledArgs& A, int* s_item, TiledItem& it) {
+// claim the next queue item (all threads get the same record); false when the queue is exhausted
+__device__ __forceinline__ bool next_item(const TiledArgs& A, int* s_item, rgcn_tile_item& it) {
     if (threadIdx.x == 0) *s_item = atomicAdd(A.queue, 1);
     __syncthreads();
     const int item = *s_item;
     __syncthreads();
-    const int32_t* stepptr = A.tl.stepptr;
-    if (item >= stepptr[A.T + 1]) return false;
-    int lo = 0, hi = A.T + 1;                       // stepptr[lo] <= item < stepptr[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (stepptr[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int local = item - stepptr[lo];
-    const int n1 = lo < A.T ? A.tl.chunkptr[(lo + 1) * A.Rp] - A.tl.chunkptr[lo * A.Rp] : 0;
-    it.transform = local < n1;
-    it.tile = it.transform ? lo : lo - 1;
-    it.local = it.transform ? local : local - n1;
+    if (item >= __ldg(A.tl.stepptr + A.T + A.depth / 2)) return false;
+    const int4* rec = reinterpret_cast<const int4*>(A.tl.items) + 2 * (size_t)item;
+    const int4 lo = __ldg(rec), hi = __ldg(rec + 1);
+    it.kind = lo.x; it.tile = lo.y; it.a = lo.z; it.b = lo.w;
+    it.c = hi.x; it.slot_bias = hi.y; it.need = hi.z; it.pad = 0;
     return true;
 }
 
-// chunk `local` of tile k -> Chunk over the tiling's arrays
-__device__ __forceinline__ Chunk tile_chunk(const TiledArgs& A, int k, int local) {
-    const int32_t* cp = A.tl.chunkptr;
-    const int c = cp[k * A.Rp] + local;
-    int lo = k * A.Rp, hi = (k + 1) * A.Rp;         // cp[lo] <= c < cp[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (cp[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int e0 = A.tl.grpptr[lo] + (c - cp[lo]) * RGCN_CHUNK_EDGES;
-    const int e1 = min(A.tl.grpptr[lo + 1], e0 + RGCN_CHUNK_EDGES);
+__device__ __forceinline__ Chunk item_chunk(const TiledArgs& A, const rgcn_tile_item& it) {
     Chunk C;
-    C.p = lo - k * A.Rp; C.n = e1 - e0;
-    C.gather = nullptr; C.other = nullptr;
-    C.slot = A.tl.slot + e0; C.val = A.tl.val + e0;
-    C.slot_bias = A.rowptr[A.tl.tilerow[k]];
-    // caller fills gather / other from tl.row / tl.col (+ e0)
-    C.gather = A.tl.row + e0; C.other = A.tl.col + e0;
+    C.p = it.a; C.n = it.c;
+    C.gather = A.tl.row + it.b; C.other = A.tl.col + it.b;
+    C.slot = A.tl.slot + it.b; C.val = A.tl.val + it.b;
+    C.slot_bias = it.slot_bias;
     return C;
 }
 
@@ -554,48 +543,45 @@ __global__ void __launch_bounds__(256) k_tiled_mma_fwd(TiledArgs A, const __nv_b
     extern __shared__ __align__(128) unsigned char smem_tiled_fwd[];
     __shared__ int s_item;
     const size_t width = (size_t)A.nb * 16;
-    TiledItem it;
+    rgcn_tile_item it;
     while (next_item(A, &s_item, it)) {
         const int k = it.tile;
         __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
-        if (it.transform) {
-            Chunk C = tile_chunk(A, k, it.local);
+        if (it.kind == 0) {
+            Chunk C = item_chunk(A, it);
             C.gather = C.other;                      // forward gathers the source endpoint (tl.col)
             C.other = nullptr;
-            wait_count(A.slot_done + (k % A.depth), A.tl.slotneed[k], A.status);
+            wait_count(A.slot_done + (k % A.depth), it.need, A.status);
             mma_fwd_chunk(C, A.W, A.nb, X, slot_base, smem_tiled_fwd);
             signal_done(A.done1 + k);
         } else {
-            const int r0 = A.tl.tilerow[k] + it.local * RGCN_TILE_ROWS_PER_ITEM;
-            const int r1 = min(A.tl.tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM);
-            wait_count(A.done1 + k, A.tl.chunkptr[(k + 1) * A.Rp] - A.tl.chunkptr[k * A.Rp], A.status);
-            row_sum_block(A.rowptr, r0, r1, (int)width, slot_base, A.rowptr[A.tl.tilerow[k]], A.bias, out);
+            wait_count(A.done1 + k, it.need, A.status);
+            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, A.bias, out);
             signal_done(A.slot_done + (k % A.depth));
         }
     }
 }
 
-// backward: rows = sources; gather X[row] (bf16) and G[col] (fp32); messages summed into the feature gradient
-__global__ void __launch_bounds__(256, 1) k_tiled_mma_bwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
-                                                          const float* __restrict__ G, __nv_bfloat16* __restrict__ ring,
+// backward: rows = sources; gather X[row] (bf16) and G[col] (bf16 copy); messages summed into the feature gradient
+__global__ void __launch_bounds__(256, 2) k_tiled_mma_bwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
+                                                          const __nv_bfloat16* __restrict__ Gb,
+                                                          __nv_bfloat16* __restrict__ ring,
                                                           float* __restrict__ gX, float* __restrict__ gW) {
     extern __shared__ __align__(128) unsigned char smem_tiled_bwd[];
     __shared__ int s_item;
     const size_t width = (size_t)A.nb * 16;
-    TiledItem it;
+    rgcn_tile_item it;
     while (next_item(A, &s_item, it)) {
         const int k = it.tile;
         __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
-        if (it.transform) {
-            Chunk C = tile_chunk(A, k, it.local);   // gather = tl.row (source, X rows), other = tl.col (G rows)
-            wait_count(A.slot_done + (k % A.depth), A.tl.slotneed[k], A.status);
-            mma_bwd_chunk<false>(C, A.W, A.nb, X, G, slot_base, gW, smem_tiled_bwd);
+        if (it.kind == 0) {
+            Chunk C = item_chunk(A, it);            // gather = tl.row (source, X rows), other = tl.col (G rows)
+            wait_count(A.slot_done + (k % A.depth), it.need, A.status);
+            mma_bwd_chunk<true>(C, A.W, A.nb, X, Gb, slot_base, gW, smem_tiled_bwd);
             signal_done(A.done1 + k);
         } else {
-            const int r0 = A.tl.tilerow[k] + it.local * RGCN_TILE_ROWS_PER_ITEM;
-            const int r1 = min(A.tl.tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM);
-            wait_count(A.done1 + k, A.tl.chunkptr[(k + 1) * A.Rp] - A.tl.chunkptr[k * A.Rp], A.status);
-            row_sum_block(A.rowptr, r0, r1, (int)width, slot_base, A.rowptr[A.tl.tilerow[k]], nullptr, gX);
+            wait_count(A.done1 + k, it.need, A.status);
+            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, nullptr, gX);
             signal_done(A.slot_done + (k % A.depth));
         }
     }
@@ -642,18 +628,17 @@ inline int launch_cast_colsum(const float* G, int64_t N, int O, __nv_bfloat16* G
     return RGCN_OK;
 }
 
-constexpr int kRingDepth = RGCN_RING_DEPTH;
 
-inline size_t tiled_counter_bytes(int64_t T) { return align_up((size_t)(T + 4 + 4) * sizeof(int32_t)); }
+inline size_t tiled_counter_bytes(int64_t T) { return align_up((size_t)(T + 4 + RGCN_MAX_RING_DEPTH) * sizeof(int32_t)); }
 
 inline TiledArgs make_tiled_args(const rgcn_graph* g, bool backward, int nb, const float* W, const float* bias,
                                  int32_t* counters) {
     TiledArgs A{};
     A.tl = backward ? g->bt : g->ft;
     A.rowptr = backward ? g->s_rowptr : g->d_rowptr;
-    A.T = (int)g->num_tiles; A.Rp = (int)g->num_rels; A.nb = nb; A.depth = kRingDepth;
+    A.T = (int)g->num_tiles; A.Rp = (int)g->num_rels; A.nb = nb; A.depth = (int)g->ring_depth;
     A.capacity = (long long)g->tile_capacity;
-    A.queue = counters; A.slot_done = counters + 4; A.done1 = counters + 8;
+    A.queue = counters; A.slot_done = counters + 4; A.done1 = counters + 4 + RGCN_MAX_RING_DEPTH;
     A.status = g->status; A.W = W; A.bias = bias;
     return A;
 }
@@ -671,16 +656,16 @@ inline int launch_tiled_mma_fwd(const TiledArgs& A, const __nv_bfloat16* X, __nv
     return RGCN_OK;
 }
 
-inline int launch_tiled_mma_bwd(const TiledArgs& A, const __nv_bfloat16* X, const float* G, __nv_bfloat16* ring,
+inline int launch_tiled_mma_bwd(const TiledArgs& A, const __nv_bfloat16* X, const __nv_bfloat16* G, __nv_bfloat16* ring,
                                 float* gX, float* gW, cudaStream_t st) {
     static int grid = 0;
     if (!grid) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<false>::kBytes));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<true>::kBytes));
         int per_sm = 0;
-        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, BwdSmem<false>::kBytes));
+        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, BwdSmem<true>::kBytes));
         grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
     }
-    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, BwdSmem<false>::kBytes, st, A, X, G, ring, gX, gW);
+    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, BwdSmem<true>::kBytes, st, A, X, G, ring, gX, gW);
     return RGCN_OK;
 }
 

@@ -19,7 +19,7 @@ class GraphPlan:
     """
 
     def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True,
-                 tile_edges=0):
+                 tile_edges=0, ring_depth=8):
         _lib.require_cuda(triples_plus)
         assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
         t = triples_plus.contiguous()
@@ -48,15 +48,18 @@ class GraphPlan:
         # optional super-tiling for the L2-resident message ring (see include/rgcn_b200.h: rgcn_tiling)
         self.tile_edges = int(tile_edges) if nnz > 0 else 0
         g.tile_edges = self.tile_edges
+        g.ring_depth = self.ring_depth = max(2, min(int(ring_depth), 64))
         self._tiling = []
         if self.tile_edges > 0:
             T = (nnz - 1) // self.tile_edges + 1
             groups = T * num_rels
+            n_items = _lib.lib.rgcn_tile_items_bound(nnz, num_nodes, num_rels, self.tile_edges)
             for tl in (g.ft, g.bt):
                 arrs = dict(tilerow=torch.empty(T + 1, **i32), grpptr=torch.empty(groups + 1, **i32),
                             chunkptr=torch.empty(groups + 1, **i32), row=torch.empty(n1, **i32),
                             col=torch.empty(n1, **i32), slot=torch.empty(n1, **i32), val=torch.empty(n1, **f32),
-                            stepptr=torch.empty(T + 2, **i32), slotneed=torch.empty(T, **i32))
+                            stepptr=torch.empty(_lib.lib.rgcn_tile_steps_len(nnz, self.tile_edges, self.ring_depth), **i32), slotneed=torch.empty(T, **i32),
+                            items=torch.empty(n_items, 8, **i32))
                 self._tiling.append(arrs)
                 for k, v in arrs.items():
                     setattr(tl, k, v.data_ptr())

@@ -142,7 +142,8 @@ class RelationalGraphConvolutionNC(Module):
             n_general = int((nnz - self.num_nodes) / 2)          # reference layers.py:235
             norm = _lib.NORM_ROW if self.vertical_stacking else _lib.NORM_COL_SWAPPED
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
-                             validate=self.validate_triples, tile_edges=tile_edges)
+                             validate=self.validate_triples, tile_edges=tile_edges,
+                             ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

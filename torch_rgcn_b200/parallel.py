@@ -10,6 +10,7 @@ Host logic here (planner, edge partition, the two autograd collectives) is devic
 CPU with a world_size-2 gloo test; the per-rank compute is the CUDA engine.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -91,13 +92,15 @@ class RelationShardedNC(torch.nn.Module):
             if L.vertical_stacking:
                 # (p, s) segment counts are relation-local: normalise the shard directly
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_ROW,
-                                        validate=L.validate_triples, tile_edges=tile_edges)
+                                        validate=L.validate_triples, tile_edges=tile_edges,
+                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
             else:
                 # the horizontal permutation pairs each edge with its inverse in another relation: take the
                 # per-edge weights from the full graph, then keep this rank's rows
                 full = L._plan(device)
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT,
-                                        val=full.val[:full.nnz][mask], validate=False, tile_edges=tile_edges)
+                                        val=full.val[:full.nnz][mask], validate=False, tile_edges=tile_edges,
+                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
                 L._plan_cache = None
         return self._local
 
