@@ -59,8 +59,11 @@ def dist_info():
 # ------------------------------------------------------------------------------------------------------
 # workload construction
 # ------------------------------------------------------------------------------------------------------
-def build_triples(wl, device, scale=1.0, seed=0):
-    from torch_rgcn_b200.synthetic import SHAPES, random_triples
+def build_triples(wl, device, scale=1.0, seed=0, skew=False):
+    from torch_rgcn_b200.synthetic import SHAPES, random_triples as _rt
+
+    def random_triples(*a, **k):
+        return _rt(*a, rel_dist='zipf' if skew else 'uniform', node_skew=skew, **k)
     N, R, E = SHAPES[wl['shape']]
     if scale != 1.0:
         N, E = max(int(N * scale), 64), max(int(E * scale), 64)
@@ -147,7 +150,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     wl = WORKLOADS[args.workload]
-    t, N, Rp, nnz = build_triples(wl, dev)
+    t, N, Rp, nnz = build_triples(wl, dev, skew=args.skew)
     xdt = torch.bfloat16 if wl['dtype'] == 'bf16' else torch.float32
     I, O = wl['in_f'], wl['out_f']
     torch.manual_seed(2)
@@ -303,7 +306,8 @@ def run_ours(args):
         'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': nnz / (ms_step * 1e-3), 'unit': 'edges/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': wl['dtype'], 'data': 'synthetic',
-        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'num_relations': Rp, 'nnz': nnz,
+        'config': {'workload': wl['label'] + (' [skewed: cubic node skew, Zipf relations]' if args.skew else ''),
+                   'name': args.workload, 'num_nodes': N, 'num_relations': Rp, 'nnz': nnz,
                    'l2': 'L2 flushed (256 MB write) between timed steps; flush outside the event pairs',
                    'parallelism': f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)'
                    if world > 1 else 'single GPU',
@@ -427,6 +431,7 @@ def main():
     ap.add_argument('--workload', default='am64', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--skew', action='store_true', help='power-law node degrees + Zipf relation sizes (hub rows)')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == 'reference':

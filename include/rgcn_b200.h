@@ -31,10 +31,11 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 5
+#define RGCN_ABI_VERSION 7
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_MAX_RING_DEPTH 64        /* upper bound on rgcn_graph.ring_depth */
+#define RGCN_LONG_ROW 512             /* rows with more edges are listed in d_long / s_long and processed cooperatively */
 
 typedef void* rgcn_stream_t;
 
@@ -156,8 +157,14 @@ typedef struct rgcn_graph {
     int32_t* r_sslot;       /* nnz: position of relation-major edge k in the source-major list */
     int32_t* r_chunkptr;    /* R'+1: relation p owns chunks [r_chunkptr[p], r_chunkptr[p+1]) of RGCN_CHUNK_EDGES edges */
     float* val;             /* nnz, in the caller's edge order: the reference's `vals` (layers.py:273) */
-    int32_t* status;        /* 4 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164),
-                               [1] / [2] = largest destination / source tile in edges, [3] = kernel watchdog flag */
+    int32_t* status;        /* 8 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164),
+                               [1] / [2] = largest destination / source tile in edges, [3] = kernel watchdog flag,
+                               [4] / [5] = number of long destination / source rows */
+    int32_t* d_long;        /* nnz / RGCN_LONG_ROW + 1: destination rows with more than RGCN_LONG_ROW edges */
+    int32_t* s_long;        /* nnz / RGCN_LONG_ROW + 1: source rows with more than RGCN_LONG_ROW edges */
+    int64_t num_long_dst;   /* host copy of status[4], or -1 if the caller did not read it back (kernels then launch
+                               the upper bound nnz / RGCN_LONG_ROW of CTAs and exit early) */
+    int64_t num_long_src;   /* host copy of status[5], or -1 */
     int64_t tile_edges;     /* 0: no tiling (ft / bt unused) */
     int64_t num_tiles;      /* T = (nnz - 1) / tile_edges + 1 (trailing tiles may be empty) */
     int64_t tile_capacity;  /* host copy of max(status[1], status[2]), filled by the caller after the build */

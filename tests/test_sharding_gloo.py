@@ -55,7 +55,7 @@ def _worker(rank, world, port, out_dir):
     Wl = W.clone().requires_grad_(True)
     xs = _CopyToShards.apply(x, None)
     part = _OracleShard.apply(xs, Wl, torch.from_numpy(tp[mask]), torch.from_numpy(val[mask]))
-    out = _ReduceFromShards.apply(part, None)
+    out = _ReduceFromShards.apply(part, None, None)
     out.backward(G)
     dist.all_reduce(Wl.grad)                              # disjoint supports -> sum is the full gradient
     full = orc.propagate(tp, val, W.numpy(), x.detach().numpy(), None, N)

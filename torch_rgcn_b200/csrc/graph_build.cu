@@ -356,6 +356,13 @@ __global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t*
     items[q] = it;
 }
 
+// rows with more than RGCN_LONG_ROW edges (hubs) are listed so that kernels can process them cooperatively
+__global__ void k_long_rows(const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ list, int32_t* count) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    if (rowptr[r + 1] - rowptr[r] > RGCN_LONG_ROW) list[atomicAdd(count, 1)] = (int32_t)r;
+}
+
 int bits_for(unsigned __int128 maxkey) {
     int b = 1;
     while (b < 64 && (maxkey >> b) != 0) ++b;
@@ -508,9 +515,10 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
     RGCN_REQUIRE(ws_bytes >= b.total && (ws || b.total == 0), RGCN_ERR_WORKSPACE,
                  "rgcn_graph_build: workspace %zu < %zu bytes", ws_bytes, b.total);
     g->num_nodes = N; g->num_rels = Rp; g->nnz = nnz;
-    g->num_tiles = 0; g->tile_capacity = 0;
+    g->num_tiles = 0; g->tile_capacity = 0; g->num_long_dst = g->num_long_src = -1;
     RGCN_REQUIRE(g->tile_edges >= 0, RGCN_ERR_ARG, "rgcn_graph_build: negative tile_edges");
-    RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 4 * sizeof(int32_t), stream));
+    RGCN_REQUIRE(g->d_long && g->s_long, RGCN_ERR_ARG, "rgcn_graph_build: NULL long-row list");
+    RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 8 * sizeof(int32_t), stream));
     if (nnz == 0) {
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->d_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
         RGCN_CHECK_CUDA(cudaMemsetAsync(g->s_rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
@@ -556,6 +564,8 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr);
         }
     }
+    RGCN_LAUNCH(k_long_rows, grid_for(N, kBlock), kBlock, 0, stream, g->d_rowptr, N, g->d_long, g->status + 4);
+    RGCN_LAUNCH(k_long_rows, grid_for(N, kBlock), kBlock, 0, stream, g->s_rowptr, N, g->s_long, g->status + 5);
     if (g->tile_edges > 0) {
         const int64_t te = g->tile_edges;
         const int64_t T = (nnz - 1) / te + 1;

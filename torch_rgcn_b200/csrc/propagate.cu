@@ -31,12 +31,20 @@ int launch_prop_generic(const PropArgs& A, const XT* X, cudaStream_t st) {
     int64_t want = (A.nrows + wpb - 1) / wpb;
     int grid = (int)(want < (int64_t)kNumSMs * 64 ? want : (int64_t)kNumSMs * 64);
     if (grid < 1) grid = 1;
-    switch (K) {
-        case 1: RGCN_LAUNCH((k_prop_generic<XT, 1>), grid, block, smem, st, A, X); break;
-        case 2: RGCN_LAUNCH((k_prop_generic<XT, 2>), grid, block, smem, st, A, X); break;
-        case 4: RGCN_LAUNCH((k_prop_generic<XT, 4>), grid, block, smem, st, A, X); break;
-        case 8: RGCN_LAUNCH((k_prop_generic<XT, 8>), grid, block, smem, st, A, X); break;
-        default: RGCN_LAUNCH((k_prop_generic<XT, 16>), grid, block, smem, st, A, X); break;
+    // pass 0: every row (hub rows only get their bias); pass 1: hub rows, split over the warps of 16 CTAs each
+    const int long_bound = !A.long_list ? 0 : (A.num_long >= 0 ? (int)A.num_long : (int)(A.nnz_hint / RGCN_LONG_ROW));
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && long_bound == 0) break;
+        PropArgs P = A;
+        P.long_mode = pass;
+        dim3 g = pass ? dim3(long_bound, 16) : dim3(grid);
+        switch (K) {
+            case 1: RGCN_LAUNCH((k_prop_generic<XT, 1>), g, block, smem, st, P, X); break;
+            case 2: RGCN_LAUNCH((k_prop_generic<XT, 2>), g, block, smem, st, P, X); break;
+            case 4: RGCN_LAUNCH((k_prop_generic<XT, 4>), g, block, smem, st, P, X); break;
+            case 8: RGCN_LAUNCH((k_prop_generic<XT, 8>), g, block, smem, st, P, X); break;
+            default: RGCN_LAUNCH((k_prop_generic<XT, 16>), g, block, smem, st, P, X); break;
+        }
     }
     return RGCN_OK;
 }
@@ -224,6 +232,7 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     A.nrows = s.N; A.N = s.N;
     fill_weights(A, p, s);
     A.bias = p->bias; A.out_mask = p->self_mask; A.out = out;
+    A.long_list = g->d_long; A.long_count = g->status + 4; A.nnz_hint = s.nnz; A.num_long = g->num_long_dst;
     if (p->form == RGCN_W_BASIS && !p->featureless) {      // materialise the small (R', I, O) table only
         float* weff = carve.take<float>(s.w_elems);
         int64_t IO = (int64_t)s.I * s.O;
@@ -252,12 +261,14 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
                 rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const __nv_bfloat16*>(X),
                                           static_cast<__nv_bfloat16*>(msg), max_chunks(s), st);
             if (rc) return rc;
-            return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const __nv_bfloat16*>(msg), p->bias, out, st);
+            return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const __nv_bfloat16*>(msg), p->bias, out, g->d_long,
+                                  g->status + 4, g->num_long_dst, s.nnz, st);
         }
         rc = launch_rel_transform(R, rs.bi, rs.bo, static_cast<const float*>(X), static_cast<float*>(msg),
                                   max_chunks(s), st);
         if (rc) return rc;
-        return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const float*>(msg), p->bias, out, st);
+        return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const float*>(msg), p->bias, out, g->d_long, g->status + 4,
+                              g->num_long_dst, s.nnz, st);
     }
     if (bf16) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
     return launch_prop(A, static_cast<const float*>(X), st);
@@ -326,7 +337,8 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), gb16, msg, gr->blocks, max_chunks(s), st);
         if (rc) return rc;
         if (gr->features)
-            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
+            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, g->s_long, g->status + 5,
+                                  g->num_long_src, s.nnz, st);
         return RGCN_OK;
     }
 
@@ -374,6 +386,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         fill_weights(A, p, s);
         A.I = s.O; A.O = s.I; A.bi = s.bo; A.bo = s.bi;
         A.in_mask = p->self_mask; A.out = gr->features;
+        A.long_list = g->s_long; A.long_count = g->status + 5; A.nnz_hint = s.nnz; A.num_long = g->num_long_src;
         if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
             float* wt = carve.take<float>((size_t)s.Rp * IO);
             rc = launch_transpose(p->form == RGCN_W_BASIS ? weff : p->weights, s.Rp, s.I, s.O, wt, st);
@@ -399,7 +412,8 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             float* msg = reinterpret_cast<float*>(carve.take<char>(msg_bytes));
             rc = launch_rel_transform(R, rs.bi, rs.bo, G, msg, max_chunks(s), st);
             if (rc) return rc;
-            rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, st);
+            rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, g->s_long, g->status + 5,
+                                g->num_long_src, s.nnz, st);
         } else {
             rc = launch_prop(A, G, st);
         }

@@ -151,42 +151,124 @@ __global__ void __launch_bounds__(256) k_rel_transform(RelArgs A, const XT* __re
 }
 
 // ------------------------------------------------------------------------------------------------------
-// phase 2: out[row, 4q..4q+3] = bias + sum_{e in row} msg[e, 4q..4q+3]   (thread per (row, 4 columns))
+// phase 2: out[row, V*q .. V*q+V-1] = bias + sum_{e in row} msg[e, ...]   (thread per (row, V columns), V = 4 or 8)
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
-    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    float4 r;
-    unpack_bf16x2(v.x, r.x, r.y); unpack_bf16x2(v.y, r.z, r.w);
+template <int V> struct VecF { float v[V]; };
+
+template <int V>
+__device__ __forceinline__ VecF<V> loadv(const float* p) {
+    VecF<V> r;
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p) + k);
+        r.v[4 * k] = a.x; r.v[4 * k + 1] = a.y; r.v[4 * k + 2] = a.z; r.v[4 * k + 3] = a.w;
+    }
     return r;
 }
+template <int V>
+__device__ __forceinline__ VecF<V> loadv(const __nv_bfloat16* p) {
+    VecF<V> r;
+    if constexpr (V == 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+        unpack_bf16x2(a.x, r.v[0], r.v[1]); unpack_bf16x2(a.y, r.v[2], r.v[3]);
+        unpack_bf16x2(a.z, r.v[4], r.v[5]); unpack_bf16x2(a.w, r.v[6], r.v[7]);
+    } else {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+        unpack_bf16x2(a.x, r.v[0], r.v[1]); unpack_bf16x2(a.y, r.v[2], r.v[3]);
+    }
+    return r;
+}
+template <int V>
+__device__ __forceinline__ void storev(float* p, const VecF<V>& a) {
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k)
+        reinterpret_cast<float4*>(p)[k] = make_float4(a.v[4 * k], a.v[4 * k + 1], a.v[4 * k + 2], a.v[4 * k + 3]);
+}
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-template <typename MT>
+template <typename MT, int V>
 __global__ void __launch_bounds__(256) k_row_sum(const int32_t* __restrict__ rowptr, int64_t nrows, int O,
                                                  const MT* __restrict__ msg, const float* __restrict__ bias,
                                                  float* __restrict__ out) {
-    const int cg = O >> 2;
+    const int cg = O / V;
     const int64_t total = nrows * cg;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = idx / cg;
         const int q = (int)(idx - row * cg);
         const int e0 = rowptr[row], e1 = rowptr[row + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const MT* m = msg + (size_t)e0 * O + 4 * q;
+        if (e1 - e0 > RGCN_LONG_ROW) continue;                 // hub rows: k_row_sum_long
+        VecF<V> acc;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
+        const MT* m = msg + (size_t)e0 * O + V * q;
         int e = e0;
         for (; e + 1 < e1; e += 2, m += 2 * (size_t)O) {
-            float4 a = load4(m), b = load4(m + O);
-            acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+            const VecF<V> a = loadv<V>(m), b = loadv<V>(m + O);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc.v[j] += a.v[j] + b.v[j];
         }
         if (e < e1) {
-            float4 a = load4(m);
-            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+            const VecF<V> a = loadv<V>(m);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc.v[j] += a.v[j];
         }
         if (bias) {
-            float4 b = load4(bias + 4 * q);
-            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            const VecF<V> b = loadv<V>(bias + V * q);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc.v[j] += b.v[j];
         }
-        *reinterpret_cast<float4*>(out + (size_t)row * O + 4 * q) = acc;
+        storev<V>(out + (size_t)row * O + V * q, acc);
+    }
+}
+
+// hub rows (more than RGCN_LONG_ROW messages): one CTA per row, edge-parallel partial sums (4 independent loads in
+// flight per thread), shared-memory reduction
+template <typename MT, int V>
+__global__ void __launch_bounds__(256) k_row_sum_long(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ list,
+                                                      const int32_t* __restrict__ count, int O, const MT* __restrict__ msg,
+                                                      const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float red[256 * V];
+    if ((int)blockIdx.x >= *count) return;
+    const int row = list[blockIdx.x];
+    const int e0 = rowptr[row], e1 = rowptr[row + 1];
+    const int cg = O / V;
+    const int cgb = cg < 256 ? cg : 256;                       // column groups handled per pass
+    const int lanes = 256 / cgb;                               // edge lanes per column group
+    for (int q0 = 0; q0 < cg; q0 += 256) {
+        const int q = q0 + (int)threadIdx.x % cgb, lane = threadIdx.x / cgb;
+        VecF<V> acc;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
+        if (q < cg && lane < lanes) {
+            const MT* m = msg + V * q;
+            int e = e0 + lane;
+            for (; e + 3 * lanes < e1; e += 4 * lanes) {
+                const VecF<V> a = loadv<V>(m + (size_t)e * O), b = loadv<V>(m + (size_t)(e + lanes) * O);
+                const VecF<V> c = loadv<V>(m + (size_t)(e + 2 * lanes) * O), d = loadv<V>(m + (size_t)(e + 3 * lanes) * O);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] += (a.v[j] + b.v[j]) + (c.v[j] + d.v[j]);
+            }
+            for (; e < e1; e += lanes) {
+                const VecF<V> a = loadv<V>(m + (size_t)e * O);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] += a.v[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = acc.v[j];
+        __syncthreads();
+        if (lane == 0 && q < cg) {
+            for (int l = 1; l < lanes; ++l)
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] += red[(threadIdx.x + l * cgb) * V + j];
+            if (bias) {
+                const VecF<V> b = loadv<V>(bias + V * q);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] += b.v[j];
+            }
+            storev<V>(out + (size_t)row * O + V * q, acc);
+        }
+        __syncthreads();
     }
 }
 
@@ -390,15 +472,25 @@ int launch_rel_transform(const RelArgs& A, int bi, int bo, const XT* X, MT* msg,
     return RGCN_ERR_UNSUPPORTED;
 }
 
-template <typename MT>
-int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
-                   cudaStream_t st) {
-    int64_t total = nrows * (O / 4);
+template <typename MT, int V>
+int launch_row_sum_v(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
+                     const int32_t* long_list, const int32_t* long_count, int64_t num_long, int64_t nnz, cudaStream_t st) {
+    int64_t total = nrows * (O / V);
     int64_t want = (total + 255) / 256;
     int grid = (int)(want < (int64_t)kNumSMs * 32 ? want : (int64_t)kNumSMs * 32);
     if (grid < 1) grid = 1;
-    RGCN_LAUNCH(k_row_sum<MT>, grid, 256, 0, st, rowptr, nrows, O, msg, bias, out);
+    RGCN_LAUNCH((k_row_sum<MT, V>), grid, 256, 0, st, rowptr, nrows, O, msg, bias, out);
+    // exact count when the plan read it back, else the bound: at most nnz / RGCN_LONG_ROW rows can be that long
+    const int bound = num_long >= 0 ? (int)num_long : (int)(nnz / RGCN_LONG_ROW);
+    if (bound > 0) RGCN_LAUNCH((k_row_sum_long<MT, V>), bound, 256, 0, st, rowptr, long_list, long_count, O, msg, bias, out);
     return RGCN_OK;
+}
+
+template <typename MT>
+int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
+                   const int32_t* long_list, const int32_t* long_count, int64_t num_long, int64_t nnz, cudaStream_t st) {
+    if (O % 8 == 0) return launch_row_sum_v<MT, 8>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
+    return launch_row_sum_v<MT, 4>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
 }
 
 template <typename XT, int BI, int BO, int NB>

@@ -31,6 +31,11 @@ struct PropArgs {
     const float* in_mask;     // (N, I): multiplies source rows of relation mask_rel before aggregation
     int mask_rel;
     float* out;
+    const int32_t* long_list;   // rows with more than RGCN_LONG_ROW edges (may be NULL: no special handling)
+    const int32_t* long_count;
+    int long_mode;              // 0: all rows, long rows only get bias; 1: long rows only, split over warps, atomics
+    int64_t nnz_hint;           // nnz (host-side bound on the number of long rows)
+    int64_t num_long;           // exact number of long rows if known on the host, else -1
 };
 
 template <typename XT, int K>
@@ -40,7 +45,13 @@ __global__ void __launch_bounds__(256) k_prop_generic(PropArgs A, const XT* __re
     float* a_s = smem + (size_t)warp * A.I;      // staged segment aggregate (featured forms only)
     const int I = A.I, O = A.O;
 
-    for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < A.nrows; row += (int64_t)gridDim.x * wpb) {
+    // long_mode 1: blockIdx.x = index into the long-row list, the row's edges are split into 256-edge pieces that
+    // the warps of gridDim.y CTAs take round-robin; partial results are added atomically (the sum is linear)
+    const bool long_mode = A.long_mode == 1;
+    if (long_mode && (int)blockIdx.x >= *A.long_count) return;
+    const int64_t row_begin = long_mode ? A.long_list[blockIdx.x] : (int64_t)blockIdx.x * wpb + warp;
+    const int64_t row_step = long_mode ? A.nrows : (int64_t)gridDim.x * wpb;
+    for (int64_t row = row_begin; row < A.nrows; row += row_step) {
         const int e0 = A.rowptr[row], e1 = A.rowptr[row + 1];
         float acc[K], a[K];
 #pragma unroll
@@ -83,51 +94,73 @@ __global__ void __launch_bounds__(256) k_prop_generic(PropArgs A, const XT* __re
             }
         };
 
-        for (int e = e0; e < e1; ++e) {
-            const int r = A.rel[e], c = A.col[e];
-            const float v = A.val[e];
-            if (A.featureless) {
-                if (A.form == RGCN_W_DENSE) {
-                    const float* w = A.W + ((size_t)r * A.N + c) * O;
+        auto walk = [&](int eb, int ee) {
+            for (int e = eb; e < ee; ++e) {
+                const int r = A.rel[e], c = A.col[e];
+                const float v = A.val[e];
+                if (A.featureless) {
+                    if (A.form == RGCN_W_DENSE) {
+                        const float* w = A.W + ((size_t)r * A.N + c) * O;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) { int j = lane + 32 * k; if (j < O) acc[k] += v * w[j]; }
-                } else if (A.form == RGCN_W_BASIS) {
-                    for (int b = 0; b < A.B; ++b) {
-                        const float cb = v * A.comps[(size_t)r * A.B + b];
-                        const float* w = A.bases + ((size_t)b * A.N + c) * O;
+                        for (int k = 0; k < K; ++k) { int j = lane + 32 * k; if (j < O) acc[k] += v * w[j]; }
+                    } else if (A.form == RGCN_W_BASIS) {
+                        for (int b = 0; b < A.B; ++b) {
+                            const float cb = v * A.comps[(size_t)r * A.B + b];
+                            const float* w = A.bases + ((size_t)b * A.N + c) * O;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) { int j = lane + 32 * k; if (j < O) acc[k] += cb * w[j]; }
+                            for (int k = 0; k < K; ++k) { int j = lane + 32 * k; if (j < O) acc[k] += cb * w[j]; }
+                        }
+                    } else {   // BLOCK: row c of blockdiag(blocks[r]) lives in block c / bi, columns [kb*bo, kb*bo+bo)
+                        const int kb = c / A.bi, ii = c - kb * A.bi;
+                        const float* w = A.blocks + (((size_t)r * A.nb + kb) * A.bi + ii) * A.bo;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            int j = lane + 32 * k, jj = j - kb * A.bo;
+                            if (j < O && jj >= 0 && jj < A.bo) acc[k] += v * w[jj];
+                        }
                     }
-                } else {   // BLOCK: row c of blockdiag(blocks[r]) lives in block c / bi, columns [kb*bo, kb*bo+bo)
-                    const int kb = c / A.bi, ii = c - kb * A.bi;
-                    const float* w = A.blocks + (((size_t)r * A.nb + kb) * A.bi + ii) * A.bo;
+                    continue;
+                }
+                if (r != cur) {
+                    if (cur >= 0) transform(cur);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        int j = lane + 32 * k, jj = j - kb * A.bo;
-                        if (j < O && jj >= 0 && jj < A.bo) acc[k] += v * w[jj];
+                    for (int k = 0; k < K; ++k) a[k] = 0.f;
+                    cur = r;
+                }
+                const XT* xr = X + (size_t)c * I;
+                const float* mr = (A.in_mask && r == A.mask_rel) ? A.in_mask + (size_t)c * I : nullptr;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    int i = lane + 32 * k;
+                    if (i < I) {
+                        float x = to_f32(xr[i]);
+                        if (mr) x *= mr[i];
+                        a[k] += v * x;
                     }
                 }
-                continue;
             }
-            if (r != cur) {
-                if (cur >= 0) transform(cur);
-#pragma unroll
-                for (int k = 0; k < K; ++k) a[k] = 0.f;
-                cur = r;
+            if (cur >= 0) transform(cur);
+            cur = -1;
+        };
+
+        if (long_mode) {
+            const int nsplit = (e1 - e0 + 255) / 256, nwarps = gridDim.y * wpb;
+            bool any = false;
+            for (int sp = blockIdx.y * wpb + warp; sp < nsplit; sp += nwarps) {
+                walk(e0 + sp * 256, min(e1, e0 + (sp + 1) * 256));
+                any = true;
             }
-            const XT* xr = X + (size_t)c * I;
-            const float* mr = (A.in_mask && r == A.mask_rel) ? A.in_mask + (size_t)c * I : nullptr;
+            if (any) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                int i = lane + 32 * k;
-                if (i < I) {
-                    float x = to_f32(xr[i]);
-                    if (mr) x *= mr[i];
-                    a[k] += v * x;
+                for (int k = 0; k < K; ++k) {
+                    int j = lane + 32 * k;
+                    if (j < O) atomicAdd(A.out + (size_t)row * O + j, acc[k]);
                 }
             }
+            continue;
         }
-        if (cur >= 0) transform(cur);
+        const bool is_long = A.long_list && (e1 - e0 > RGCN_LONG_ROW);   // handled by the long_mode launch
+        if (!is_long) walk(e0, e1);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             int j = lane + 32 * k;

@@ -481,12 +481,14 @@ __device__ __forceinline__ void ldcg8(const __nv_bfloat16* p, float (&f)[8]) {
 // Thread = 8 columns of one row; 4 independent 16-byte loads in flight per thread.
 __device__ __forceinline__ void row_sum_block(const int32_t* __restrict__ rowptr, int r0, int r1, int width,
                                               const __nv_bfloat16* __restrict__ ring_slot, int slot_bias,
-                                              const float* __restrict__ bias, float* __restrict__ out) {
+                                              const float* __restrict__ bias, float* __restrict__ out,
+                                              float* scratch) {
     const int cg = width >> 3;
     const int total = (r1 - r0) * cg;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int row = r0 + idx / cg, q = idx % cg;
         const int e0 = rowptr[row] - slot_bias, e1 = rowptr[row + 1] - slot_bias;
+        if (e1 - e0 > RGCN_LONG_ROW) continue;                  // hub rows: cooperative pass below
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const __nv_bfloat16* m = ring_slot + (size_t)e0 * width + 8 * q;
         int e = e0;
@@ -511,6 +513,35 @@ __device__ __forceinline__ void row_sum_block(const int32_t* __restrict__ rowptr
         float4* o = reinterpret_cast<float4*>(out + (size_t)row * width + 8 * q);
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    // hub rows: the whole CTA sums one row (edge-parallel), partials reduced through `scratch` (256 x 8 floats)
+    const int lanes = 256 / cg, q = threadIdx.x % cg, lane = threadIdx.x / cg;      // cg <= 64 (width <= 512)
+    for (int row = r0; row < r1; ++row) {
+        const int e0 = rowptr[row] - slot_bias, e1 = rowptr[row + 1] - slot_bias;
+        if (e1 - e0 <= RGCN_LONG_ROW) continue;                 // uniform across the CTA
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (lane < lanes)
+            for (int e = e0 + lane; e < e1; e += lanes) {
+                float a[8];
+                ldcg8(ring_slot + (size_t)e * width + 8 * q, a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += a[j];
+            }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scratch[threadIdx.x * 8 + j] = acc[j];
+        __syncthreads();
+        if (lane == 0) {
+            for (int l = 1; l < lanes; ++l)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += scratch[(threadIdx.x + l * cg) * 8 + j];
+            if (bias)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += bias[8 * q + j];
+            float4* o = reinterpret_cast<float4*>(out + (size_t)row * width + 8 * q);
+            o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
 }
 
@@ -556,7 +587,8 @@ __global__ void __launch_bounds__(256) k_tiled_mma_fwd(TiledArgs A, const __nv_b
             signal_done(A.done1 + k);
         } else {
             wait_count(A.done1 + k, it.need, A.status);
-            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, A.bias, out);
+            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, A.bias, out,
+                          reinterpret_cast<float*>(smem_tiled_fwd));
             signal_done(A.slot_done + (k % A.depth));
         }
     }
@@ -581,7 +613,8 @@ __global__ void __launch_bounds__(256, 2) k_tiled_mma_bwd(TiledArgs A, const __n
             signal_done(A.done1 + k);
         } else {
             wait_count(A.done1 + k, it.need, A.status);
-            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, nullptr, gX);
+            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, nullptr, gX,
+                          reinterpret_cast<float*>(smem_tiled_bwd));
             signal_done(A.slot_done + (k % A.depth));
         }
     }

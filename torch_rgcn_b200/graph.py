@@ -39,11 +39,14 @@ class GraphPlan:
          self.r_sslot) = self._ints.unbind(0)
         self.r_chunkptr = torch.empty(num_rels + 1, **i32)
         self.d_val, self.s_val, self.r_val, self.val = self._floats.unbind(0)
-        self.status = torch.zeros(4, **i32)
+        self.status = torch.zeros(8, **i32)
+        self.d_long = torch.empty(nnz // 512 + 1, **i32)
+        self.s_long = torch.empty(nnz // 512 + 1, **i32)
         g = _lib.Graph()
         g.num_nodes, g.num_rels, g.nnz = num_nodes, num_rels, nnz
         for name in ('d_rowptr', 'd_src', 'd_rel', 'd_val', 's_rowptr', 's_dst', 's_rel', 's_val',
-                     'r_relptr', 'r_dst', 'r_src', 'r_val', 'r_dslot', 'r_sslot', 'r_chunkptr', 'val', 'status'):
+                     'r_relptr', 'r_dst', 'r_src', 'r_val', 'r_dslot', 'r_sslot', 'r_chunkptr', 'val', 'status',
+                     'd_long', 's_long'):
             setattr(g, name, getattr(self, name).data_ptr())
         # optional super-tiling for the L2-resident message ring (see include/rgcn_b200.h: rgcn_tiling)
         self.tile_edges = int(tile_edges) if nnz > 0 else 0
@@ -63,6 +66,7 @@ class GraphPlan:
                 self._tiling.append(arrs)
                 for k, v in arrs.items():
                     setattr(tl, k, v.data_ptr())
+        g.num_long_dst = g.num_long_src = -1
         self.c = g
         if val is not None:
             val = val.to(device=dev, dtype=torch.float32).contiguous()
@@ -73,17 +77,13 @@ class GraphPlan:
             _lib.check(_lib.lib.rgcn_graph_build(_lib.ptr(t), nnz, num_nodes, num_rels, norm, int(n_general),
                                                  int(n_self), _lib.ptr(val), C.byref(g), _lib.ptr(ws), ws_bytes,
                                                  _lib.stream_ptr()))
-        if self.tile_edges > 0:
-            st = self.status.tolist()
+        if self.tile_edges > 0 or validate:
+            st = self.status.tolist()               # one host sync per plan build (the reference's asserts sync too)
             g.tile_capacity = self.tile_capacity = max(st[1], st[2])
+            g.num_long_dst, g.num_long_src = st[4], st[5]
             bad = st[0]
             assert bad == 0 or not validate, f'{bad} triples have a node or relation id out of range ' \
                                              f'(num_nodes={num_nodes}, num_relations={num_rels})'
-        elif validate:
-            bad = int(self.status[0].item())
-            # the reference asserts index bounds in stack_matrices (utils.py:163-164)
-            assert bad == 0, f'{bad} triples have a node or relation id out of range ' \
-                             f'(num_nodes={num_nodes}, num_relations={num_rels})'
 
     def relation_counts(self):
         """Edges per relation (host tensor), e.g. for the relation shard planner."""

@@ -52,17 +52,25 @@ class _CopyToShards(torch.autograd.Function):
 
 
 class _ReduceFromShards(torch.autograd.Function):
-    """All-reduce(sum) forward; identity backward (the upstream gradient is replicated)."""
+    """All-reduce(sum) forward; identity backward (the upstream gradient is replicated).
+
+    comm_dtype=torch.bfloat16 sends the partial sums in bf16 (half the NVLink bytes); used for bf16-feature layers,
+    whose per-edge messages are bf16 already.  The result is returned in the input dtype.
+    """
 
     @staticmethod
-    def forward(ctx, x, group):
+    def forward(ctx, x, group, comm_dtype=None):
+        if comm_dtype is not None and comm_dtype != x.dtype:
+            y = x.to(comm_dtype)
+            dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+            return y.to(x.dtype)
         x = x.contiguous()
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         return x
 
     @staticmethod
     def backward(ctx, g):
-        return g, None
+        return g, None, None
 
 
 class RelationShardedNC(torch.nn.Module):
@@ -124,7 +132,8 @@ class RelationShardedNC(torch.nn.Module):
         # bias enters the sum exactly once: rank 0's kernel adds it, every rank gets its (replicated) gradient
         out = _Propagate.apply(plan, form, in_dim, L.out_features, features, kw['weights'], kw['bases'], kw['comps'],
                                kw['blocks'], None, L.bias, None, self.rank == 0)
-        return _ReduceFromShards.apply(out, self.group)
+        comm = torch.bfloat16 if (features is not None and features.dtype == torch.bfloat16) else None
+        return _ReduceFromShards.apply(out, self.group, comm)
 
     def sync_parameter_grads(self):
         for name, p in self.layer.named_parameters():
