@@ -31,9 +31,10 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 7
+#define RGCN_ABI_VERSION 8
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
+#define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
 #define RGCN_MAX_RING_DEPTH 64        /* upper bound on rgcn_graph.ring_depth */
 #define RGCN_LONG_ROW 512             /* rows with more edges are listed in d_long / s_long and processed cooperatively */
 
@@ -106,17 +107,16 @@ int rgcn_block_diag(const float* blocks, int64_t num_rels, int64_t num_blocks, i
  * (layers.py:255-279 / :490-516).  All arrays are caller-allocated device memory.
  * ---------------------------------------------------------------------------------------- */
 /* Optional super-tiling of the rows (destination rows for the forward, source rows for the backward) so that
- * the per-edge messages of one tile fit an L2-resident ring.  Tile of row r = rowptr[r] / tile_edges.
- * Edges are sorted by (tile, relation, row); "group" g = tile * R' + relation. */
+ * the per-edge messages of one tile fit a small ring that stays in L2.  Tile of row r = rowptr[r] / tile_edges.
+ * Edges are sorted by (tile, relation, row); tile k owns positions [rowptr[tilerow[k]], rowptr[tilerow[k+1]]). */
 typedef struct rgcn_tiling {
     int32_t* tilerow;       /* T+1: first row of every tile (tilerow[T] = N) */
-    int32_t* grpptr;        /* T*R'+1: edge range of every group */
-    int32_t* chunkptr;      /* T*R'+1: chunk range of every group (RGCN_CHUNK_EDGES edges per chunk) */
     int32_t* row;           /* nnz: tile-side endpoint (forward: subject s, backward: object o) */
-    int32_t* col;           /* nnz: the other endpoint */
+    int32_t* col;           /* nnz: the other endpoint (the row that is gathered) */
+    int32_t* rel;           /* nnz: relation */
     int32_t* slot;          /* nnz: position of the edge in the row-major CSR of the tile side */
     float* val;             /* nnz */
-    int32_t* stepptr;       /* T+lag+1: work-queue prefix: step j = chunks of tile j, then row blocks of tile j-lag,
+    int32_t* stepptr;       /* T+lag+1: work-queue prefix: step j = spans of tile j, then row blocks of tile j-lag,
                                lag = ring_depth / 2 (a tile is summed only after `lag` later tiles were queued) */
     int32_t* slotneed;      /* T: row blocks of the earlier tiles that share ring slot k % ring_depth */
     int32_t* items;         /* 8 x int32 per work-queue item (see rgcn_tile_item), capacity = rgcn_tile_items_bound() */
@@ -124,11 +124,11 @@ typedef struct rgcn_tiling {
 
 /* one entry of the tiled kernels' in-order work queue */
 typedef struct rgcn_tile_item {
-    int32_t kind;           /* 0 = transform chunk, 1 = row-sum block */
+    int32_t kind;           /* 0 = transform span (<= RGCN_SPAN_EDGES consecutive edges of a tile), 1 = row-sum block */
     int32_t tile;
-    int32_t a;              /* chunk: relation        | row block: first row */
-    int32_t b;              /* chunk: first edge      | row block: end row   */
-    int32_t c;              /* chunk: number of edges | row block: unused    */
+    int32_t a;              /* span: unused          | row block: first row */
+    int32_t b;              /* span: first edge      | row block: end row   */
+    int32_t c;              /* span: number of edges | row block: unused    */
     int32_t slot_bias;      /* first CSR position of the tile (message row 0 of its ring slot) */
     int32_t need;           /* counter value to wait for before starting */
     int32_t pad;
@@ -148,7 +148,7 @@ typedef struct rgcn_graph {
     int32_t* s_dst;         /* nnz: subject s */
     int32_t* s_rel;         /* nnz */
     float* s_val;           /* nnz */
-    /* relation-major list, sorted by (p, s, o) — weight-gradient walk */
+    /* relation-major list, sorted by (p, o, s) — relation-batched kernels (gathers walk X rows in order) */
     int32_t* r_relptr;      /* R'+1 */
     int32_t* r_dst;         /* nnz */
     int32_t* r_src;         /* nnz */

@@ -21,8 +21,8 @@ _i64 = C.c_int64
 
 
 class Tiling(C.Structure):
-    _fields_ = [('tilerow', _p), ('grpptr', _p), ('chunkptr', _p), ('row', _p), ('col', _p), ('slot', _p),
-                ('val', _p), ('stepptr', _p), ('slotneed', _p), ('items', _p)]
+    _fields_ = [('tilerow', _p), ('row', _p), ('col', _p), ('rel', _p), ('slot', _p), ('val', _p),
+                ('stepptr', _p), ('slotneed', _p), ('items', _p)]
 
 
 class Graph(C.Structure):

@@ -105,7 +105,7 @@ __global__ void k_block_diag(const float* __restrict__ b, int64_t R, int64_t nb,
 // ------------------------------------------------------------------------------------------
 enum Ordering { ORD_DST = 0, ORD_SRC = 1, ORD_REL = 2 };
 
-// key layouts: DST (s*R'+p)*N+o, SRC (o*R'+p)*N+s, REL (p*N+s)*N+o
+// key layouts: DST (s*R'+p)*N+o, SRC (o*R'+p)*N+s, REL (p*N+o)*N+s (gathers of X[o] walk rows in order)
 __global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int ord,
                             uint64_t* __restrict__ keys, int32_t* __restrict__ idx, int32_t* status) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -118,7 +118,7 @@ __global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t 
     uint64_t k;
     if (ord == ORD_DST) k = ((uint64_t)s * Rp + p) * N + o;
     else if (ord == ORD_SRC) k = ((uint64_t)o * Rp + p) * N + s;
-    else k = ((uint64_t)p * N + s) * N + o;
+    else k = ((uint64_t)p * N + o) * N + s;
     keys[e] = k;
     idx[e] = (int32_t)e;
 }
@@ -132,10 +132,10 @@ __global__ void k_decode(const uint64_t* __restrict__ keys, int64_t nnz, int64_t
     uint64_t k = keys[e];
     int64_t row, prev;
     if (ord == ORD_REL) {
-        uint64_t ps = k / N;                 // p*N + s
-        row = (int64_t)(ps / N);
-        c0[e] = (int32_t)(ps % N);           // dst s
-        c1[e] = (int32_t)(k % N);            // src o
+        uint64_t po = k / N;                 // p*N + o
+        row = (int64_t)(po / N);
+        c0[e] = (int32_t)(k % N);            // dst s
+        c1[e] = (int32_t)(po % N);           // src o
         prev = e ? (int64_t)(keys[e - 1] / N / N) : -1;
     } else {
         uint64_t ap = k / N;                 // a*R' + p
@@ -147,11 +147,6 @@ __global__ void k_decode(const uint64_t* __restrict__ keys, int64_t nnz, int64_t
     for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = (int32_t)e;
     if (e == nnz - 1)
         for (int64_t r = row + 1; r <= nrows; ++r) rowptr[r] = (int32_t)nnz;
-}
-
-__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
 }
 
 // segment = run of equal key / N in the sorted list ((s,p) for DST, (o,p) for SRC)
@@ -248,24 +243,20 @@ __global__ void k_make_tile_keys(const int64_t* __restrict__ t, int64_t nnz, int
 
 __global__ void k_decode_tiles(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
                                const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
-                               int64_t ngroups, const int32_t* __restrict__ inv, const float* __restrict__ val,
-                               int32_t* __restrict__ grpptr, int32_t* __restrict__ row, int32_t* __restrict__ col,
+                               const int32_t* __restrict__ inv, const float* __restrict__ val,
+                               int32_t* __restrict__ row, int32_t* __restrict__ col, int32_t* __restrict__ rel,
                                int32_t* __restrict__ slot, float* __restrict__ oval) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     const uint64_t k = keys[e];
-    const int64_t grp = (int64_t)(k / N);
     const int32_t orig = perm[e];
     int64_t s = t[3 * (int64_t)orig], p = t[3 * (int64_t)orig + 1], o = t[3 * (int64_t)orig + 2];
     if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
     row[e] = (int32_t)(k % N);
     col[e] = (int32_t)(backward ? s : o);
+    rel[e] = (int32_t)((k / N) % Rp);
     slot[e] = inv[orig];
     oval[e] = val[orig];
-    const int64_t prev = e ? (int64_t)(keys[e - 1] / N) : -1;
-    for (int64_t g = prev + 1; g <= grp; ++g) grpptr[g] = (int32_t)e;
-    if (e == nnz - 1)
-        for (int64_t g = grp + 1; g <= ngroups; ++g) grpptr[g] = (int32_t)nnz;
 }
 
 // tilerow[k] = first row whose tile id is >= k; tilerow[T] = N
@@ -281,23 +272,17 @@ __global__ void k_tile_rows(const int32_t* __restrict__ rowptr, int64_t N, int64
         for (int64_t k = tile + 1; k <= T; ++k) tilerow[k] = (int32_t)N;
 }
 
-__global__ void k_group_chunks(const int32_t* __restrict__ grpptr, int64_t ngroups, int32_t* __restrict__ cnt) {
-    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g < ngroups) cnt[g] = (grpptr[g + 1] - grpptr[g] + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
-    else if (g == ngroups) cnt[g] = 0;
-}
-
 // per-tile capacity (atomicMax) and the work-queue prefix over steps:
-// step j = chunks of tile j (j < T) + row blocks of tile j - lag (lag <= j < T + lag)
-__global__ void k_tile_steps(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tilerow,
-                             const int32_t* __restrict__ chunkptr, int64_t T, int64_t Rp, int64_t lag,
-                             int32_t* __restrict__ stepcnt, int32_t* cap) {
+// step j = spans of tile j (j < T) + row blocks of tile j - lag (lag <= j < T + lag)
+__global__ void k_tile_steps(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tilerow, int64_t T,
+                             int64_t lag, int32_t* __restrict__ stepcnt, int32_t* cap) {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j > T + lag) return;
     int32_t n = 0;
     if (j < T) {
-        n += chunkptr[(j + 1) * Rp] - chunkptr[j * Rp];
-        atomicMax(cap, rowptr[tilerow[j + 1]] - rowptr[tilerow[j]]);
+        const int32_t edges = rowptr[tilerow[j + 1]] - rowptr[tilerow[j]];
+        n += (edges + RGCN_SPAN_EDGES - 1) / RGCN_SPAN_EDGES;
+        atomicMax(cap, edges);
     }
     if (j >= lag && j < T + lag) {
         const int32_t rows = tilerow[j - lag + 1] - tilerow[j - lag];
@@ -317,11 +302,10 @@ __global__ void k_slot_need(const int32_t* __restrict__ tilerow, int64_t T, int 
     }
 }
 
-// work-queue item table: item q of step j is a transform chunk of tile j (first) or a row block of tile j-1
-__global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t* __restrict__ chunkptr,
-                             const int32_t* __restrict__ grpptr, const int32_t* __restrict__ tilerow,
+// work-queue item table: item q of step j is a transform span of tile j (first) or a row block of tile j - lag
+__global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t* __restrict__ tilerow,
                              const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slotneed,
-                             int64_t T, int64_t Rp, int64_t lag, int64_t bound, rgcn_tile_item* __restrict__ items) {
+                             int64_t T, int64_t lag, int64_t bound, rgcn_tile_item* __restrict__ items) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= bound || q >= stepptr[T + lag]) return;
     int64_t lo = 0, hi = T + lag;                   // stepptr[lo] <= q < stepptr[hi]
@@ -330,28 +314,25 @@ __global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t*
         if (stepptr[mid] <= q) lo = mid; else hi = mid;
     }
     const int local = (int)(q - stepptr[lo]);
-    const int n1 = lo < T ? chunkptr[(lo + 1) * Rp] - chunkptr[lo * Rp] : 0;
+    int n1 = 0, t0 = 0, t1 = 0;
+    if (lo < T) {
+        t0 = rowptr[tilerow[lo]]; t1 = rowptr[tilerow[lo + 1]];
+        n1 = (t1 - t0 + RGCN_SPAN_EDGES - 1) / RGCN_SPAN_EDGES;
+    }
     rgcn_tile_item it;
-    it.pad = 0;
+    it.pad = 0; it.a = 0;
     if (local < n1) {
-        const int64_t k = lo;
-        const int c = chunkptr[k * Rp] + local;
-        int64_t glo = k * Rp, ghi = (k + 1) * Rp;   // chunkptr[glo] <= c < chunkptr[ghi]
-        while (ghi - glo > 1) {
-            int64_t mid = (glo + ghi) >> 1;
-            if (chunkptr[mid] <= c) glo = mid; else ghi = mid;
-        }
-        const int e0 = grpptr[glo] + (c - chunkptr[glo]) * RGCN_CHUNK_EDGES;
-        const int e1 = min(grpptr[glo + 1], e0 + RGCN_CHUNK_EDGES);
-        it.kind = 0; it.tile = (int)k; it.a = (int)(glo - k * Rp); it.b = e0; it.c = e1 - e0;
-        it.slot_bias = rowptr[tilerow[k]];
-        it.need = slotneed[k];
+        const int e0 = t0 + local * RGCN_SPAN_EDGES;
+        it.kind = 0; it.tile = (int)lo; it.b = e0; it.c = min(t1, e0 + RGCN_SPAN_EDGES) - e0;
+        it.slot_bias = t0;
+        it.need = slotneed[lo];
     } else {
         const int64_t k = lo - lag;
         const int r0 = tilerow[k] + (local - n1) * RGCN_TILE_ROWS_PER_ITEM;
+        const int k0 = rowptr[tilerow[k]], k1 = rowptr[tilerow[k + 1]];
         it.kind = 1; it.tile = (int)k; it.a = r0; it.b = min(tilerow[k + 1], r0 + RGCN_TILE_ROWS_PER_ITEM); it.c = 0;
-        it.slot_bias = rowptr[tilerow[k]];
-        it.need = chunkptr[(k + 1) * Rp] - chunkptr[k * Rp];
+        it.slot_bias = k0;
+        it.need = (k1 - k0 + RGCN_SPAN_EDGES - 1) / RGCN_SPAN_EDGES;
     }
     items[q] = it;
 }
@@ -474,7 +455,8 @@ static int64_t tile_groups(int64_t nnz, int64_t Rp, int64_t tile_edges) {
 extern "C" int64_t rgcn_tile_items_bound(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges) {
     if (tile_edges <= 0 || nnz <= 0) return 0;
     const int64_t T = (nnz - 1) / tile_edges + 1;
-    return nnz / RGCN_CHUNK_EDGES + T * Rp + N / RGCN_TILE_ROWS_PER_ITEM + T + 2;
+    (void)Rp;
+    return nnz / RGCN_SPAN_EDGES + T + N / RGCN_TILE_ROWS_PER_ITEM + T + 2;
 }
 
 extern "C" int64_t rgcn_tile_steps_len(int64_t nnz, int64_t tile_edges, int64_t ring_depth) {
@@ -579,28 +561,25 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         RGCN_REQUIRE(tbits <= 63, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: tile key does not fit 64 bits");
         for (int backward = 0; backward < 2; ++backward) {
             rgcn_tiling& tl = backward ? g->bt : g->ft;
-            RGCN_REQUIRE(tl.tilerow && tl.grpptr && tl.chunkptr && tl.row && tl.col && tl.slot && tl.val && tl.stepptr && tl.slotneed && tl.items,
+            RGCN_REQUIRE(tl.tilerow && tl.row && tl.col && tl.rel && tl.slot && tl.val && tl.stepptr && tl.slotneed && tl.items,
                          RGCN_ERR_ARG, "rgcn_graph_build: NULL tiling array");
             const int32_t* rowptr = backward ? g->s_rowptr : g->d_rowptr;
             RGCN_LAUNCH(k_make_tile_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, rowptr, te, b.k0, b.i0);
             size_t cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, tbits, stream));
             rgcn::g_launches.fetch_add((tbits + 7) / 8 + 1, std::memory_order_relaxed);
-            RGCN_LAUNCH(k_decode_tiles, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, ngroups,
-                        backward ? b.inv_s : b.inv_d, g->val, tl.grpptr, tl.row, tl.col, tl.slot, tl.val);
+            RGCN_LAUNCH(k_decode_tiles, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward,
+                        backward ? b.inv_s : b.inv_d, g->val, tl.row, tl.col, tl.rel, tl.slot, tl.val);
             RGCN_LAUNCH(k_tile_rows, grid_for(N, kBlock), kBlock, 0, stream, rowptr, N, te, T, tl.tilerow);
             RGCN_LAUNCH(k_slot_need, 1, 64, 0, stream, tl.tilerow, T, (int)depth, tl.slotneed);
-            RGCN_LAUNCH(k_group_chunks, grid_for(ngroups + 1, kBlock), kBlock, 0, stream, tl.grpptr, ngroups, b.flag);
-            cub_bytes = b.cub_bytes;
-            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.flag, tl.chunkptr, (int)(ngroups + 1), stream));
-            RGCN_LAUNCH(k_tile_steps, grid_for(T + lag + 1, kBlock), kBlock, 0, stream, rowptr, tl.tilerow, tl.chunkptr, T,
-                        Rp, lag, b.segid, g->status + 1 + backward);
+            RGCN_LAUNCH(k_tile_steps, grid_for(T + lag + 1, kBlock), kBlock, 0, stream, rowptr, tl.tilerow, T, lag, b.segid,
+                        g->status + 1 + backward);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.segid, tl.stepptr, (int)(T + lag + 1), stream));
-            rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
+            rgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
             const int64_t bound = rgcn_tile_items_bound(nnz, N, Rp, te);
-            RGCN_LAUNCH(k_fill_items, grid_for(bound, kBlock), kBlock, 0, stream, tl.stepptr, tl.chunkptr, tl.grpptr,
-                        tl.tilerow, rowptr, tl.slotneed, T, Rp, lag, bound, reinterpret_cast<rgcn_tile_item*>(tl.items));
+            RGCN_LAUNCH(k_fill_items, grid_for(bound, kBlock), kBlock, 0, stream, tl.stepptr, tl.tilerow, rowptr, tl.slotneed,
+                        T, lag, bound, reinterpret_cast<rgcn_tile_item*>(tl.items));
         }
     }
     return RGCN_OK;

@@ -208,7 +208,8 @@ extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_p
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
     size_t bytes = 0;
     if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
-    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O);
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
+        return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
     if (rel_path(p, s, x_dtype == RGCN_BF16, false, &rs, &msg)) bytes += msg;
     return bytes;
@@ -244,9 +245,12 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     if (tiled_path(g, p, s, bf16)) {
         int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
         __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.O)));
+        uint32_t* frag = reinterpret_cast<uint32_t*>(carve.take<char>(wfrag_bytes(s.Rp, s.nb)));
         RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
-        TiledArgs T = make_tiled_args(g, false, s.nb, p->blocks, p->bias, counters);
-        return launch_tiled_mma_fwd(T, static_cast<const __nv_bfloat16*>(X), ring, out, st);
+        rc = launch_pack_wfrag(p->blocks, s.Rp, s.nb, false, frag, st);
+        if (rc) return rc;
+        TiledArgs T = make_tiled_args(g, false, s.nb, frag, p->bias, counters);
+        return launch_tiled_span(T, static_cast<const __nv_bfloat16*>(X), ring, out, st);
     }
     RelShape rs; size_t msg_bytes = 0;
     if (rel_path(p, s, bf16, false, &rs, &msg_bytes)) {
@@ -290,7 +294,8 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
         default: break;
     }
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
-    if (tiled_path(g, p, s, x_dtype == RGCN_BF16)) return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I);
+    if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
+        return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
     if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32 upper bound)
     return bytes;
@@ -324,12 +329,22 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         rc = launch_cast_colsum(G, s.N, s.O, gb16, gr->bias, st);
         if (rc) return rc;
         if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
-        if (tiled_bwd) {      // feature-gradient messages stay in an L2-resident ring
+        if (tiled_bwd) {
+            // weight gradient: untiled relation-major pass (needs full relation batches); feature gradient: span kernel
+            // on the source tiling with W^T fragments, messages stay in the ring
+            if (gr->blocks) {
+                RelArgs Rw{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, nullptr, g->r_val, p->blocks, s.nb};
+                rc = launch_rel_mma_bwd(Rw, static_cast<const __nv_bfloat16*>(X), gb16, nullptr, gr->blocks, max_chunks(s), st);
+                if (rc) return rc;
+            }
             int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
             __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.I)));
+            uint32_t* frag = reinterpret_cast<uint32_t*>(carve.take<char>(wfrag_bytes(s.Rp, s.nb)));
             RGCN_CHECK_CUDA(cudaMemsetAsync(counters, 0, tiled_counter_bytes(g->num_tiles), st));
-            TiledArgs T = make_tiled_args(g, true, s.nb, p->blocks, nullptr, counters);
-            return launch_tiled_mma_bwd(T, static_cast<const __nv_bfloat16*>(X), gb16, ring, gr->features, gr->blocks, st);
+            rc = launch_pack_wfrag(p->blocks, s.Rp, s.nb, true, frag, st);
+            if (rc) return rc;
+            TiledArgs T = make_tiled_args(g, true, s.nb, frag, nullptr, counters);
+            return launch_tiled_span(T, gb16, ring, gr->features, st);
         }
         RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
         __nv_bfloat16* msg = nullptr;

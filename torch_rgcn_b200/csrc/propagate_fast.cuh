@@ -8,12 +8,15 @@
 //   k_rel_transform : msg[slot(e)] = val_e * X[src_e] @ W_p        (gather rows, per-block FMA, scatter rows)
 //   k_row_sum       : out[row] = bias + sum of the row's messages  (slot order == row-major order, so this is
 //                                                                   a contiguous streaming segmented sum)
-//   k_rel_wgrad     : gW_p += sum_e val_e X[src_e]^T G[dst_e]      (cp.async-staged rows, 8x8 register tiles)
+//   k_row_sum_long  : the same for hub rows (> RGCN_LONG_ROW messages): one CTA per row, edge-parallel
+//   k_rel_wgrad     : gW_p += sum_e val_e X[src_e]^T G[dst_e]      (cp.async-staged rows, 8x8 register tiles,
+//                                                                   compile-time shapes, shuffle split-K reduction)
 //
 // The same two kernels serve the feature gradient: walk with (gather = dst, slot = source-major position),
-// transposed weights and the upstream gradient as the feature matrix.
+// transposed weights and the upstream gradient as the feature matrix.  These are the exact-fp32 kernels; bf16
+// features with 16x16 blocks use the tensor-core kernels of propagate_mma.cuh.
 //
-// Return convention of the try_* dispatchers: 0 = launched, < 0 = error, > 0 = shape not served here.
+// Return convention of the launch_* dispatchers: 0 = launched, < 0 = error, > 0 = shape not instantiated here.
 #pragma once
 #include "common.cuh"
 #include "propagate_generic.cuh"
@@ -169,7 +172,7 @@ template <int V>
 __device__ __forceinline__ VecF<V> loadv(const __nv_bfloat16* p) {
     VecF<V> r;
     if constexpr (V == 8) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p));      // messages are read exactly once
         unpack_bf16x2(a.x, r.v[0], r.v[1]); unpack_bf16x2(a.y, r.v[2], r.v[3]);
         unpack_bf16x2(a.z, r.v[4], r.v[5]); unpack_bf16x2(a.w, r.v[6], r.v[7]);
     } else {

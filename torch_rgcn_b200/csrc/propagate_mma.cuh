@@ -145,7 +145,7 @@ __device__ __forceinline__ void mma_fwd_chunk(const Chunk& C, const float* __res
             const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
             if (le < n) {
                 const uint4 v = *reinterpret_cast<const uint4*>(st + tile_off(row, chunk));
-                *reinterpret_cast<uint4*>(Mb + (size_t)s_slot[le] * row_bytes + chunk * 16) = v;
+                __stcs(reinterpret_cast<uint4*>(Mb + (size_t)s_slot[le] * row_bytes + chunk * 16), v);   // streaming: read once, later
             }
         }
         __syncwarp();                                   // before a later issue() refills this stage
@@ -330,7 +330,7 @@ __device__ __forceinline__ void mma_bwd_chunk(const Chunk& C, const float* __res
                 const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
                 if (le < n) {
                     const uint4 v = *reinterpret_cast<const uint4*>(st + tile_off(row, chunk));
-                    *reinterpret_cast<uint4*>(Mb + (size_t)s_slot[le] * xrow_bytes + chunk * 16) = v;
+                    __stcs(reinterpret_cast<uint4*>(Mb + (size_t)s_slot[le] * xrow_bytes + chunk * 16), v);
                 }
             }
         }
@@ -423,27 +423,53 @@ __global__ void __launch_bounds__(256, GBF16 ? 2 : 1) k_rel_mma_bwd(RelArgs A, c
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Persistent tiled drivers: in-order work queue over row super-tiles, messages in an L2-resident ring.
-//   step j of the queue = [transform chunks of tile j] then [row-sum blocks of tile j-1]
-//   a row-sum block of tile k waits until all chunks of tile k are done (done1[k]);
-//   a chunk of tile k waits until every earlier tile that used ring slot k % depth has been summed: per-slot
+// Persistent tiled driver: in-order work queue over row super-tiles, messages in a small ring that stays in L2.
+//   step j of the queue = [transform spans of tile j] then [row-sum blocks of tile j - lag]
+//   a row-sum block of tile k waits until all spans of tile k are done (done1[k]);
+//   a span of tile k waits until every earlier tile that used ring slot k % depth has been summed: per-slot
 //   counter slot_done[k % depth] >= slotneed[k] (a per-tile "tile k-depth is done" test is NOT enough: empty
 //   tiles in between break the chain).
 // Items are claimed in order, so a waiting CTA only ever waits for items held by running CTAs: no deadlock.
+//
+// A span is up to 1024 consecutive edges of a tile in (relation, row) order and may cross relation boundaries:
+// each warp walks a contiguous run of 16-edge MMA tiles and reloads its (pre-packed, bf16) weight fragments when
+// the relation changes; a 16-edge tile that straddles relations is multiplied once per relation run and every
+// row keeps the result of its own relation.  The same kernel serves the forward (X, W) and the feature-gradient
+// messages (bf16 copy of grad_out, W^T).
 // ------------------------------------------------------------------------------------------------------
 struct TiledArgs {
     rgcn_tiling tl;
     const int32_t* rowptr;     // CSR of the tile side (d_rowptr forward, s_rowptr backward)
-    int T, Rp, nb, depth;
-    int total_items;           // filled in-kernel from stepptr[T + 1]
+    int T, nb, depth;
     long long capacity;        // message rows per ring slot
     int32_t* queue;            // [0]: next item
-    int32_t* done1;            // [T] finished chunks per tile
     int32_t* slot_done;        // [depth] finished row blocks per ring slot
+    int32_t* done1;            // [T] finished spans per tile
     int32_t* status;           // [3] set if a wait gave up (watchdog)
-    const float* W;
+    const uint4* wfrag;        // packed bf16 weight fragments, see k_pack_wfrag
     const float* bias;
 };
+
+// frag[((p * NG + bg) * 32 + lane) * 16 + kb * 4 + h * 2 + r]: the two B-operand registers (r) of block 4bg+kb,
+// output half h, for lane (g = lane / 4, t = lane % 4).  transpose = 0: B[k][n] = W[k][n] (forward);
+// transpose = 1: B[k][n] = W[n][k] (messages of the feature gradient).
+__global__ void k_pack_wfrag(const float* __restrict__ W, int Rp, int nb, int transpose, uint32_t* __restrict__ frag) {
+    const int NG = nb >> 2;
+    const long long total = (long long)Rp * NG * 32 * 16;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int reg = (int)(i & 15), lane = (int)((i >> 4) & 31);
+    const long long pg = i >> 9;                   // p * NG + bg
+    const int bg = (int)(pg % NG);
+    const long long p = pg / NG;
+    const int kb = reg >> 2, h = (reg >> 1) & 1, r = reg & 1;
+    const int g = lane >> 2, t = lane & 3;
+    const float* wb = W + ((size_t)p * nb + (size_t)bg * 4 + kb) * 256;
+    const int n = h * 8 + g, k0 = 2 * t + 8 * r;
+    const float lo = transpose ? wb[n * 16 + k0] : wb[k0 * 16 + n];
+    const float hi = transpose ? wb[n * 16 + k0 + 1] : wb[(k0 + 1) * 16 + n];
+    frag[i] = pack_bf16x2(lo, hi);
+}
 
 __device__ __forceinline__ int ld_acquire(const int32_t* p) {
     int v;
@@ -468,6 +494,143 @@ __device__ __forceinline__ void signal_done(int32_t* counter) {
         __threadfence();
         atomicAdd(counter, 1);
     }
+}
+
+constexpr size_t kSpanSmemBytes = 4 * RGCN_SPAN_EDGES * sizeof(int32_t) + (size_t)8 * kMmaStages * kTileBytes;
+
+struct Span {
+    int n;                     // edges (<= RGCN_SPAN_EDGES)
+    const int32_t* gather;     // rows of the bf16 source matrix
+    const int32_t* rel;
+    const int32_t* slot;
+    const float* val;
+    int slot_bias;
+};
+
+__device__ __forceinline__ void mma_span(const Span& S, const uint4* __restrict__ wfrag, int nb,
+                                         const __nv_bfloat16* __restrict__ X, __nv_bfloat16* __restrict__ msg,
+                                         unsigned char* smem) {
+    const int n = S.n;
+    int32_t* s_src = reinterpret_cast<int32_t*>(smem);
+    int32_t* s_slot = s_src + RGCN_SPAN_EDGES;
+    int32_t* s_rel = s_slot + RGCN_SPAN_EDGES;
+    float* s_val = reinterpret_cast<float*>(s_rel + RGCN_SPAN_EDGES);
+    unsigned char* rings = reinterpret_cast<unsigned char*>(s_val + RGCN_SPAN_EDGES);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_src[i] = S.gather[i]; s_slot[i] = S.slot[i] - S.slot_bias; s_rel[i] = S.rel[i]; s_val[i] = S.val[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int NG = nb >> 2;
+    const int bg = warp % NG, wsub = warp / NG, nsub = 8 / NG;
+    const size_t row_bytes = (size_t)nb * 32;
+    unsigned char* ring = rings + (size_t)warp * kMmaStages * kTileBytes;
+    const int ntiles = (n + 15) >> 4;
+    const int per = (ntiles + nsub - 1) / nsub;      // this warp: contiguous MMA tiles [t0, t1)
+    const int t0 = wsub * per, t1 = min(ntiles, t0 + per);
+    const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X) + (size_t)bg * 128;
+    unsigned char* Mb = reinterpret_cast<unsigned char*>(msg) + (size_t)bg * 128;
+
+    uint32_t bf[16];
+    int cur_rel = -1;
+    auto load_frags = [&](int p) {
+        if (p == cur_rel) return;
+        const uint4* f = wfrag + ((size_t)p * NG + bg) * 32 * 4 + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(f + q);
+            bf[4 * q] = v.x; bf[4 * q + 1] = v.y; bf[4 * q + 2] = v.z; bf[4 * q + 3] = v.w;
+        }
+        cur_rel = p;
+    };
+    auto issue = [&](int k) {
+        const int tile = t0 + k;
+        if (tile < t1) {
+            unsigned char* st = ring + (k % kMmaStages) * kTileBytes;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
+                const bool ok = le < n;
+                cp_async16(st + tile_off(row, chunk), Xb + (size_t)s_src[ok ? le : 0] * row_bytes + chunk * 16, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    for (int k = 0; t0 + k < t1; ++k) {
+        issue(k + 2);
+        cp_async_wait<2>();
+        __syncwarp();
+        unsigned char* st = ring + (k % kMmaStages) * kTileBytes;
+        const int tile = t0 + k;
+        const int rows = min(16, n - tile * 16);
+        uint32_t a[4][4];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8, chunk = kb * 2 + (lane >> 4);
+            ldmatrix_x4(a[kb], smem_u32(st + tile_off(row, chunk)));
+        }
+        float acc[4][2][4];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[kb][h][q] = 0.f;
+        const int r_first = s_rel[tile * 16], r_last = s_rel[tile * 16 + rows - 1];
+        if (r_first == r_last) {
+            load_frags(r_first);
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                mma_bf16_16816(acc[kb][0], a[kb], bf[kb * 4], bf[kb * 4 + 1]);
+                mma_bf16_16816(acc[kb][1], a[kb], bf[kb * 4 + 2], bf[kb * 4 + 3]);
+            }
+        } else {                                        // tile straddles relations: one pass per relation run
+            int row0 = 0;
+            while (row0 < rows) {
+                const int p = s_rel[tile * 16 + row0];
+                int row1 = row0 + 1;
+                while (row1 < rows && s_rel[tile * 16 + row1] == p) ++row1;
+                load_frags(p);
+                const bool top = g >= row0 && g < row1, bot = g + 8 >= row0 && g + 8 < row1;
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float c[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma_bf16_16816(c, a[kb], bf[kb * 4 + 2 * h], bf[kb * 4 + 2 * h + 1]);
+                        if (top) { acc[kb][h][0] = c[0]; acc[kb][h][1] = c[1]; }
+                        if (bot) { acc[kb][h][2] = c[2]; acc[kb][h][3] = c[3]; }
+                    }
+                row0 = row1;
+            }
+        }
+        __syncwarp();                                   // tile fully consumed; reuse it to transpose the result
+        const int le0 = tile * 16 + g, le1 = le0 + 8;
+        const float v0 = le0 < n ? s_val[le0] : 0.f, v1 = le1 < n ? s_val[le1] : 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int chunk = kb * 2 + h;
+                *reinterpret_cast<uint32_t*>(st + tile_off(g, chunk) + t * 4) =
+                    pack_bf16x2(acc[kb][h][0] * v0, acc[kb][h][1] * v0);
+                *reinterpret_cast<uint32_t*>(st + tile_off(g + 8, chunk) + t * 4) =
+                    pack_bf16x2(acc[kb][h][2] * v1, acc[kb][h][3] * v1);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int row = (lane >> 3) + 4 * it, chunk = lane & 7, le = tile * 16 + row;
+            if (le < n) {
+                const uint4 v = *reinterpret_cast<const uint4*>(st + tile_off(row, chunk));
+                __stcs(reinterpret_cast<uint4*>(Mb + (size_t)s_slot[le] * row_bytes + chunk * 16), v);   // streaming: read once, later
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
 }
 
 // L2-only 16-byte load (the ring is rewritten inside the kernel, so L1 must not serve it)
@@ -559,19 +722,10 @@ __device__ __forceinline__ bool next_item(const TiledArgs& A, int* s_item, rgcn_
     return true;
 }
 
-__device__ __forceinline__ Chunk item_chunk(const TiledArgs& A, const rgcn_tile_item& it) {
-    Chunk C;
-    C.p = it.a; C.n = it.c;
-    C.gather = A.tl.row + it.b; C.other = A.tl.col + it.b;
-    C.slot = A.tl.slot + it.b; C.val = A.tl.val + it.b;
-    C.slot_bias = it.slot_bias;
-    return C;
-}
-
-// forward: rows = destinations; gather X[col] (sources)
-__global__ void __launch_bounds__(256) k_tiled_mma_fwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
+// rows = tile side; gathers src[tl.col]; writes out[row] = bias + sum of messages
+__global__ void __launch_bounds__(256, 2) k_tiled_span(TiledArgs A, const __nv_bfloat16* __restrict__ src,
                                                        __nv_bfloat16* __restrict__ ring, float* __restrict__ out) {
-    extern __shared__ __align__(128) unsigned char smem_tiled_fwd[];
+    extern __shared__ __align__(128) unsigned char smem_tiled[];
     __shared__ int s_item;
     const size_t width = (size_t)A.nb * 16;
     rgcn_tile_item it;
@@ -579,42 +733,16 @@ __global__ void __launch_bounds__(256) k_tiled_mma_fwd(TiledArgs A, const __nv_b
         const int k = it.tile;
         __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
         if (it.kind == 0) {
-            Chunk C = item_chunk(A, it);
-            C.gather = C.other;                      // forward gathers the source endpoint (tl.col)
-            C.other = nullptr;
+            Span S;
+            S.n = it.c; S.gather = A.tl.col + it.b; S.rel = A.tl.rel + it.b; S.slot = A.tl.slot + it.b;
+            S.val = A.tl.val + it.b; S.slot_bias = it.slot_bias;
             wait_count(A.slot_done + (k % A.depth), it.need, A.status);
-            mma_fwd_chunk(C, A.W, A.nb, X, slot_base, smem_tiled_fwd);
+            mma_span(S, A.wfrag, A.nb, src, slot_base, smem_tiled);
             signal_done(A.done1 + k);
         } else {
             wait_count(A.done1 + k, it.need, A.status);
             row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, A.bias, out,
-                          reinterpret_cast<float*>(smem_tiled_fwd));
-            signal_done(A.slot_done + (k % A.depth));
-        }
-    }
-}
-
-// backward: rows = sources; gather X[row] (bf16) and G[col] (bf16 copy); messages summed into the feature gradient
-__global__ void __launch_bounds__(256, 2) k_tiled_mma_bwd(TiledArgs A, const __nv_bfloat16* __restrict__ X,
-                                                          const __nv_bfloat16* __restrict__ Gb,
-                                                          __nv_bfloat16* __restrict__ ring,
-                                                          float* __restrict__ gX, float* __restrict__ gW) {
-    extern __shared__ __align__(128) unsigned char smem_tiled_bwd[];
-    __shared__ int s_item;
-    const size_t width = (size_t)A.nb * 16;
-    rgcn_tile_item it;
-    while (next_item(A, &s_item, it)) {
-        const int k = it.tile;
-        __nv_bfloat16* slot_base = ring + (size_t)(k % A.depth) * A.capacity * width;
-        if (it.kind == 0) {
-            Chunk C = item_chunk(A, it);            // gather = tl.row (source, X rows), other = tl.col (G rows)
-            wait_count(A.slot_done + (k % A.depth), it.need, A.status);
-            mma_bwd_chunk<true>(C, A.W, A.nb, X, Gb, slot_base, gW, smem_tiled_bwd);
-            signal_done(A.done1 + k);
-        } else {
-            wait_count(A.done1 + k, it.need, A.status);
-            row_sum_block(A.rowptr, it.a, it.b, (int)width, slot_base, it.slot_bias, nullptr, gX,
-                          reinterpret_cast<float*>(smem_tiled_bwd));
+                          reinterpret_cast<float*>(smem_tiled));
             signal_done(A.slot_done + (k % A.depth));
         }
     }
@@ -663,42 +791,36 @@ inline int launch_cast_colsum(const float* G, int64_t N, int O, __nv_bfloat16* G
 
 
 inline size_t tiled_counter_bytes(int64_t T) { return align_up((size_t)(T + 4 + RGCN_MAX_RING_DEPTH) * sizeof(int32_t)); }
+inline size_t wfrag_bytes(int64_t Rp, int nb) { return align_up((size_t)Rp * (nb / 4) * 32 * 16 * sizeof(uint32_t)); }
 
-inline TiledArgs make_tiled_args(const rgcn_graph* g, bool backward, int nb, const float* W, const float* bias,
+inline int launch_pack_wfrag(const float* W, int64_t Rp, int nb, bool transpose, uint32_t* frag, cudaStream_t st) {
+    const long long total = (long long)Rp * (nb / 4) * 32 * 16;
+    RGCN_LAUNCH(k_pack_wfrag, grid_for(total, 256), 256, 0, st, W, (int)Rp, nb, transpose ? 1 : 0, frag);
+    return RGCN_OK;
+}
+
+inline TiledArgs make_tiled_args(const rgcn_graph* g, bool backward, int nb, const uint32_t* wfrag, const float* bias,
                                  int32_t* counters) {
     TiledArgs A{};
     A.tl = backward ? g->bt : g->ft;
     A.rowptr = backward ? g->s_rowptr : g->d_rowptr;
-    A.T = (int)g->num_tiles; A.Rp = (int)g->num_rels; A.nb = nb; A.depth = (int)g->ring_depth;
+    A.T = (int)g->num_tiles; A.nb = nb; A.depth = (int)g->ring_depth;
     A.capacity = (long long)g->tile_capacity;
     A.queue = counters; A.slot_done = counters + 4; A.done1 = counters + 4 + RGCN_MAX_RING_DEPTH;
-    A.status = g->status; A.W = W; A.bias = bias;
+    A.status = g->status; A.wfrag = reinterpret_cast<const uint4*>(wfrag); A.bias = bias;
     return A;
 }
 
-inline int launch_tiled_mma_fwd(const TiledArgs& A, const __nv_bfloat16* X, __nv_bfloat16* ring, float* out,
-                                cudaStream_t st) {
+inline int launch_tiled_span(const TiledArgs& A, const __nv_bfloat16* src, __nv_bfloat16* ring, float* out,
+                             cudaStream_t st) {
     static int grid = 0;
     if (!grid) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmemBytes));
         int per_sm = 0;
-        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_fwd, 256, kFwdSmemBytes));
+        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_span, 256, kSpanSmemBytes));
         grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
     }
-    RGCN_LAUNCH(k_tiled_mma_fwd, grid, 256, kFwdSmemBytes, st, A, X, ring, out);
-    return RGCN_OK;
-}
-
-inline int launch_tiled_mma_bwd(const TiledArgs& A, const __nv_bfloat16* X, const __nv_bfloat16* G, __nv_bfloat16* ring,
-                                float* gX, float* gW, cudaStream_t st) {
-    static int grid = 0;
-    if (!grid) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<true>::kBytes));
-        int per_sm = 0;
-        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_mma_bwd, 256, BwdSmem<true>::kBytes));
-        grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
-    }
-    RGCN_LAUNCH(k_tiled_mma_bwd, grid, 256, BwdSmem<true>::kBytes, st, A, X, G, ring, gX, gW);
+    RGCN_LAUNCH(k_tiled_span, grid, 256, kSpanSmemBytes, st, A, src, ring, out);
     return RGCN_OK;
 }
 

@@ -55,14 +55,12 @@ class GraphPlan:
         self._tiling = []
         if self.tile_edges > 0:
             T = (nnz - 1) // self.tile_edges + 1
-            groups = T * num_rels
             n_items = _lib.lib.rgcn_tile_items_bound(nnz, num_nodes, num_rels, self.tile_edges)
             for tl in (g.ft, g.bt):
-                arrs = dict(tilerow=torch.empty(T + 1, **i32), grpptr=torch.empty(groups + 1, **i32),
-                            chunkptr=torch.empty(groups + 1, **i32), row=torch.empty(n1, **i32),
-                            col=torch.empty(n1, **i32), slot=torch.empty(n1, **i32), val=torch.empty(n1, **f32),
-                            stepptr=torch.empty(_lib.lib.rgcn_tile_steps_len(nnz, self.tile_edges, self.ring_depth), **i32), slotneed=torch.empty(T, **i32),
-                            items=torch.empty(n_items, 8, **i32))
+                arrs = dict(tilerow=torch.empty(T + 1, **i32), row=torch.empty(n1, **i32), col=torch.empty(n1, **i32),
+                            rel=torch.empty(n1, **i32), slot=torch.empty(n1, **i32), val=torch.empty(n1, **f32),
+                            stepptr=torch.empty(_lib.lib.rgcn_tile_steps_len(nnz, self.tile_edges, self.ring_depth), **i32),
+                            slotneed=torch.empty(T, **i32), items=torch.empty(n_items, 8, **i32))
                 self._tiling.append(arrs)
                 for k, v in arrs.items():
                     setattr(tl, k, v.data_ptr())
