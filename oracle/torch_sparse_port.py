@@ -5,7 +5,8 @@ it, op for op on torch CPU tensors, so that `bench.py`'s `cpu_baseline` / `--imp
 work the reference does: stacked COO adjacency, `sum_sparse` through a sparse x ones product, the dense
 (R', N, d) temporaries of the horizontal / vertical branches, and plain autograd for the backward.
 The reference checkout itself is pure Python and does not travel to the GPU box, hence a port
-(`cpu_baseline.kind = "port"`).  Pinned by tests/test_oracle_golden.py::test_port_* against the golden
+(`cpu_baseline.kind = "port"`).  The ops are device-agnostic, so the same port on CUDA tensors gives the reference's
+GPU path (`bench.py --impl reference-gpu`, informational).  Pinned by tests/test_oracle_golden.py::test_port_* against the golden
 fixtures (reference outputs and autograd gradients).
 
 Only bench.py and tests/ import this file.  References: torch_rgcn/utils.py:71-97, :143-196;
@@ -36,20 +37,20 @@ def sums_per_entry(indices, values, size, row_normalisation):   # utils.py:71-97
     if not row_normalisation:
         indices = torch.cat([indices[:, 1:2], indices[:, 0:1]], dim=1)
         size = (size[1], size[0])
-    ones = torch.ones((size[1], 1))
+    ones = torch.ones((size[1], 1), device=indices.device)
     sums = torch.sparse.mm(_coo(indices, values, size), ones)
     return sums[indices[:, 0], 0]
 
 
 def block_diag(m):                                        # utils.py:168-196
     r, nb, bi, bo = m.shape
-    eye = torch.eye(nb).view(1, nb, 1, nb, 1)
+    eye = torch.eye(nb, device=m.device).view(1, nb, 1, nb, 1)
     return (m.unsqueeze(-2) * eye).reshape(r, nb * bi, nb * bo)
 
 
 def adjacency(triples_plus, n_nodes, n_rels, vertical, n, i):   # layers.py:255-279 / :490-516
     idx, size = stack(triples_plus, n_nodes, n_rels, vertical)
-    vals = torch.ones(idx.size(0))
+    vals = torch.ones(idx.size(0), device=idx.device)
     sums = sums_per_entry(idx, vals, size, vertical)
     if not vertical:
         sums = torch.cat([sums[n:2 * n], sums[:n], sums[-i:]], dim=0)
@@ -86,7 +87,7 @@ def lp_forward(triples, n_nodes, n_rels, params, features, vertical=False):
     """RelationalGraphConvolutionLP.forward in eval mode, op for op (layers.py:450-565)."""
     r = int((n_rels - 1) / 2)
     inv = torch.cat([triples[:, 2, None], triples[:, 1, None] + r, triples[:, 0, None]], dim=1)
-    ids = torch.arange(n_nodes)[:, None]
+    ids = torch.arange(n_nodes, device=triples.device)[:, None]
     loops = torch.cat([ids, torch.full_like(ids, 2 * r), ids], dim=1)
     self_part = torch.cat([triples, loops], dim=0)        # utils.py:124
     tp = torch.cat([triples, inv, self_part], dim=0)
