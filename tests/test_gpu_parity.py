@@ -347,6 +347,27 @@ def test_bf16_features(cuda_device, monkeypatch, width, nb, grads, tile_mb):
         close(feats.grad.float().cpu().numpy(), ref_g['features'], 'features')
 
 
+def test_gradient_dtypes_follow_inputs(cuda_device):
+    """float64 / float16 features and bf16 parameters: the layer computes in fp32 and returns gradients in the
+    dtype each tensor arrived in (what autograd requires)."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R = 300, 3
+    tp = torch.as_tensor(orc.add_inverse_and_self(random_triples(N, R, 2000, seed=9).numpy(), N, R))
+    for fdt in (torch.float64, torch.float16):
+        layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=16,
+                                             out_features=8).to(cuda_device)
+        x = torch.randn(N, 16, device=cuda_device, dtype=fdt, requires_grad=True)
+        out = layer(x)
+        out.sum().backward()
+        assert out.dtype == torch.float32 and x.grad.dtype == fdt and layer.weights.grad.dtype == torch.float32
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=16,
+                                         out_features=8).to(cuda_device).to(torch.bfloat16)
+    x = torch.randn(N, 16, device=cuda_device, requires_grad=True)
+    layer(x).sum().backward()
+    assert layer.weights.grad.dtype == torch.bfloat16 and layer.bias.grad.dtype == torch.bfloat16
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at a large shape
 # ---------------------------------------------------------------------------------------------------

@@ -41,6 +41,9 @@ class _Propagate(torch.autograd.Function):
     def forward(ctx, plan, form, in_dim, out_dim, features, weights, bases, comps, blocks, blocks_self, bias,
                 self_mask, add_bias=True):
         featureless = features is None
+        # gradients are handed back in the dtype each input arrived in (the kernels compute in fp32 / bf16)
+        ctx.in_dtypes = [None if t is None else t.dtype
+                         for t in (features, weights, bases, comps, blocks, blocks_self, bias)]
         tensors = [_f32c(t) for t in (weights, bases, comps, blocks, blocks_self, bias, self_mask)]
         weights, bases, comps, blocks, blocks_self, bias, self_mask = tensors
         if features is not None:
@@ -98,10 +101,9 @@ class _Propagate(torch.autograd.Function):
             _lib.check(_lib.lib.rgcn_backward(C.byref(plan.c), C.byref(p), _lib.ptr(features), dt,
                                               _lib.ptr(grad_out), C.byref(gr), _lib.ptr(ws), ws_bytes,
                                               _lib.stream_ptr()))
-        if g_feat is not None and features.dtype != torch.float32:
-            g_feat = g_feat.to(features.dtype)
-        return (None, None, None, None, g_feat, g_w, g_bases if need[6] else None, g_comps if need[7] else None,
-                g_blocks, g_self, g_bias, None, None)
+        grads = [g_feat, g_w, g_bases if need[6] else None, g_comps if need[7] else None, g_blocks, g_self, g_bias]
+        grads = [g if (g is None or dt is None or g.dtype == dt) else g.to(dt) for g, dt in zip(grads, ctx.in_dtypes)]
+        return (None, None, None, None, *grads, None, None)
 
 
 def rgcn_propagate(plan, form, in_dim, out_dim, features=None, weights=None, bases=None, comps=None, blocks=None,
