@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 8
+#define RGCN_ABI_VERSION 9
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
@@ -208,13 +208,14 @@ typedef struct rgcn_params {
 } rgcn_params;
 
 typedef struct rgcn_grads { /* NULL = gradient not wanted; buffers are overwritten, not accumulated */
-    float* features;        /* (N, I) */
+    void* features;         /* (N, I), fp32 unless features_dtype says bf16 */
     float* weights;
     float* bases;
     float* comps;
     float* blocks;
     float* blocks_self;
     float* bias;
+    int32_t features_dtype; /* enum rgcn_dtype of the `features` buffer (RGCN_BF16 only with bf16 input features) */
 } rgcn_grads;
 
 size_t rgcn_forward_workspace_bytes(const rgcn_graph* graph, const rgcn_params* params, int feature_dtype);

@@ -46,7 +46,7 @@ class Params(C.Structure):
 
 class Grads(C.Structure):
     _fields_ = [('features', _p), ('weights', _p), ('bases', _p), ('comps', _p), ('blocks', _p),
-                ('blocks_self', _p), ('bias', _p)]
+                ('blocks_self', _p), ('bias', _p), ('features_dtype', C.c_int32)]
 
 
 def build(force=False):

@@ -294,6 +294,7 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
         default: break;
     }
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
+    if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.I * 4);   // fp32 staging of a bf16 feature gradient
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
@@ -314,6 +315,16 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     RGCN_REQUIRE(ws_bytes >= need && (ws || need == 0), RGCN_ERR_WORKSPACE, "rgcn_backward: workspace %zu < %zu", ws_bytes, need);
     Carver carve(ws);
     const int64_t IO = (int64_t)s.I * s.O;
+    const bool gx_bf16 = gr->features && gr->features_dtype == RGCN_BF16;
+    RGCN_REQUIRE(!gx_bf16 || x_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_backward: bf16 feature gradient needs bf16 features");
+    // paths that produce an fp32 feature gradient write it here first when the caller wants bf16
+    float* gx_f32 = gx_bf16 ? carve.take<float>((size_t)s.N * s.I) : static_cast<float*>(gr->features);
+    auto finish_gx = [&]() -> int {
+        if (!gx_bf16) return RGCN_OK;
+        const int64_t n = s.N * (int64_t)s.I;
+        RGCN_LAUNCH(k_cast_bf16, grid_for(n, 256), 256, 0, st, gx_f32, n, static_cast<__nv_bfloat16*>(gr->features));
+        return RGCN_OK;
+    };
 
     // ---- bf16 features + 16x16 blocks (untiled): G is rounded to bf16 once, fused with the bias gradient, then ONE
     //      tensor-core pass produces the feature-gradient messages and the weight gradient
@@ -344,16 +355,21 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             rc = launch_pack_wfrag(p->blocks, s.Rp, s.nb, true, frag, st);
             if (rc) return rc;
             TiledArgs T = make_tiled_args(g, true, s.nb, frag, nullptr, counters);
-            return launch_tiled_span(T, gb16, ring, gr->features, st);
+            rc = launch_tiled_span(T, gb16, ring, gx_f32, st);
+            if (rc) return rc;
+            return finish_gx();
         }
         RelArgs R{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_sslot, g->r_val, p->blocks, s.nb};
         __nv_bfloat16* msg = nullptr;
         if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
         rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), gb16, msg, gr->blocks, max_chunks(s), st);
         if (rc) return rc;
+        if (gr->features && gx_bf16)
+            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr,
+                                  static_cast<__nv_bfloat16*>(gr->features), g->s_long, g->status + 5, g->num_long_src, s.nnz, st);
         if (gr->features)
-            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, g->s_long, g->status + 5,
-                                  g->num_long_src, s.nnz, st);
+            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, static_cast<float*>(gr->features),
+                                  g->s_long, g->status + 5, g->num_long_src, s.nnz, st);
         return RGCN_OK;
     }
 
@@ -400,7 +416,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         A.nrows = s.N; A.N = s.N;
         fill_weights(A, p, s);
         A.I = s.O; A.O = s.I; A.bi = s.bo; A.bo = s.bi;
-        A.in_mask = p->self_mask; A.out = gr->features;
+        A.in_mask = p->self_mask; A.out = gx_f32;
         A.long_list = g->s_long; A.long_count = g->status + 5; A.nnz_hint = s.nnz; A.num_long = g->num_long_src;
         if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
             float* wt = carve.take<float>((size_t)s.Rp * IO);
@@ -427,11 +443,13 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             float* msg = reinterpret_cast<float*>(carve.take<char>(msg_bytes));
             rc = launch_rel_transform(R, rs.bi, rs.bo, G, msg, max_chunks(s), st);
             if (rc) return rc;
-            rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gr->features, g->s_long, g->status + 5,
+            rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gx_f32, g->s_long, g->status + 5,
                                 g->num_long_src, s.nnz, st);
         } else {
             rc = launch_prop(A, G, st);
         }
+        if (rc) return rc;
+        rc = finish_gx();
         if (rc) return rc;
     } else if (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) {
         carve.take<float>((size_t)s.Rp * IO);            // keep the layout identical to the query

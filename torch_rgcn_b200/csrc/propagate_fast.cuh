@@ -187,12 +187,18 @@ __device__ __forceinline__ void storev(float* p, const VecF<V>& a) {
     for (int k = 0; k < V / 4; ++k)
         reinterpret_cast<float4*>(p)[k] = make_float4(a.v[4 * k], a.v[4 * k + 1], a.v[4 * k + 2], a.v[4 * k + 3]);
 }
+template <int V>
+__device__ __forceinline__ void storev(__nv_bfloat16* p, const VecF<V>& a) {
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k)
+        reinterpret_cast<uint2*>(p)[k] = make_uint2(pack_bf16x2(a.v[4 * k], a.v[4 * k + 1]), pack_bf16x2(a.v[4 * k + 2], a.v[4 * k + 3]));
+}
 __device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-template <typename MT, int V>
+template <typename MT, int V, typename OT>
 __global__ void __launch_bounds__(256) k_row_sum(const int32_t* __restrict__ rowptr, int64_t nrows, int O,
                                                  const MT* __restrict__ msg, const float* __restrict__ bias,
-                                                 float* __restrict__ out) {
+                                                 OT* __restrict__ out) {
     const int cg = O / V;
     const int64_t total = nrows * cg;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -226,10 +232,10 @@ __global__ void __launch_bounds__(256) k_row_sum(const int32_t* __restrict__ row
 
 // hub rows (more than RGCN_LONG_ROW messages): one CTA per row, edge-parallel partial sums (4 independent loads in
 // flight per thread), shared-memory reduction
-template <typename MT, int V>
+template <typename MT, int V, typename OT>
 __global__ void __launch_bounds__(256) k_row_sum_long(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ list,
                                                       const int32_t* __restrict__ count, int O, const MT* __restrict__ msg,
-                                                      const float* __restrict__ bias, float* __restrict__ out) {
+                                                      const float* __restrict__ bias, OT* __restrict__ out) {
     __shared__ float red[256 * V];
     if ((int)blockIdx.x >= *count) return;
     const int row = list[blockIdx.x];
@@ -475,25 +481,31 @@ int launch_rel_transform(const RelArgs& A, int bi, int bo, const XT* X, MT* msg,
     return RGCN_ERR_UNSUPPORTED;
 }
 
-template <typename MT, int V>
-int launch_row_sum_v(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
+template <typename MT, int V, typename OT>
+int launch_row_sum_v(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, OT* out,
                      const int32_t* long_list, const int32_t* long_count, int64_t num_long, int64_t nnz, cudaStream_t st) {
     int64_t total = nrows * (O / V);
     int64_t want = (total + 255) / 256;
     int grid = (int)(want < (int64_t)kNumSMs * 32 ? want : (int64_t)kNumSMs * 32);
     if (grid < 1) grid = 1;
-    RGCN_LAUNCH((k_row_sum<MT, V>), grid, 256, 0, st, rowptr, nrows, O, msg, bias, out);
+    RGCN_LAUNCH((k_row_sum<MT, V, OT>), grid, 256, 0, st, rowptr, nrows, O, msg, bias, out);
     // exact count when the plan read it back, else the bound: at most nnz / RGCN_LONG_ROW rows can be that long
     const int bound = num_long >= 0 ? (int)num_long : (int)(nnz / RGCN_LONG_ROW);
-    if (bound > 0) RGCN_LAUNCH((k_row_sum_long<MT, V>), bound, 256, 0, st, rowptr, long_list, long_count, O, msg, bias, out);
+    if (bound > 0) RGCN_LAUNCH((k_row_sum_long<MT, V, OT>), bound, 256, 0, st, rowptr, long_list, long_count, O, msg, bias, out);
     return RGCN_OK;
 }
 
-template <typename MT>
-int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, float* out,
+template <typename MT, typename OT>
+int launch_row_sum(const int32_t* rowptr, int64_t nrows, int O, const MT* msg, const float* bias, OT* out,
                    const int32_t* long_list, const int32_t* long_count, int64_t num_long, int64_t nnz, cudaStream_t st) {
-    if (O % 8 == 0) return launch_row_sum_v<MT, 8>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
-    return launch_row_sum_v<MT, 4>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
+    if (O % 8 == 0) return launch_row_sum_v<MT, 8, OT>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
+    return launch_row_sum_v<MT, 4, OT>(rowptr, nrows, O, msg, bias, out, long_list, long_count, num_long, nnz, st);
+}
+
+// fp32 -> bf16 copy (feature gradient of paths that produce fp32 when the caller asked for bf16)
+__global__ void k_cast_bf16(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
 template <typename XT, int BI, int BO, int NB>

@@ -82,7 +82,9 @@ class _Propagate(torch.autograd.Function):
         def alloc(flag, like, dtype=torch.float32):
             return torch.empty(like.shape, dtype=dtype, device=dev) if (flag and like is not None) else None
 
-        g_feat = alloc(need[4], features)
+        # bf16 features: the engine writes the feature gradient in bf16 directly (no fp32 round trip)
+        g_feat = alloc(need[4], features, torch.bfloat16 if (features is not None and features.dtype == torch.bfloat16)
+                       else torch.float32)
         g_w = alloc(need[5], weights)
         want_basis = (need[6] or need[7]) and bases is not None
         g_bases = alloc(want_basis, bases)
@@ -94,6 +96,7 @@ class _Propagate(torch.autograd.Function):
         for name, t in (('features', g_feat), ('weights', g_w), ('bases', g_bases), ('comps', g_comps),
                         ('blocks', g_blocks), ('blocks_self', g_self), ('bias', g_bias)):
             setattr(gr, name, t.data_ptr() if t is not None else None)
+        gr.features_dtype = _lib.BF16 if (g_feat is not None and g_feat.dtype == torch.bfloat16) else _lib.F32
         dt = _lib.BF16 if (features is not None and features.dtype == torch.bfloat16) else _lib.F32
         ws_bytes = _lib.lib.rgcn_backward_workspace_bytes(C.byref(plan.c), C.byref(p), dt)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
