@@ -43,6 +43,14 @@ WORKLOADS = {
     'wn18': dict(shape='wn18', kind='lp', in_f=16, out_f=16, decomp=None, dtype='f32', vertical=False,
                  label='WN18-shaped lp rgcn layer (40,943 nodes, R\'=37, 70,721 sampled triples -> nnz=253,106), '
                        '16->16, fp32; graph build inside the step'),
+    # the whole two-layer NodeClassifier step (featureless layer 1 -> ReLU -> layer 2 -> CE loss)
+    'aifb_model': dict(shape='aifb', kind='nc_model', in_f=None, out_f=4, hidden=16, decomp=None, dtype='f32',
+                       vertical=False, label='AIFB-shaped 2-layer NodeClassifier step (8,285 nodes, R\'=91, '
+                                             'nnz=66,371 per layer), no decomposition, hidden 16, 4 classes, fp32'),
+    'mutag_model': dict(shape='mutag', kind='nc_model', in_f=None, out_f=2, hidden=16,
+                        decomp={'type': 'basis', 'num_bases': 30}, dtype='f32', vertical=False,
+                        label='MUTAG-shaped 2-layer NodeClassifier step (23,644 nodes, R\'=47, nnz=172,098 per layer), '
+                              'basis B=30, hidden 16, 2 classes, fp32'),
     'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
                 vertical=True, raw=True,
                 label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
@@ -407,6 +415,82 @@ def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
                       f'per-edge rate is scale-invariant because the reference cost is O(R\'*N*d) with N/nnz fixed'}
 
 
+def run_model(args):
+    """Two-layer NodeClassifier training step on the B200 layers vs the CPU port of the reference wiring."""
+    from torch_rgcn_b200 import _lib, models
+    from oracle import torch_sparse_port as port
+    wl = WORKLOADS[args.workload]
+    dev = torch.device('cuda', 0)
+    t, N, Rp, nnz = build_triples(wl, 'cpu')
+    R = (Rp - 1) // 2
+    torch.manual_seed(2)
+    model = models.NodeClassifier(triples=t, nnodes=N, nrel=R, nhid=wl['hidden'], nlayers=2, nclass=wl['out_f'],
+                                  decomposition=wl['decomp']).to(dev)
+    g = torch.Generator().manual_seed(3)
+    train_idx = torch.randperm(N, generator=g)[:max(N // 10, 8)].to(dev)
+    labels = torch.randint(0, wl['out_f'], (train_idx.numel(),), generator=g).to(dev)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        loss = crit(model()[train_idx], labels)
+        loss.backward()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.lib.rgcn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.lib.rgcn_launch_count() - l0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step().item()                                   # e2e: loss read back every step (the model has no host inputs)
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    # CPU port of the same wiring (reference models.py:192-200)
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu = {n: p.detach().cpu().clone().requires_grad_(True) for n, p in model.named_parameters()}
+    tp = model.triples_plus.cpu()
+    ti, lb = train_idx.cpu(), labels.cpu()
+
+    def cpu_step():
+        p1 = {k[5:]: v for k, v in cpu.items() if k.startswith('rgc1.')}
+        p2 = {k[5:]: v for k, v in cpu.items() if k.startswith('rgc2.')}
+        h = torch.relu(port.nc_forward(tp, N, Rp, p1, None, False))
+        out = port.nc_forward(tp, N, Rp, p2, h, True)
+        crit(out[ti], lb).backward()
+        for v in cpu.values():
+            v.grad = None
+
+    cpu_step()
+    times = []
+    for _ in range(3):
+        a = time.perf_counter()
+        cpu_step()
+        times.append(time.perf_counter() - a)
+    cpu_s = sum(times) / len(times)
+    edges = 2 * nnz
+    print(json.dumps({
+        'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': edges / (ms * 1e-3), 'unit': 'edges/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': wl['dtype'], 'data': 'synthetic',
+        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'num_relations': Rp,
+                   'edges_per_step': edges, 'l2': 'working set fits L2 (latency-bound shape); not flushed'},
+        'e2e': {'value': edges / (ms_e2e * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'cpu_baseline': {'value': edges / cpu_s, 'unit': 'edges/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         's_per_step': cpu_s, 'sample': 'full-size model step with oracle/torch_sparse_port.py'}}),
+        flush=True)
+
+
 def run_reference_gpu(args):
     """Informational: the reference's torch.sparse algorithm (the port) on CUDA tensors at full workload size —
     the north-star's '>= 1.0x the reference GPU path' comparison.  Falls back to a scaled graph on OOM."""
@@ -499,6 +583,8 @@ def main():
         run_reference_gpu(args)
     elif args.impl == 'reference':
         run_reference(args)
+    elif WORKLOADS[args.workload]['kind'] == 'nc_model':
+        run_model(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -21,6 +21,7 @@ REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
 sys.path.insert(0, REF)
 from torch_rgcn.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP  # noqa: E402
 from torch_rgcn.utils import add_inverse_and_self  # noqa: E402
+from torch_rgcn.models import NodeClassifier, EmbeddingNodeClassifier  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -128,6 +129,28 @@ def make_lp(name, seed, N, R, E, in_f, out_f, decomposition=None, vertical=False
     save(name, meta, arrays)
 
 
+def make_model(name, seed, cls, N, R, E, nclass, **kw):
+    """Whole reference model (models.py:137-296): logits and autograd gradients of every parameter."""
+    gen = torch.Generator().manual_seed(seed)
+    triples = rand_triples(gen, N, R, E)
+    torch.manual_seed(seed + 2)
+    model = cls(triples=triples.tolist(), nnodes=N, nrel=R, nclass=nclass, **kw)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('bias'):
+                p.normal_(0, 1, generator=gen)
+    out = model()
+    G = torch.randn(out.shape, generator=gen)
+    out.backward(G)
+    arrays = {'triples': triples.numpy(), 'out': out.detach().numpy(), 'G': G.numpy()}
+    for n, p in model.named_parameters():
+        arrays['param_' + n] = p.detach().numpy()
+        arrays['grad_' + n] = p.grad.detach().numpy()
+    meta = dict(kind='model', cls=cls.__name__, N=N, R=R, nclass=nclass, kwargs=kw,
+                state_keys=sorted(model.state_dict().keys()))
+    save(name, meta, arrays)
+
+
 def main():
     N, R, E = 24, 3, 70
     basis = {'type': 'basis', 'num_bases': 3}
@@ -161,6 +184,14 @@ def main():
     make_lp('lp_block_h_train_schlichtkrull', 26, N, R, E, 12, 8, decomposition=block, b_init='zeros',
             train='schlichtkrull')
     make_lp('lp_none_h_wn18like', 27, 60, 9, 300, 16, 16, b_init='zeros')
+    # --- whole node-classification models (reference models.py:137-296)
+    make_model('model_nc_none', 30, NodeClassifier, 40, 4, 160, 3, nhid=16, nlayers=2)
+    make_model('model_nc_basis', 31, NodeClassifier, 40, 4, 160, 3, nhid=16, nlayers=2,
+               decomposition={'type': 'basis', 'num_bases': 5})
+    make_model('model_nc_block', 32, NodeClassifier, 40, 4, 160, 4, nhid=16, nlayers=2,
+               decomposition={'type': 'block', 'num_blocks': 2})
+    make_model('model_nc_1layer', 33, NodeClassifier, 40, 4, 160, 3, nlayers=1)
+    make_model('model_ernn', 34, EmbeddingNodeClassifier, 40, 4, 160, 3, nemb=32, nlayers=2)
 
 
 if __name__ == '__main__':

@@ -406,3 +406,24 @@ def test_properties_large(cuda_device):
     lhs = (y.detach().double() * g.double()).sum()
     rhs = (x.detach().double() * x.grad.double()).sum()
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole node-classification models against the reference's models
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_models_match_reference(cuda_device, name):
+    from torch_rgcn_b200 import models
+    meta, d, params, grads = load_golden(name)
+    cls = getattr(models, meta['cls'])
+    model = cls(triples=d['triples'].tolist(), nnodes=meta['N'], nrel=meta['R'], nclass=meta['nclass'], **meta['kwargs'])
+    assert sorted(model.state_dict().keys()) == meta['state_keys']
+    model.to(cuda_device)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(_t(params[n], cuda_device))
+    out = model()
+    out.backward(_t(d['G'], cuda_device))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), d['out'], atol=ATOL, rtol=1e-4)
+    for n, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), grads[n], atol=ATOL, rtol=1e-4, err_msg=n)

@@ -116,3 +116,39 @@ def test_port_matches_reference_lp(name):
     from oracle import torch_sparse_port as port
     _port_check(name, lambda meta, d, p, x: port.lp_forward(torch.tensor(d['triples']), meta['N'],
                                                             meta['num_relations'], p, x, meta['vertical']))
+
+
+# ---- whole models: the oracle layers composed like reference models.py:192-200 / :288-296 --------------------
+def _split(params, prefix):
+    return {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize('name', golden_names('model_'))
+def test_oracle_matches_reference_models(name):
+    meta, d, params, grads = load_golden(name)
+    N, R = meta['N'], meta['R']
+    tp = orc.add_inverse_and_self(d['triples'], N, R)
+    Rp = 2 * R + 1
+    G = d['G']
+    if meta['cls'] == 'EmbeddingNodeClassifier':
+        emb = params['node_embeddings']
+        h, _ = orc.nc_layer(tp, N, Rp, _split(params, 'rgcn_no_hidden.'), emb, False, np.zeros((N, emb.shape[1])))
+        a = np.maximum(h, 0)
+        out, g1 = orc.nc_layer(tp, N, Rp, _split(params, 'rgc1.'), a, False, G)
+        _, g0 = orc.nc_layer(tp, N, Rp, _split(params, 'rgcn_no_hidden.'), emb, False, g1['features'] * (h > 0))
+        got = {'rgc1.' + k: v for k, v in g1.items() if k != 'features'}
+        got.update({'rgcn_no_hidden.' + k: v for k, v in g0.items() if k != 'features'})
+        got['node_embeddings'] = g0['features']
+    elif meta['kwargs'].get('nlayers') == 1:
+        out, g1 = orc.nc_layer(tp, N, Rp, _split(params, 'rgc1.'), None, False, G)
+        got = {'rgc1.' + k: v for k, v in g1.items() if v is not None}
+    else:
+        h, _ = orc.nc_layer(tp, N, Rp, _split(params, 'rgc1.'), None, False, np.zeros((N, 16)))
+        a = np.maximum(h, 0)
+        out, g2 = orc.nc_layer(tp, N, Rp, _split(params, 'rgc2.'), a, True, G)
+        _, g1 = orc.nc_layer(tp, N, Rp, _split(params, 'rgc1.'), None, False, g2['features'] * (h > 0))
+        got = {'rgc2.' + k: v for k, v in g2.items() if k != 'features'}
+        got.update({'rgc1.' + k: v for k, v in g1.items() if v is not None})
+    np.testing.assert_allclose(out, d['out'], atol=2e-5, rtol=1e-5)
+    for k, g in grads.items():
+        np.testing.assert_allclose(got[k], g, atol=2e-5, rtol=1e-4, err_msg=k)
