@@ -63,7 +63,9 @@ int launch_wgrad_generic(WGradArgs A, const XT* X, const float* G, int64_t nnz, 
     A.tile = tile;
     const size_t smem = (size_t)tile * (A.I + A.O) * sizeof(float);
     RGCN_REQUIRE(smem <= 48 * 1024, RGCN_ERR_UNSUPPORTED, "generic weight-grad: I+O=%d too wide", A.I + A.O);
-    int64_t gy = nnz / ((int64_t)Rp * 2048) + 1;
+    // edges per CTA slice: small weights (few atomics per flush) get many short slices, large weights long ones
+    int64_t slice = nel < 256 ? 256 : (nel > 4096 ? 4096 : nel);
+    int64_t gy = nnz / ((int64_t)Rp * slice) + 1;
     if (gy > 1024) gy = 1024;
     dim3 grid(Rp, (unsigned)gy);
     switch (KE) {

@@ -321,6 +321,19 @@ __global__ void __launch_bounds__(256) k_wgrad_featureless(FeaturelessGradArgs A
                     int j = lane + 32 * k, jj = j - kb * A.bo;
                     if (j < O && jj >= 0 && jj < A.bo) d[jj] = t[k];
                 }
+            } else if (K == 1 && B <= 32) {
+                // basis, O <= 32: lanes own output columns for gbases and basis indices for gcomps, so the
+                // <bases[b, o, :], t> products need no cross-lane reduction (one atomic per (segment, basis))
+                const float tj = t[0];
+                for (int b = 0; b < B; ++b)
+                    if (lane < O) gb_s[b * O + lane] += A.comps[(size_t)p * B + b] * tj;
+                const float* bs = A.bases + ((size_t)(lane < B ? lane : 0) * A.N + row) * O;
+                float dot = 0.f;
+                for (int j = 0; j < O; ++j) {
+                    const float tv = __shfl_sync(0xffffffffu, tj, j);
+                    if (lane < B) dot += bs[j] * tv;
+                }
+                if (lane < B) atomicAdd((A.comps_in_smem ? gc_s : A.gcomps) + (size_t)p * B + lane, dot);
             } else {
                 for (int b = 0; b < B; ++b) {
                     const float c = A.comps[(size_t)p * B + b];
