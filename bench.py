@@ -305,11 +305,26 @@ def run_ours(args):
     ach_f = bf_rank / (ms_fwd * 1e-3) / 1e9
     ach_b = bb_rank / (ms_bwd * 1e-3) / 1e9
     ach_s = (bf_rank + bb_rank) / (ms_step * 1e-3) / 1e9
+    # which kernels served the step: the fused row-block kernel (propagate_fused.cuh) or the two-phase kernels
+    plan = None
+    inner = getattr(layer, 'layer', layer)
+    if getattr(inner, '_plan_cache', None):
+        plan = inner._plan_cache[1]
+    if getattr(layer, '_local', None) is not None:
+        plan = layer._local
+    fused = bool(plan is not None and getattr(plan, 'fuse_rows', 0) > 0 and all(plan.fused_ok))
     traffic = {}
     try:       # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (1 GPU)
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload, {}) if world == 1 else {}
+        key = args.workload + ('_fused' if fused else '')
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(key, {}) if world == 1 else {}
     except OSError:
         pass
+    fwd_kernel = ('forward edge gather: rgcn_forward = ONE fused row-block kernel (gather + per-relation MMA + '
+                  'shared-memory row sums), k_fused_rows') if fused else \
+        'forward edge gather: rgcn_forward = gather+transform kernel + row-sum kernel'
+    bwd_kernel = ('rgcn_backward = bf16 cast + bias grad, weight-gradient MMA pass, fused row-block kernel for the '
+                  'feature gradient') if fused else \
+        'rgcn_backward = bf16 cast + bias grad, fused feature/weight gradient kernel, row-sum'
     line = {
         'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': nnz / (ms_step * 1e-3), 'unit': 'edges/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -319,17 +334,18 @@ def run_ours(args):
                    'l2': 'L2 flushed (256 MB write) between timed steps; flush outside the event pairs',
                    'parallelism': f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)'
                    if world > 1 else 'single GPU',
+                   'kernels': 'fused row-block (RGCN_FUSED=1)' if fused else 'two-phase (messages through HBM)',
                    'graph_plan': 'built once at first call (outside timed region)' if wl['kind'] == 'nc'
                    else 'rebuilt every step (inside timed region)'},
         'ms_fwd': ms_fwd, 'ms_bwd': ms_bwd, 'first_call_s_incl_plan_build': t_build,
         'e2e': {'value': nnz / (ms_e2e * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches),
-        'roofline': {'kernel': 'forward edge gather: rgcn_forward = gather+transform kernel + row-sum kernel',
+        'roofline': {'kernel': fwd_kernel,
                      'bound': 'hbm', 'achieved': ach_f, 'peak': peak, 'unit': 'GB/s', 'frac': ach_f / peak,
                      'traffic': traffic.get('fwd_dram_bytes'), 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': bf_rank, 'bytes_per_edge': per_edge},
-        'roofline_bwd': {'kernel': 'rgcn_backward = bf16 cast + bias grad, fused feature/weight gradient kernel, row-sum',
+        'roofline_bwd': {'kernel': bwd_kernel,
                          'bound': 'hbm', 'achieved': ach_b, 'peak': peak, 'unit': 'GB/s', 'frac': ach_b / peak,
                          'traffic': traffic.get('bwd_dram_bytes'), 'algorithmic_bytes_per_step': bb_rank},
         'roofline_step': {'definition': 'SURVEY 8(d): (B_f + B_b) / (t_fwd + t_bwd)', 'achieved': ach_s, 'peak': peak,

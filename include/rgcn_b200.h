@@ -31,12 +31,14 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 9
+#define RGCN_ABI_VERSION 10
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
 #define RGCN_MAX_RING_DEPTH 64        /* upper bound on rgcn_graph.ring_depth */
 #define RGCN_LONG_ROW 512             /* rows with more edges are listed in d_long / s_long and processed cooperatively */
+#define RGCN_FUSE_TILE 16             /* entries per MMA tile of the fused row-block lists (one relation per tile) */
+#define RGCN_FUSE_MAX_ITEM_TILES 512  /* upper bound on rgcn_graph.fuse_item_tiles */
 
 typedef void* rgcn_stream_t;
 
@@ -134,6 +136,23 @@ typedef struct rgcn_tile_item {
     int32_t pad;
 } rgcn_tile_item;
 
+/* Optional fused row-block lists (bf16 features, four 16x16 blocks): rows are cut into blocks of `fuse_rows`
+ * consecutive rows whose fp32 output tile lives in shared memory; the edges of a block are sorted by
+ * (relation, row) and every (block, relation) run is padded to whole 16-entry tiles, so that one MMA tile never
+ * mixes relations.  Blocks with more than fuse_item_tiles tiles are split into several work items, which then
+ * add their partial tiles into the output with atomics ("shared" items). */
+typedef struct rgcn_fused {
+    int32_t* col;           /* cap: row of the gathered matrix, -1 = padding */
+    int32_t* rv;            /* 2 x cap: per entry {row - first row of its block, bits of the fp32 edge weight};
+                               padding is {0, 0} */
+    int32_t* tile_rel;      /* cap / 16: relation of every tile */
+    int32_t* blk_tile;      /* NB + 1: first tile of every row block, NB = ceil(N / fuse_rows) */
+    int32_t* items;         /* 4 x int32 per work item {block, first tile, end tile, shared};
+                               capacity rgcn_fused_items_bound() */
+    int32_t* meta;          /* 4 x int32: [0] work items, [1] tiles, [2] 1 if the tiles do not fit cap (list unusable),
+                               [3] row blocks that were split */
+} rgcn_fused;
+
 typedef struct rgcn_graph {
     int64_t num_nodes;
     int64_t num_rels;       /* R' = number of relation ids the layer sees */
@@ -171,20 +190,33 @@ typedef struct rgcn_graph {
     int64_t ring_depth;     /* message tiles in flight (2 .. RGCN_MAX_RING_DEPTH); set by the caller with tile_edges */
     rgcn_tiling ft;         /* forward tiling (destination rows) */
     rgcn_tiling bt;         /* backward tiling (source rows) */
+    int64_t fuse_rows;      /* 0: no fused row-block lists (ff / fb unused); else rows per block (multiple of 16) */
+    int64_t fuse_cap;       /* entries allocated per list (multiple of 16) */
+    int64_t fuse_item_tiles;/* tiles per work item, 1 .. RGCN_FUSE_MAX_ITEM_TILES */
+    int64_t fuse_items[2];  /* host copies of ff / fb meta[0] filled by the caller after the build;
+                               0 = list unusable (overflow or not read back): the kernels fall back */
+    int64_t fuse_split[2];  /* host copies of ff / fb meta[3] */
+    rgcn_fused ff;          /* forward lists (blocks of destination rows, gathers X[o]) */
+    rgcn_fused fb;          /* backward lists (blocks of source rows, gathers grad_out[s]) */
 } rgcn_graph;
 
-size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges);
+size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges,
+                                  int64_t fuse_rows);
 /* upper bound on the number of work-queue items of one tiling (host-side sizing of rgcn_tiling.items) */
 int64_t rgcn_tile_items_bound(int64_t nnz, int64_t num_nodes, int64_t num_rels, int64_t tile_edges);
 /* length of rgcn_tiling.stepptr for a given tiling */
 int64_t rgcn_tile_steps_len(int64_t nnz, int64_t tile_edges, int64_t ring_depth);
+
+/* host-side sizing of rgcn_fused.items */
+int64_t rgcn_fused_items_bound(int64_t num_nodes, int64_t fuse_rows, int64_t fuse_cap, int64_t fuse_item_tiles);
 
 /* n_general / n_self are the (n, i) of the horizontal permutation: NC ((nnz-N)/2, N), LP (|T|, |T|+|self|).
  * val_in (nnz floats, caller order) is read only for RGCN_NORM_EXPLICIT. */
 int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t num_nodes, int64_t num_rels,
                      int norm, int64_t n_general, int64_t n_self, const float* val_in,
                      rgcn_graph* graph, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
-/* graph->tile_edges > 0 asks rgcn_graph_build to also fill graph->ft / graph->bt (arrays caller-allocated). */
+/* graph->tile_edges > 0 asks rgcn_graph_build to also fill graph->ft / graph->bt (arrays caller-allocated);
+ * graph->fuse_rows > 0 asks for graph->ff / graph->fb (fuse_cap and fuse_item_tiles set by the caller). */
 
 /* ------------------------------------------------------------------------------------------
  * Propagation: out[s] = bias + sum_e val_e * T_{p_e}(X[o_e]) and its gradients.

@@ -27,10 +27,10 @@ def test_struct_layouts_match_header():
     from torch_rgcn_b200 import _lib
     header = open(os.path.join(ROOT, 'include', 'rgcn_b200.h')).read()
     for cname, cls in (('rgcn_graph', _lib.Graph), ('rgcn_params', _lib.Params), ('rgcn_grads', _lib.Grads),
-                       ('rgcn_tiling', _lib.Tiling)):
+                       ('rgcn_tiling', _lib.Tiling), ('rgcn_fused', _lib.Fused)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), header, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-        members = re.findall(r'(\w+)\s*;', body)
+        members = re.findall(r'(\w+)\s*(?:\[\d+\])?\s*;', body)
         assert members == [f[0] for f in cls._fields_], cname
 
 
@@ -59,7 +59,7 @@ def test_bad_arguments_return_errors_without_a_gpu():
         _lib.check(_lib.lib.rgcn_shard_plan(None, 3, 2, None))
     with pytest.raises(_lib.RgcnError):
         _lib.check(_lib.lib.rgcn_block_diag(None, 1, 0, 1, 1, None, None))
-    assert _lib.lib.rgcn_graph_workspace_bytes(1000, 10, 3, 0) > 1000 * 40
+    assert _lib.lib.rgcn_graph_workspace_bytes(1000, 10, 3, 0, 0) > 1000 * 40
 
 
 @pytest.mark.parametrize('name', ['nc_none_h_feat', 'nc_basis_h_featureless', 'nc_block_v_feat_odd', 'nc_diag_h'])

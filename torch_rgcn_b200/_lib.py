@@ -25,6 +25,10 @@ class Tiling(C.Structure):
                 ('stepptr', _p), ('slotneed', _p), ('items', _p)]
 
 
+class Fused(C.Structure):
+    _fields_ = [('col', _p), ('rv', _p), ('tile_rel', _p), ('blk_tile', _p), ('items', _p), ('meta', _p)]
+
+
 class Graph(C.Structure):
     _fields_ = [('num_nodes', _i64), ('num_rels', _i64), ('nnz', _i64),
                 ('d_rowptr', _p), ('d_src', _p), ('d_rel', _p), ('d_val', _p),
@@ -33,7 +37,9 @@ class Graph(C.Structure):
                 ('r_dslot', _p), ('r_sslot', _p), ('r_chunkptr', _p),
                 ('val', _p), ('status', _p), ('d_long', _p), ('s_long', _p), ('num_long_dst', _i64), ('num_long_src', _i64),
                 ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ring_depth', _i64),
-                ('ft', Tiling), ('bt', Tiling)]
+                ('ft', Tiling), ('bt', Tiling),
+                ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64),
+                ('fuse_items', _i64 * 2), ('fuse_split', _i64 * 2), ('ff', Fused), ('fb', Fused)]
 
 
 class Params(C.Structure):
@@ -76,7 +82,8 @@ def _load():
         'rgcn_stack_matrices': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _p, _p, _p]),
         'rgcn_sum_sparse': (C.c_int, [_p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p]),
         'rgcn_block_diag': (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
-        'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64, _i64]),
+        'rgcn_graph_workspace_bytes': (C.c_size_t, [_i64, _i64, _i64, _i64, _i64]),
+        'rgcn_fused_items_bound': (_i64, [_i64, _i64, _i64, _i64]),
         'rgcn_tile_items_bound': (_i64, [_i64, _i64, _i64, _i64]),
         'rgcn_tile_steps_len': (_i64, [_i64, _i64, _i64]),
         'rgcn_graph_build': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _i64, _i64, _p, C.POINTER(Graph), _p,
@@ -98,7 +105,7 @@ def _load():
 lib = _load()
 EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add_inverse_and_self',
            'rgcn_generate_inverses', 'rgcn_lp_triples_plus', 'rgcn_stack_matrices', 'rgcn_sum_sparse',
-           'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
+           'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_fused_items_bound', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
            'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan']
 
 

@@ -337,6 +337,95 @@ __global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t*
     items[q] = it;
 }
 
+// ---- fused row-block lists (rgcn_fused) ----------------------------------------------------------------
+// key = (block * R' + p) * N + a,  a = block-side endpoint, block = a / fuse_rows
+__global__ void k_make_block_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
+                                  int64_t fuse_rows, uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int64_t s = t[3 * e], p = t[3 * e + 1], o = t[3 * e + 2];
+    if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
+    const int64_t a = backward ? o : s;
+    keys[e] = ((uint64_t)(a / fuse_rows) * Rp + p) * N + a;
+    idx[e] = (int32_t)e;
+}
+
+// cnt[g] = 16-entry tiles of run g (runs = segments of equal key / N), 0 beyond the last run
+__global__ void k_fused_run_tiles(int64_t nnz, const int32_t* __restrict__ segid, const int32_t* __restrict__ starts,
+                                  const int32_t* __restrict__ ends, int32_t* __restrict__ cnt) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= nnz) return;
+    cnt[g] = g < segid[nnz - 1] ? (ends[g] - starts[g] + RGCN_FUSE_TILE - 1) / RGCN_FUSE_TILE : 0;
+}
+
+// sorted edge e of run g goes to entry tbase[g] * 16 + (e - starts[g]); the first edge of a run also labels the
+// run's tiles and, for the first run of a row block, the block's first tile
+__global__ void k_fused_scatter(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
+                                const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
+                                int64_t fuse_rows, int64_t NB, const int32_t* __restrict__ segid,
+                                const int32_t* __restrict__ starts, const int32_t* __restrict__ tbase,
+                                const int32_t* __restrict__ cnt, const float* __restrict__ val, int64_t cap,
+                                int32_t* __restrict__ col, int32_t* __restrict__ rv, int32_t* __restrict__ tile_rel,
+                                int32_t* __restrict__ blk_tile, int32_t* __restrict__ meta) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const uint64_t k = keys[e];
+    const int64_t a = (int64_t)(k % N);
+    const uint64_t grp = k / N;
+    const int64_t p = (int64_t)(grp % Rp), blk = (int64_t)(grp / Rp);
+    const int32_t g = segid[e] - 1;
+    const int32_t orig = perm[e];
+    int64_t s = t[3 * (int64_t)orig], pp = t[3 * (int64_t)orig + 1], o = t[3 * (int64_t)orig + 2];
+    if (s < 0 || s >= N || o < 0 || o >= N || pp < 0 || pp >= Rp) s = o = 0;
+    const int64_t first_tile = tbase[g], ntile = cnt[g];
+    const int64_t pos = first_tile * RGCN_FUSE_TILE + (e - starts[g]);
+    if (pos < cap) {
+        col[pos] = (int32_t)(backward ? s : o);
+        rv[2 * pos] = (int32_t)(a - blk * fuse_rows);
+        rv[2 * pos + 1] = __float_as_int(val[orig]);
+    }
+    if (e == starts[g]) {
+        for (int64_t q = first_tile; q < first_tile + ntile && q * RGCN_FUSE_TILE < cap; ++q) tile_rel[q] = (int32_t)p;
+        const int64_t prev = e ? (int64_t)(keys[e - 1] / N / Rp) : -1;        // block of the previous run
+        for (int64_t b = prev + 1; b <= blk; ++b) blk_tile[b] = (int32_t)first_tile;
+    }
+    if (e == nnz - 1) {
+        const int64_t total = first_tile + ntile;
+        for (int64_t b = blk + 1; b <= NB; ++b) blk_tile[b] = (int32_t)total;
+        meta[1] = (int32_t)total;
+        meta[2] = total * RGCN_FUSE_TILE > cap ? 1 : 0;
+    }
+}
+
+__global__ void k_fused_item_counts(const int32_t* __restrict__ blk_tile, int64_t NB, int item_tiles,
+                                    int32_t* __restrict__ icnt) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b > NB) return;
+    int32_t n = 0;
+    if (b < NB) {
+        n = (blk_tile[b + 1] - blk_tile[b] + item_tiles - 1) / item_tiles;
+        if (n < 1) n = 1;                              // empty blocks still write their bias rows
+    }
+    icnt[b] = n;
+}
+
+__global__ void k_fused_fill_items(const int32_t* __restrict__ blk_tile, const int32_t* __restrict__ iptr, int64_t NB,
+                                   int item_tiles, int64_t bound, int32_t* __restrict__ items, int32_t* __restrict__ meta) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    const int32_t q0 = iptr[b], n = iptr[b + 1] - q0, t0 = blk_tile[b], t1 = blk_tile[b + 1];
+    for (int32_t i = 0; i < n; ++i) {
+        const int64_t q = (int64_t)q0 + i;
+        if (q >= bound) break;
+        const int32_t a = t0 + i * item_tiles;
+        int32_t z = a + item_tiles;
+        if (z > t1) z = t1;
+        reinterpret_cast<int4*>(items)[q] = make_int4((int)b, a, z, n > 1 ? 1 : 0);
+    }
+    if (n > 1) atomicAdd(meta + 3, 1);
+    if (b == NB - 1) meta[0] = iptr[NB];
+}
+
 // rows with more than RGCN_LONG_ROW edges (hubs) are listed so that kernels can process them cooperatively
 __global__ void k_long_rows(const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ list, int32_t* count) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -464,9 +553,21 @@ extern "C" int64_t rgcn_tile_steps_len(int64_t nnz, int64_t tile_edges, int64_t 
     return (nnz - 1) / tile_edges + 1 + ring_depth / 2 + 1;
 }
 
-extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges) {
-    (void)N;
-    return carve_build(nullptr, nnz, tile_groups(nnz, Rp, tile_edges)).total;
+static int64_t fused_blocks(int64_t N, int64_t fuse_rows) { return fuse_rows > 0 ? (N + fuse_rows - 1) / fuse_rows : 0; }
+
+// scans over (tile, relation) groups, queue steps and row blocks reuse the int scratch of the build
+static int64_t scratch_items(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges, int64_t fuse_rows) {
+    const int64_t a = tile_groups(nnz, Rp, tile_edges), b = fused_blocks(N, fuse_rows) + 2;
+    return a > b ? a : b;
+}
+
+extern "C" int64_t rgcn_fused_items_bound(int64_t N, int64_t fuse_rows, int64_t fuse_cap, int64_t item_tiles) {
+    if (fuse_rows <= 0 || item_tiles <= 0) return 0;
+    return fused_blocks(N, fuse_rows) + fuse_cap / RGCN_FUSE_TILE / item_tiles + 2;
+}
+
+extern "C" size_t rgcn_graph_workspace_bytes(int64_t nnz, int64_t N, int64_t Rp, int64_t tile_edges, int64_t fuse_rows) {
+    return carve_build(nullptr, nnz, scratch_items(nnz, N, Rp, tile_edges, fuse_rows)).total;
 }
 
 extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, int64_t Rp, int norm,
@@ -493,11 +594,14 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
     if (nnz > 0)
         RGCN_REQUIRE(triples && g->d_src && g->d_rel && g->d_val && g->s_dst && g->s_rel && g->s_val && g->r_dst &&
                          g->r_src && g->r_val && g->r_dslot && g->r_sslot && g->val, RGCN_ERR_ARG, "rgcn_graph_build: NULL plan array");
-    BuildWs b = carve_build(ws, nnz, tile_groups(nnz, Rp, g->tile_edges));
+    RGCN_REQUIRE(g->fuse_rows >= 0 && g->fuse_rows % RGCN_FUSE_TILE == 0 && g->fuse_rows < 65536, RGCN_ERR_ARG,
+                 "rgcn_graph_build: fuse_rows must be a multiple of 16 below 65536");
+    BuildWs b = carve_build(ws, nnz, scratch_items(nnz, N, Rp, g->tile_edges, g->fuse_rows));
     RGCN_REQUIRE(ws_bytes >= b.total && (ws || b.total == 0), RGCN_ERR_WORKSPACE,
                  "rgcn_graph_build: workspace %zu < %zu bytes", ws_bytes, b.total);
     g->num_nodes = N; g->num_rels = Rp; g->nnz = nnz;
     g->num_tiles = 0; g->tile_capacity = 0; g->num_long_dst = g->num_long_src = -1;
+    g->fuse_items[0] = g->fuse_items[1] = 0; g->fuse_split[0] = g->fuse_split[1] = 0;
     RGCN_REQUIRE(g->tile_edges >= 0, RGCN_ERR_ARG, "rgcn_graph_build: negative tile_edges");
     RGCN_REQUIRE(g->d_long && g->s_long, RGCN_ERR_ARG, "rgcn_graph_build: NULL long-row list");
     RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 8 * sizeof(int32_t), stream));
@@ -580,6 +684,49 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             const int64_t bound = rgcn_tile_items_bound(nnz, N, Rp, te);
             RGCN_LAUNCH(k_fill_items, grid_for(bound, kBlock), kBlock, 0, stream, tl.stepptr, tl.tilerow, rowptr, tl.slotneed,
                         T, lag, bound, reinterpret_cast<rgcn_tile_item*>(tl.items));
+        }
+    }
+    if (g->fuse_rows > 0) {
+        const int64_t FR = g->fuse_rows, NB = fused_blocks(N, FR), cap = g->fuse_cap;
+        const int item_tiles = (int)g->fuse_item_tiles;
+        RGCN_REQUIRE(cap > 0 && cap % RGCN_FUSE_TILE == 0 && cap < (int64_t)INT32_MAX, RGCN_ERR_ARG,
+                     "rgcn_graph_build: fuse_cap must be a positive multiple of 16 that fits int32");
+        RGCN_REQUIRE(item_tiles >= 1 && item_tiles <= RGCN_FUSE_MAX_ITEM_TILES, RGCN_ERR_ARG,
+                     "rgcn_graph_build: fuse_item_tiles %d out of range", item_tiles);
+        const unsigned __int128 fkey = (unsigned __int128)NB * (unsigned __int128)Rp * (unsigned __int128)N;
+        RGCN_REQUIRE((fkey >> 63) == 0, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: row-block key does not fit 64 bits");
+        const int fbits = bits_for(fkey);
+        const int64_t bound = rgcn_fused_items_bound(N, FR, cap, item_tiles);
+        for (int backward = 0; backward < 2; ++backward) {
+            rgcn_fused& fl = backward ? g->fb : g->ff;
+            RGCN_REQUIRE(fl.col && fl.rv && fl.tile_rel && fl.blk_tile && fl.items && fl.meta, RGCN_ERR_ARG,
+                         "rgcn_graph_build: NULL fused list array");
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.meta, 0, 4 * sizeof(int32_t), stream));
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.col, 0xFF, (size_t)cap * sizeof(int32_t), stream));
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.rv, 0, (size_t)cap * 2 * sizeof(int32_t), stream));
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.tile_rel, 0, (size_t)(cap / RGCN_FUSE_TILE) * sizeof(int32_t), stream));
+            RGCN_LAUNCH(k_make_block_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, FR, b.k0, b.i0);
+            size_t cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, fbits, stream));
+            rgcn::g_launches.fetch_add((fbits + 7) / 8 + 1, std::memory_order_relaxed);
+            // runs = (block, relation) segments of the sorted list
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, N, b.flag);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, N, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_fused_run_tiles, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.cnt);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.cnt, b.inv_d, (int)nnz, stream));
+            rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
+            RGCN_LAUNCH(k_fused_scatter, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, FR, NB,
+                        b.segid, b.starts, b.inv_d, b.cnt, g->val, cap, fl.col, fl.rv, fl.tile_rel, fl.blk_tile, fl.meta);
+            // work items: every row block, split into pieces of at most item_tiles tiles
+            RGCN_LAUNCH(k_fused_item_counts, grid_for(NB + 1, kBlock), kBlock, 0, stream, fl.blk_tile, NB, item_tiles, b.flag);
+            cub_bytes = b.cub_bytes;
+            RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)(NB + 1), stream));
+            rgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+            RGCN_LAUNCH(k_fused_fill_items, grid_for(NB, kBlock), kBlock, 0, stream, fl.blk_tile, b.segid, NB, item_tiles,
+                        bound, fl.items, fl.meta);
         }
     }
     return RGCN_OK;

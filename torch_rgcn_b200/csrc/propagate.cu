@@ -9,6 +9,7 @@
 #include "propagate_generic.cuh"
 #include "propagate_fast.cuh"
 #include "propagate_mma.cuh"
+#include "propagate_fused.cuh"
 
 using namespace rgcn;
 
@@ -197,6 +198,14 @@ bool tiled_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool 
            mma_shape_supported(s.nb, s.bi, s.bo);
 }
 
+// Fused row-block path (propagate_fused.cuh): bf16 features, four 16x16 blocks (64 -> 64), and a plan whose fused
+// list for this direction was built and fits (fuse_items > 0).
+bool fused_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool bf16, bool backward) {
+    return bf16 && g->fuse_rows > 0 && g->fuse_items[backward ? 1 : 0] > 0 && !p->featureless &&
+           p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 && s.nb == 4 && s.bi == 16 &&
+           s.bo == 16;
+}
+
 size_t tiled_ring_bytes(const rgcn_graph* g, int width) {
     return align_up((size_t)g->ring_depth * (size_t)g->tile_capacity * width * 2);
 }
@@ -210,6 +219,7 @@ extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_p
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
     size_t bytes = 0;
     if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
+    if (fused_path(g, p, s, x_dtype == RGCN_BF16, false)) return bytes + fused_ws_bytes(s.Rp);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
@@ -244,6 +254,10 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         A.form = RGCN_W_DENSE; A.W = weff;
     }
     const bool bf16 = x_dtype == RGCN_BF16 && !p->featureless;
+    if (fused_path(g, p, s, bf16, false)) {
+        void* fws = carve.take<char>(fused_ws_bytes(s.Rp));
+        return launch_fused_rows<float>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X), out, fws, st);
+    }
     if (tiled_path(g, p, s, bf16)) {
         int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
         __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.O)));
@@ -297,6 +311,7 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
     }
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.I * 4);   // fp32 staging of a bf16 feature gradient
+    if (fused_path(g, p, s, x_dtype == RGCN_BF16, true)) return bytes + fused_ws_bytes(s.Rp);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
@@ -333,8 +348,9 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     const bool mma_bwd = x_dtype == RGCN_BF16 && !p->featureless && p->form == RGCN_W_BLOCK && !p->blocks_self &&
                          !p->self_mask && s.nnz > 0 && mma_shape_supported(s.nb, s.bi, s.bo) &&
                          (gr->features || gr->blocks);
-    const bool tiled_bwd = mma_bwd && gr->features && tiled_path(g, p, s, true);
-    RGCN_REQUIRE(!mma_bwd || tiled_bwd || !gr->features || align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes,
+    const bool fused_bwd = mma_bwd && gr->features && fused_path(g, p, s, true, true);
+    const bool tiled_bwd = mma_bwd && !fused_bwd && gr->features && tiled_path(g, p, s, true);
+    RGCN_REQUIRE(!mma_bwd || fused_bwd || tiled_bwd || !gr->features || align_up((size_t)s.nnz * s.I * 2) <= kMaxMsgBytes,
                  RGCN_ERR_UNSUPPORTED, "rgcn_backward: message buffer too large; build the plan with tile_edges > 0");
     if (mma_bwd) {
         __nv_bfloat16* gb16 = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
@@ -342,6 +358,22 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         rc = launch_cast_colsum(G, s.N, s.O, gb16, gr->bias, st);
         if (rc) return rc;
         if (gr->blocks) RGCN_CHECK_CUDA(cudaMemsetAsync(gr->blocks, 0, s.blocks_elems * sizeof(float), st));
+        if (fused_bwd) {
+            // weight gradient: relation-major pass without messages; feature gradient: fused row-block kernel on the
+            // source-row lists with W^T slices, gathering the bf16 copy of grad_out
+            if (gr->blocks) {
+                RelArgs Rw{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, nullptr, g->r_val, p->blocks, s.nb};
+                rc = launch_rel_mma_bwd(Rw, static_cast<const __nv_bfloat16*>(X), gb16, nullptr, gr->blocks, max_chunks(s), st);
+                if (rc) return rc;
+            }
+            void* fws = carve.take<char>(fused_ws_bytes(s.Rp));
+            if (gx_bf16 && g->fuse_split[1] == 0)
+                return launch_fused_rows<__nv_bfloat16>(g, true, p->blocks, nullptr, gb16,
+                                                        static_cast<__nv_bfloat16*>(gr->features), fws, st);
+            rc = launch_fused_rows<float>(g, true, p->blocks, nullptr, gb16, gx_f32, fws, st);
+            if (rc) return rc;
+            return finish_gx();
+        }
         if (tiled_bwd) {
             // weight gradient: untiled relation-major pass (needs full relation batches); feature gradient: span kernel
             // on the source tiling with W^T fragments, messages stay in the ring

@@ -18,6 +18,10 @@ from .functional import rgcn_propagate
 from .graph import GraphPlan
 from .utils import select_b_init, select_w_init, schlichtkrull_normal_
 
+# RGCN_FUSED default: '1' routes bf16 64 -> 64 block layers to the fused row-block kernel (propagate_fused.cuh),
+# '0' keeps the two-phase tensor-core kernels (propagate_mma.cuh)
+_FUSED_DEFAULT = '0'
+
 
 def _unpack_decomposition(decomposition):
     d = decomposition if decomposition is not None else {}
@@ -133,24 +137,39 @@ class RelationalGraphConvolutionNC(Module):
             tile_bytes = int(float(env) * (1 << 20))
         return max(tile_bytes // row_bytes, 4096) if tile_bytes > 0 else 0
 
+    def _fuse_rows(self, features):
+        """Rows per block of the fused row-block kernel (bf16 features, four 16x16 blocks, i.e. 64 -> 64), 0 = off.
+
+        RGCN_FUSED=0 disables it, RGCN_FUSE_ROWS overrides the block height (a multiple of 16; 512 rows x 64 fp32
+        columns = 128 KB of the CTA's shared memory)."""
+        if (features is None or features.dtype != torch.bfloat16 or self.weight_decomp != 'block' or
+                self.in_features != 64 or self.out_features != 64 or self.num_blocks != 4):
+            return 0
+        if os.environ.get('RGCN_FUSED', _FUSED_DEFAULT) == '0':
+            return 0
+        return int(os.environ.get('RGCN_FUSE_ROWS', '512'))
+
     def _plan(self, device, features=None):
         t = self.triples
         tile_edges = self._tile_edges(features)
-        key = (str(device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, tile_edges)
+        fuse_rows = self._fuse_rows(features)
+        key = (str(device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, tile_edges, fuse_rows)
         if self._plan_cache is None or self._plan_cache[0] != key:
             nnz = t.size(0)
             n_general = int((nnz - self.num_nodes) / 2)          # reference layers.py:235
             norm = _lib.NORM_ROW if self.vertical_stacking else _lib.NORM_COL_SWAPPED
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
                              validate=self.validate_triples, tile_edges=tile_edges,
-                             ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
+                             ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), fuse_rows=fuse_rows,
+                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')))
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 
     def set_plan(self, plan):
         """Install an externally built plan (e.g. a relation shard, see parallel.py)."""
         t = self.triples
-        key = (str(plan.device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, plan.tile_edges)
+        key = (str(plan.device), t.data_ptr(), t._version, tuple(t.shape), self.vertical_stacking, plan.tile_edges,
+               plan.fuse_rows)
         self._plan_cache = (key, plan)
 
     def forward(self, features=None):

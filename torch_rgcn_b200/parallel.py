@@ -91,7 +91,10 @@ class RelationShardedNC(torch.nn.Module):
 
     def _local_plan(self, device, features=None):
         tile_edges = self.layer._tile_edges(features)
-        if self._local is None or self._local.device != device or self._local.tile_edges != tile_edges:
+        fuse = dict(fuse_rows=self.layer._fuse_rows(features),
+                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')))
+        if (self._local is None or self._local.device != device or self._local.tile_edges != tile_edges or
+                self._local.fuse_rows != fuse['fuse_rows']):
             L = self.layer
             tp = L.triples.to(device)
             counts = torch.bincount(tp[:, 1], minlength=L.num_relations).cpu()
@@ -101,14 +104,14 @@ class RelationShardedNC(torch.nn.Module):
                 # (p, s) segment counts are relation-local: normalise the shard directly
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_ROW,
                                         validate=L.validate_triples, tile_edges=tile_edges,
-                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
+                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), **fuse)
             else:
                 # the horizontal permutation pairs each edge with its inverse in another relation: take the
                 # per-edge weights from the full graph, then keep this rank's rows
                 full = L._plan(device)
                 self._local = GraphPlan(tp[mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT,
                                         val=full.val[:full.nnz][mask], validate=False, tile_edges=tile_edges,
-                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
+                                        ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), **fuse)
                 L._plan_cache = None
         return self._local
 
