@@ -145,7 +145,9 @@ typedef struct rgcn_fused {
     int32_t* col;           /* cap: row of the gathered matrix, -1 = padding */
     int32_t* rv;            /* 2 x cap: per entry {row - first row of its block, bits of the fp32 edge weight};
                                padding is {0, 0} */
-    int32_t* tile_rel;      /* cap / 16: relation of every tile */
+    int32_t* tile_rel;      /* cap / 16: relation of every tile; bit 31 set if two entries that the kernel would add
+                               in the same step (slots 0-7, then slots 8-15) share a row: the kernel then adds the
+                               tile's entries one at a time */
     int32_t* blk_tile;      /* NB + 1: first tile of every row block, NB = ceil(N / fuse_rows) */
     int32_t* items;         /* 4 x int32 per work item {block, first tile, end tile, shared};
                                capacity rgcn_fused_items_bound() */
@@ -193,6 +195,11 @@ typedef struct rgcn_graph {
     int64_t fuse_rows;      /* 0: no fused row-block lists (ff / fb unused); else rows per block (multiple of 16) */
     int64_t fuse_cap;       /* entries allocated per list (multiple of 16) */
     int64_t fuse_item_tiles;/* tiles per work item, 1 .. RGCN_FUSE_MAX_ITEM_TILES */
+    int64_t fuse_order;     /* placement of a run's edges in its tiles.  0: in row order.  1: sorted by (row % 4, row),
+                               dealt round-robin over the run's tiles, consecutive edges alternating between the
+                               two halves of a tile, so that edges with the same row are added in different steps
+                               and the four rows one shared-memory access phase touches fall into different
+                               bank groups (row % 4) whenever the run has them */
     int64_t fuse_items[2];  /* host copies of ff / fb meta[0] filled by the caller after the build;
                                0 = list unusable (overflow or not read back): the kernels fall back */
     int64_t fuse_split[2];  /* host copies of ff / fb meta[3] */

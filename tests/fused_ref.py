@@ -4,14 +4,14 @@ does with them.  Test infrastructure: the GPU plan is compared with `expected_li
 import numpy as np
 
 
-def expected_lists(tp, N, Rp, val, FR, item_tiles, backward):
+def expected_lists(tp, N, Rp, val, FR, item_tiles, backward, order=1):
     """numpy restatement of include/rgcn_b200.h: rgcn_fused for one direction."""
     s, p, o = tp[:, 0], tp[:, 1], tp[:, 2]
     a, other = (o, s) if backward else (s, o)
     blk = a // FR
-    key = (blk * Rp + p) * N + a
-    order = np.argsort(key, kind='stable')
-    grp = (key // N)[order]
+    key = ((blk * Rp + p) * 4 + (a % 4 if order else 0)) * N + a
+    order_mode, order = order, np.argsort(key, kind='stable')
+    grp = (key // N // 4)[order]
     starts = np.flatnonzero(np.r_[True, grp[1:] != grp[:-1]])
     ends = np.r_[starts[1:], len(order)]
     ntile = (ends - starts + 15) // 16
@@ -23,9 +23,21 @@ def expected_lists(tp, N, Rp, val, FR, item_tiles, backward):
     tile_rel = np.zeros(total, np.int64)
     NB = (N + FR - 1) // FR
     run_blk = grp[starts] // Rp
+    flags = np.zeros(total, bool)
     for g in range(len(starts)):
         e = order[starts[g]:ends[g]]
-        pos = tbase[g] * 16 + np.arange(len(e))
+        i = np.arange(len(e))
+        if order_mode:                      # dealt round-robin over the run's tiles, alternating between the halves
+            w = i // ntile[g]
+            tile_i, slot = i % ntile[g], (w % 2) * 8 + (w // 2 % 2) * 4 + w // 4
+        else:
+            tile_i, slot = i // 16, i % 16
+        pos = (tbase[g] + tile_i) * 16 + slot
+        for tl in range(ntile[g]):          # tiles in which two entries added in the same step share a row
+            for half in ((0, 1) if order_mode else (None,)):
+                sel = (tile_i == tl) if half is None else (tile_i == tl) & (slot // 8 == half)
+                rows_here = a[e[sel]]
+                flags[tbase[g] + tl] |= len(np.unique(rows_here)) < len(rows_here)
         col[pos] = other[e]
         row[pos] = a[e] - run_blk[g] * FR
         v[pos] = val[e]
@@ -40,7 +52,7 @@ def expected_lists(tp, N, Rp, val, FR, item_tiles, backward):
         for i in range(n):
             items.append((b, t0 + i * item_tiles, min(t1, t0 + (i + 1) * item_tiles), int(n > 1)))
     split = int(sum(1 for b in range(NB) if blk_tile[b + 1] - blk_tile[b] > item_tiles))
-    return dict(col=col, row=row, val=v, tile_rel=tile_rel, blk_tile=blk_tile, items=np.array(items, np.int64),
+    return dict(col=col, row=row, val=v, tile_rel=tile_rel, serial=flags, blk_tile=blk_tile, items=np.array(items, np.int64),
                 total=total, split=split)
 
 
@@ -55,11 +67,18 @@ def emulate_forward(lists, N, FR, X, blocks, bias):
         tile = np.zeros((FR, O))
         for ti in range(t0, t1):
             W = blocks[lists['tile_rel'][ti]]
-            for e in range(ti * 16, ti * 16 + 16):
-                if lists['val'][e] == 0:
+            for half in (0, 1):                          # the kernel adds slots 0-7, then 8-15, each as one step
+                ent = np.arange(ti * 16 + 8 * half, ti * 16 + 8 * half + 8)
+                ent = ent[lists['val'][ent] != 0]
+                if len(ent) == 0:
                     continue
-                x = X[lists['col'][e]].reshape(nb, bi)
-                tile[lists['row'][e]] += lists['val'][e] * np.einsum('bi,bio->bo', x, W).reshape(O)
+                x = X[lists['col'][ent]].reshape(len(ent), nb, bi)
+                msg = lists['val'][ent, None] * np.einsum('ebi,bio->ebo', x, W).reshape(len(ent), O)
+                rows = lists['row'][ent]
+                if lists['serial'][ti]:
+                    np.add.at(tile, rows, msg)
+                else:                                    # read-modify-write of all entries at once: equal rows would
+                    tile[rows] = tile[rows] + msg        # lose updates, which is what the plan's flag must prevent
         rows = slice(b * FR, min(N, (b + 1) * FR))
         n = rows.stop - rows.start
         if shared:

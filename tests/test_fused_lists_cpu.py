@@ -7,11 +7,12 @@ from fused_ref import emulate_forward, expected_lists
 from oracle import rgcn_oracle as orc
 
 
+@pytest.mark.parametrize('order', [0, 1])
 @pytest.mark.parametrize('FR,item_tiles', [(64, 512), (32, 3)])
-def test_walking_the_lists_reproduces_the_oracle(FR, item_tiles):
+def test_walking_the_lists_reproduces_the_oracle(FR, item_tiles, order):
     rng = np.random.RandomState(5)
     N, R, E = 300, 3, 2500
-    t = np.stack([rng.randint(0, N, E) ** 2 % N, rng.randint(0, R, E), rng.randint(0, N, E)], 1)
+    t = np.stack([rng.randint(0, N, E) ** 2 % N, rng.randint(0, R, E), rng.randint(0, N, E) % 20], 1)   # hubs + multi-edge segments
     tp = orc.add_inverse_and_self(t, N, R)
     Rp = 2 * R + 1
     blocks = rng.randn(Rp, 4, 16, 16).astype(np.float32)
@@ -20,9 +21,10 @@ def test_walking_the_lists_reproduces_the_oracle(FR, item_tiles):
     G = rng.randn(N, 64).astype(np.float32)
     ref_out, ref_g = orc.nc_layer(tp, N, Rp, {'blocks': blocks, 'bias': bias}, X, True, G)
     val = orc.nc_edge_values(tp, N, Rp, True)
-    fwd = expected_lists(tp, N, Rp, val, FR, item_tiles, backward=False)
+    fwd = expected_lists(tp, N, Rp, val, FR, item_tiles, backward=False, order=order)
     assert fwd['split'] > 0 or item_tiles == 512
+    assert fwd['serial'].any() and not fwd['serial'].all()
     np.testing.assert_allclose(emulate_forward(fwd, N, FR, X, blocks, bias), ref_out, atol=1e-4, rtol=1e-4)
-    bwd = expected_lists(tp, N, Rp, val, FR, item_tiles, backward=True)
+    bwd = expected_lists(tp, N, Rp, val, FR, item_tiles, backward=True, order=order)
     gx = emulate_forward(bwd, N, FR, G, blocks.transpose(0, 1, 3, 2), np.zeros(64))
     np.testing.assert_allclose(gx, ref_g['features'], atol=1e-4, rtol=1e-4)

@@ -15,8 +15,9 @@ from fused_ref import expected_lists as _expected_lists
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize('order', [0, 1])
 @pytest.mark.parametrize('FR,item_tiles,skew', [(64, 512, False), (512, 512, False), (32, 3, True)])
-def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew):
+def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew, order):
     from torch_rgcn_b200 import _lib
     from torch_rgcn_b200.graph import GraphPlan
     from torch_rgcn_b200.synthetic import random_triples
@@ -24,10 +25,11 @@ def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew):
     t = random_triples(N, R, E, seed=11, rel_dist='zipf' if skew else 'uniform', node_skew=skew)
     tp = orc.add_inverse_and_self(t.numpy(), N, R)
     Rp = 2 * R + 1
-    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles)
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles,
+                     fuse_order=order)
     val = plan.val[:plan.nnz].cpu().numpy()
     for d in (0, 1):
-        exp = _expected_lists(tp, N, Rp, val, FR, item_tiles, backward=bool(d))
+        exp = _expected_lists(tp, N, Rp, val, FR, item_tiles, backward=bool(d), order=order)
         arrs = {k: v.cpu().numpy() for k, v in plan._fused[d].items()}
         n_items, tiles, overflow, split = arrs['meta'].tolist()
         assert overflow == 0 and plan.fused_ok[d]
@@ -36,7 +38,8 @@ def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew):
         np.testing.assert_array_equal(arrs['col'][:n], exp['col'], err_msg=f'col d={d}')
         np.testing.assert_array_equal(arrs['rv'][:n, 0], exp['row'], err_msg=f'row d={d}')
         np.testing.assert_array_equal(np.ascontiguousarray(arrs['rv'][:n, 1]).view(np.float32), exp['val'], err_msg=f'val d={d}')
-        np.testing.assert_array_equal(arrs['tile_rel'][:tiles], exp['tile_rel'], err_msg=f'tile_rel d={d}')
+        np.testing.assert_array_equal(arrs['tile_rel'][:tiles] & 0x7fffffff, exp['tile_rel'], err_msg=f'tile_rel d={d}')
+        np.testing.assert_array_equal(arrs['tile_rel'][:tiles] < 0, exp['serial'], err_msg=f'serial flags d={d}')
         np.testing.assert_array_equal(arrs['blk_tile'], exp['blk_tile'], err_msg=f'blk_tile d={d}')
         assert n_items == len(exp['items']), (d, n_items, len(exp['items']))
         np.testing.assert_array_equal(arrs['items'][:n_items], exp['items'], err_msg=f'items d={d}')
@@ -61,12 +64,13 @@ def _graph(kind, N, R, E):
     return t
 
 
-def _run(cuda_device, monkeypatch, fused, N, R, t, vertical, grads, fuse_rows='512', item_tiles='512', seed=8):
+def _run(cuda_device, monkeypatch, fused, N, R, t, vertical, grads, fuse_rows='512', item_tiles='512', seed=8, order='1'):
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
     monkeypatch.setenv('RGCN_FUSED', '1' if fused else '0')
     monkeypatch.setenv('RGCN_FUSE_ROWS', fuse_rows)
     monkeypatch.setenv('RGCN_FUSE_ITEM_TILES', item_tiles)
     monkeypatch.setenv('RGCN_TILE_MB', '0')
+    monkeypatch.setenv('RGCN_FUSE_ORDER', order)
     tp = torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, R))
     torch.manual_seed(seed)
     layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=64,
@@ -101,14 +105,14 @@ def _close(got, ref, name, tol=1e-2):
 
 @pytest.mark.parametrize('kind,N,R,E', [('uniform', 3000, 9, 40000), ('hub', 3000, 9, 40000), ('multi', 1500, 4, 30000),
                                         ('uniform', 50, 2, 40)])
-@pytest.mark.parametrize('fuse_rows,item_tiles', [('512', '512'), ('64', '512'), ('128', '2')])
+@pytest.mark.parametrize('fuse_rows,item_tiles,order', [('512', '512', '1'), ('64', '512', '0'), ('128', '2', '1')])
 @pytest.mark.parametrize('grads', ['all', 'features_only'])
-def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows, item_tiles, grads):
+def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows, item_tiles, order, grads):
     """bf16 tolerance of the tensor-core paths: 1e-2 of the tensor's scale (features and MMA operands are bf16,
     products and sums fp32)."""
     t = _graph(kind, N, R, E)
     vertical = kind != 'hub'                       # hub graph also exercises the horizontal (permuted) weights
-    layer, tp, feats, out, G, plan = _run(cuda_device, monkeypatch, True, N, R, t, vertical, grads, fuse_rows, item_tiles)
+    layer, tp, feats, out, G, plan = _run(cuda_device, monkeypatch, True, N, R, t, vertical, grads, fuse_rows, item_tiles, order=order)
     if item_tiles == '2' and E > 1000:
         assert plan.c.fuse_split[0] > 0 and plan.c.fuse_split[1] > 0, 'expected split row blocks'
     ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().float().cpu().numpy(),

@@ -338,15 +338,16 @@ __global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t*
 }
 
 // ---- fused row-block lists (rgcn_fused) ----------------------------------------------------------------
-// key = (block * R' + p) * N + a,  a = block-side endpoint, block = a / fuse_rows
+// key = ((block * R' + p) * 4 + c) * N + a,  a = block-side endpoint, block = a / fuse_rows,
+// c = a % 4 (bank group of the row's slice in the shared-memory tile) for fuse_order 1, else 0
 __global__ void k_make_block_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
-                                  int64_t fuse_rows, uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+                                  int64_t fuse_rows, int order, uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     int64_t s = t[3 * e], p = t[3 * e + 1], o = t[3 * e + 2];
     if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
     const int64_t a = backward ? o : s;
-    keys[e] = ((uint64_t)(a / fuse_rows) * Rp + p) * N + a;
+    keys[e] = (((uint64_t)(a / fuse_rows) * Rp + p) * 4 + (order ? (a & 3) : 0)) * N + a;
     idx[e] = (int32_t)e;
 }
 
@@ -358,11 +359,18 @@ __global__ void k_fused_run_tiles(int64_t nnz, const int32_t* __restrict__ segid
     cnt[g] = g < segid[nnz - 1] ? (ends[g] - starts[g] + RGCN_FUSE_TILE - 1) / RGCN_FUSE_TILE : 0;
 }
 
-// sorted edge e of run g goes to entry tbase[g] * 16 + (e - starts[g]); the first edge of a run also labels the
-// run's tiles and, for the first run of a row block, the block's first tile
+// Sorted edge e is edge i = e - starts[g] of run g, which owns tiles tbase[g] .. tbase[g] + cnt[g] - 1:
+//   order 0: tile i / 16, slot i % 16;
+//   order 1: tile i % cnt[g]; the tile's w-th edge (w = i / cnt[g]) takes slot 8 (w & 1) + 4 (w >> 1 & 1) + (w >> 2):
+//            odd / even w alternate between the two halves of the tile (two edges with the same row are
+//            neighbours in w, so they are added in different steps), and each group of four consecutive
+//            slots holds w, w + 4, w + 8, w + 12, i.e. one row of every bank group when the run has them.
+// A tile in which two edges with the same row would be added in the same step is flagged (bit 31 of tile_rel):
+// order 0: any pair inside the tile; order 1: a pair inside one half, i.e. a row with three or more edges.  The first edge of a
+// run also labels the run's tiles and, for the first run of a row block, the block's first tile.
 __global__ void k_fused_scatter(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
                                 const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
-                                int64_t fuse_rows, int64_t NB, const int32_t* __restrict__ segid,
+                                int64_t fuse_rows, int order, int64_t NB, const int32_t* __restrict__ segid,
                                 const int32_t* __restrict__ starts, const int32_t* __restrict__ tbase,
                                 const int32_t* __restrict__ cnt, const float* __restrict__ val, int64_t cap,
                                 int32_t* __restrict__ col, int32_t* __restrict__ rv, int32_t* __restrict__ tile_rel,
@@ -371,22 +379,33 @@ __global__ void k_fused_scatter(const uint64_t* __restrict__ keys, const int32_t
     if (e >= nnz) return;
     const uint64_t k = keys[e];
     const int64_t a = (int64_t)(k % N);
-    const uint64_t grp = k / N;
+    const uint64_t grp = k / N / 4;
     const int64_t p = (int64_t)(grp % Rp), blk = (int64_t)(grp / Rp);
     const int32_t g = segid[e] - 1;
     const int32_t orig = perm[e];
     int64_t s = t[3 * (int64_t)orig], pp = t[3 * (int64_t)orig + 1], o = t[3 * (int64_t)orig + 2];
     if (s < 0 || s >= N || o < 0 || o >= N || pp < 0 || pp >= Rp) s = o = 0;
     const int64_t first_tile = tbase[g], ntile = cnt[g];
-    const int64_t pos = first_tile * RGCN_FUSE_TILE + (e - starts[g]);
+    const int64_t i = e - starts[g];
+    int64_t tile_i, slot, twin;                      // twin: nearest earlier edge of the run that shares the tile
+    if (order) {
+        tile_i = i % ntile; twin = 2 * ntile;
+        const int64_t w = i / ntile;
+        slot = (w & 1) * 8 + ((w >> 1) & 1) * 4 + (w >> 2);
+    } else {
+        tile_i = i / RGCN_FUSE_TILE; slot = i % RGCN_FUSE_TILE; twin = slot ? 1 : 0;
+    }
+    const int64_t pos = (first_tile + tile_i) * RGCN_FUSE_TILE + slot;
     if (pos < cap) {
         col[pos] = (int32_t)(backward ? s : o);
         rv[2 * pos] = (int32_t)(a - blk * fuse_rows);
         rv[2 * pos + 1] = __float_as_int(val[orig]);
+        // equal rows of a run are neighbours in the sorted list, so one look-back finds any pair inside a tile
+        if (twin && i >= twin && (int64_t)(keys[e - twin] % N) == a) atomicOr(tile_rel + first_tile + tile_i, (int)0x80000000);
     }
     if (e == starts[g]) {
-        for (int64_t q = first_tile; q < first_tile + ntile && q * RGCN_FUSE_TILE < cap; ++q) tile_rel[q] = (int32_t)p;
-        const int64_t prev = e ? (int64_t)(keys[e - 1] / N / Rp) : -1;        // block of the previous run
+        for (int64_t q = first_tile; q < first_tile + ntile && q * RGCN_FUSE_TILE < cap; ++q) atomicOr(tile_rel + q, (int)p);
+        const int64_t prev = e ? (int64_t)(keys[e - 1] / N / 4 / Rp) : -1;    // block of the previous run
         for (int64_t b = prev + 1; b <= blk; ++b) blk_tile[b] = (int32_t)first_tile;
     }
     if (e == nnz - 1) {
@@ -693,7 +712,8 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
                      "rgcn_graph_build: fuse_cap must be a positive multiple of 16 that fits int32");
         RGCN_REQUIRE(item_tiles >= 1 && item_tiles <= RGCN_FUSE_MAX_ITEM_TILES, RGCN_ERR_ARG,
                      "rgcn_graph_build: fuse_item_tiles %d out of range", item_tiles);
-        const unsigned __int128 fkey = (unsigned __int128)NB * (unsigned __int128)Rp * (unsigned __int128)N;
+        const int order = g->fuse_order ? 1 : 0;
+        const unsigned __int128 fkey = (unsigned __int128)NB * (unsigned __int128)Rp * 4 * (unsigned __int128)N;
         RGCN_REQUIRE((fkey >> 63) == 0, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: row-block key does not fit 64 bits");
         const int fbits = bits_for(fkey);
         const int64_t bound = rgcn_fused_items_bound(N, FR, cap, item_tiles);
@@ -705,20 +725,20 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             RGCN_CHECK_CUDA(cudaMemsetAsync(fl.col, 0xFF, (size_t)cap * sizeof(int32_t), stream));
             RGCN_CHECK_CUDA(cudaMemsetAsync(fl.rv, 0, (size_t)cap * 2 * sizeof(int32_t), stream));
             RGCN_CHECK_CUDA(cudaMemsetAsync(fl.tile_rel, 0, (size_t)(cap / RGCN_FUSE_TILE) * sizeof(int32_t), stream));
-            RGCN_LAUNCH(k_make_block_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, FR, b.k0, b.i0);
+            RGCN_LAUNCH(k_make_block_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, FR, order, b.k0, b.i0);
             size_t cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, fbits, stream));
             rgcn::g_launches.fetch_add((fbits + 7) / 8 + 1, std::memory_order_relaxed);
-            // runs = (block, relation) segments of the sorted list
-            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, N, b.flag);
+            // runs = (block, relation) segments of the sorted list: equal key / (4 N)
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, b.flag);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
-            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, N, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, b.segid, b.starts, b.ends);
             RGCN_LAUNCH(k_fused_run_tiles, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.cnt);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.cnt, b.inv_d, (int)nnz, stream));
             rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
-            RGCN_LAUNCH(k_fused_scatter, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, FR, NB,
+            RGCN_LAUNCH(k_fused_scatter, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, FR, order, NB,
                         b.segid, b.starts, b.inv_d, b.cnt, g->val, cap, fl.col, fl.rv, fl.tile_rel, fl.blk_tile, fl.meta);
             // work items: every row block, split into pieces of at most item_tiles tiles
             RGCN_LAUNCH(k_fused_item_counts, grid_for(NB + 1, kBlock), kBlock, 0, stream, fl.blk_tile, NB, item_tiles, b.flag);

@@ -15,9 +15,10 @@
 //                packed table one stage ahead) and adds val * result into its private column slice of the
 //                shared-memory tile.  No two warps ever touch the same address, so the accumulation needs no
 //                atomics and its order is fixed by the plan: results are run-to-run deterministic.
-//   duplicates = two entries of one tile with the same row (a (row, relation) segment longer than one edge) sit
-//                next to each other because runs are sorted by row; a tile half that contains such a pair is
-//                accumulated one entry at a time
+//   duplicates = tiles in which two entries share a row (a (row, relation) segment longer than one edge) are
+//                flagged by the plan (bit 31 of tile_rel) and accumulated one entry at a time
+//   banks      = a row's 32-byte slice sits in bank group row % 4; with fuse_order 1 the plan places a run's
+//                edges so that the four rows of one access phase come from different groups when possible
 //   flush      = out[row] = bias + sum, 256-byte coalesced rows (fp32, or bf16 for a bf16 feature gradient); items
 //                of a split (hub) block add into rows pre-set by k_fused_init_shared with fp32 atomics
 //
@@ -102,7 +103,6 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
     const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X);
     const uint2* wmine = A.wslice + (size_t)warp * 32 + lane;
     unsigned char* myslice = tile + (size_t)warp * slice_stride + t * 8;
-    constexpr unsigned kFull = 0xffffffffu;
 
     while (true) {
         if (tid == 0) *s_item = atomicAdd(A.counter, 1);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int ti = 4 * k + j;
-                const int rel = ti < nt ? s_rel[ti] : 0;
+                const int rel = ti < nt ? (s_rel[ti] & 0x7fffffff) : 0;
                 w[j] = __ldg(wmine + (size_t)rel * 256);
             }
         };
@@ -176,22 +176,20 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
                 ldmatrix_x4(a, smem_u32(xs + j * kTileBytes + tile_off(row, chunk)));
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_bf16_16816(c, a, wc[j].x, wc[j].y);
+                const bool serial = s_rel[4 * k + j] < 0;          // plan flag: two entries of this tile share a row
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {           // entries g (c[0], c[1]) then g + 8 (c[2], c[3])
                     const int2 r = rvs[j * 16 + g + 8 * half];
                     const bool valid = r.y != 0;                // padding and zero-weight edges add nothing
                     const float v = __int_as_float(r.y), x0 = c[2 * half], x1 = c[2 * half + 1];
                     float2* p = reinterpret_cast<float2*>(myslice + (size_t)r.x * 32);
-                    const int nrow = __shfl_down_sync(kFull, r.x, 4);
-                    const int nval = __shfl_down_sync(kFull, r.y, 4);
-                    const bool dup = valid && lane < 28 && nval != 0 && nrow == r.x;
-                    if (!__any_sync(kFull, dup)) {
+                    if (!serial) {
                         if (valid) {
                             float2 o = *p;
                             o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
                             *p = o;
                         }
-                    } else {                                    // equal rows inside this half: one entry at a time
+                    } else {                                    // equal rows may meet in this half: one entry at a time
 #pragma unroll 1
                         for (int i = 0; i < 8; ++i) {
                             if (valid && g == i) {

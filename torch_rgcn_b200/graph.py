@@ -19,7 +19,7 @@ class GraphPlan:
     """
 
     def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True,
-                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=512):
+                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=512, fuse_order=1):
         _lib.require_cuda(triples_plus)
         assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
         t = triples_plus.contiguous()
@@ -73,6 +73,7 @@ class GraphPlan:
             assert self.fuse_rows % 16 == 0 and 16 <= self.fuse_rows <= 4096
             cap = (2 * nnz + 15) // 16 * 16 + 16
             g.fuse_cap, g.fuse_item_tiles = cap, max(1, min(int(fuse_item_tiles), 512))
+            g.fuse_order = self.fuse_order = 1 if fuse_order else 0
             NB = (num_nodes + self.fuse_rows - 1) // self.fuse_rows
             n_items = _lib.lib.rgcn_fused_items_bound(num_nodes, self.fuse_rows, cap, g.fuse_item_tiles)
             for fl in (g.ff, g.fb):

@@ -161,7 +161,8 @@ class RelationalGraphConvolutionNC(Module):
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
                              validate=self.validate_triples, tile_edges=tile_edges,
                              ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), fuse_rows=fuse_rows,
-                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')))
+                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
+                             fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

@@ -92,7 +92,8 @@ class RelationShardedNC(torch.nn.Module):
     def _local_plan(self, device, features=None):
         tile_edges = self.layer._tile_edges(features)
         fuse = dict(fuse_rows=self.layer._fuse_rows(features),
-                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')))
+                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
+                             fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
         if (self._local is None or self._local.device != device or self._local.tile_edges != tile_edges or
                 self._local.fuse_rows != fuse['fuse_rows']):
             L = self.layer
