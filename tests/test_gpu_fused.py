@@ -126,7 +126,7 @@ def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows
 
 
 def test_fused_is_reproducible_and_agrees_with_two_phase(cuda_device, monkeypatch):
-    N, R, E = 4000, 7, 50000
+    N, R, E = 4000, 7, 20000
     t = _graph('uniform', N, R, E)
     la, _, fa, out_a, _, plan = _run(cuda_device, monkeypatch, True, N, R, t, True, 'all')
     assert plan.c.fuse_split[0] == 0

@@ -6,10 +6,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/smi.txt 2>
 echo "== fused tests"; timeout 600 python -m pytest tests/test_gpu_fused.py -q -x 2>&1 | tail -40 | tee $O/test_fused.log
 echo "== sweep"; timeout 400 python tools/fused_sweep.py 0 512 384 256 2>&1 | tail -12 | tee $O/sweep.log
 RGCN_FUSE_ORDER=0 timeout 200 python tools/fused_sweep.py 512 2>&1 | tail -3 | tee $O/sweep_order0.log
-SWEEP_SKEW=1 timeout 300 python tools/fused_sweep.py 0 512 2>&1 | tail -4 | tee $O/sweep_skew.log
 echo "== full gpu suite"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee $O/test_all.log
 echo "== bench"; RGCN_FUSED=1 timeout 400 python bench.py > $O/bench_fused.json 2> $O/bench_fused.err; tail -c 600 $O/bench_fused.json
-RGCN_FUSED=0 timeout 400 python bench.py --no-cpu-baseline > $O/bench_twophase.json 2> $O/bench_twophase.err; tail -c 300 $O/bench_twophase.json
 echo "== ncu"
 RGCN_FUSED=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fused.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_b.log 2>&1
 RGCN_FUSED=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_fused_rows -s 2 -c 2 -f -o $O/fused_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_full.log 2>&1

@@ -8,8 +8,8 @@
 //   work item  = (row block, range of 16-entry tiles) from the plan's rgcn_fused list: the block's edges sorted by
 //                (relation, row), every (block, relation) run padded to whole tiles -> one relation per MMA tile
 //   pipeline   = 64-entry stages (4 tiles): the gathered rows (64 x 128 B, XOR-swizzled like propagate_mma.cuh) and
-//                the {row, val} records land through cp.async, kFuStages - 1 stages in flight; the gather indices of
-//                the stage after those are prefetched into registers one iteration earlier
+//                the {row, val} records land through cp.async, kFuAhead stages in flight; the gather indices and
+//                the weight slices are requested equally early into register rings (see the note in the kernel)
 //   ownership  = warp w owns output columns [8w, 8w + 8): per tile it runs ONE mma.sync.m16n8k16 (A = the 16
 //                inputs of block w / 2 of the 16 gathered rows, B = its 16 x 8 weight slice, prefetched from the
 //                packed table one stage ahead) and adds val * result into its private column slice of the
@@ -31,7 +31,8 @@
 
 namespace rgcn {
 
-constexpr int kFuStages = 8;
+constexpr int kFuAhead = 5;                            // stages in flight (gathers, indices, weight slices)
+constexpr int kFuStages = kFuAhead + 1;
 constexpr int kFuStageEntries = 64;
 constexpr int kFuXBytes = kFuStageEntries * 128;       // gathered rows of one stage
 constexpr int kFuRvBytes = kFuStageEntries * 8;        // {row, val} records of one stage
@@ -103,6 +104,11 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
     const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X);
     const uint2* wmine = A.wslice + (size_t)warp * 32 + lane;
     unsigned char* myslice = tile + (size_t)warp * slice_stride + t * 8;
+    float4 bias_lo = make_float4(0.f, 0.f, 0.f, 0.f), bias_hi = bias_lo;   // flush role: columns 8 (tid % 8) .. + 7
+    if (A.bias) {
+        bias_lo = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * (tid & 7));
+        bias_hi = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * (tid & 7) + 1);
+    }
 
     while (true) {
         if (tid == 0) *s_item = atomicAdd(A.counter, 1);
@@ -150,61 +156,88 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
             }
         };
 
-        int pc0[kFuStages - 1], pc1[kFuStages - 1], n0, n1;
+        // Everything the loop reads from global memory is requested kFuAhead stages early: the L1 returns data in
+        // request order, so a plain load issued now completes only after every gather already in flight -- a load
+        // consumed one stage later would stall for the whole depth of the gather pipeline.
+        //   colr[u] : gather indices of stage k + kFuAhead   (k % kFuAhead == u), refilled for stage k + 2 kFuAhead
+        //   wr[u]   : weight slices of stage k,               refilled for stage k + kFuAhead
+        int colr[kFuAhead][2];
+        uint2 wr[kFuAhead][4];
+        {
+            int pc[kFuAhead][2];
 #pragma unroll
-        for (int k = 0; k < kFuStages - 1; ++k) load_cols(k, pc0[k], pc1[k]);
-        load_cols(kFuStages - 1, n0, n1);
-        __syncthreads();                                        // tile zeroed, s_rel filled
+            for (int d = 0; d < kFuAhead; ++d) load_cols(d, pc[d][0], pc[d][1]);
 #pragma unroll
-        for (int k = 0; k < kFuStages - 1; ++k) issue(k, pc0[k], pc1[k]);
-        uint2 wc[4], wn[4];
-        load_w(0, wc);
+            for (int d = 0; d < kFuAhead; ++d) load_cols(kFuAhead + d, colr[d][0], colr[d][1]);
+            __syncthreads();                                    // tile zeroed, s_rel filled
+#pragma unroll
+            for (int d = 0; d < kFuAhead; ++d) load_w(d, wr[d]);
+#pragma unroll
+            for (int d = 0; d < kFuAhead; ++d) issue(d, pc[d][0], pc[d][1]);
+        }
 
-        for (int k = 0; k < nst; ++k) {
-            cp_async_wait<kFuStages - 2>();                     // stage k has landed (this thread's copies)
-            __syncthreads();                                    // ... everyone's, and stage k - 1 is fully consumed
-            issue(k + kFuStages - 1, n0, n1);                   // refills the buffer of stage k - 1
-            load_cols(k + kFuStages, n0, n1);
-            load_w(k + 1, wn);
-            const unsigned char* xs = xst + (size_t)(k % kFuStages) * kFuXBytes;
-            const int2* rvs = reinterpret_cast<const int2*>(rvst + (size_t)(k % kFuStages) * kFuRvBytes);
+        for (int k0 = 0; k0 < nst; k0 += kFuAhead) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (4 * k + j >= nt) break;
-                uint32_t a[4];
-                const int row = (lane & 7) + ((lane >> 3) & 1) * 8, chunk = kb * 2 + (lane >> 4);
-                ldmatrix_x4(a, smem_u32(xs + j * kTileBytes + tile_off(row, chunk)));
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16_16816(c, a, wc[j].x, wc[j].y);
-                const bool serial = s_rel[4 * k + j] < 0;          // plan flag: two entries of this tile share a row
+            for (int u = 0; u < kFuAhead; ++u) {
+                const int k = k0 + u;
+                if (k >= nst) break;
+                cp_async_wait<kFuAhead - 1>();                  // stage k has landed (this thread's copies)
+                __syncthreads();                                // ... everyone's, and stage k - 1 is fully consumed
+                issue(k + kFuAhead, colr[u][0], colr[u][1]);    // refills the buffer of stage k - 1
+                load_cols(k + 2 * kFuAhead, colr[u][0], colr[u][1]);
+                uint2 w[4];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {           // entries g (c[0], c[1]) then g + 8 (c[2], c[3])
-                    const int2 r = rvs[j * 16 + g + 8 * half];
-                    const bool valid = r.y != 0;                // padding and zero-weight edges add nothing
-                    const float v = __int_as_float(r.y), x0 = c[2 * half], x1 = c[2 * half + 1];
-                    float2* p = reinterpret_cast<float2*>(myslice + (size_t)r.x * 32);
-                    if (!serial) {
-                        if (valid) {
-                            float2 o = *p;
-                            o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
-                            *p = o;
-                        }
-                    } else {                                    // equal rows may meet in this half: one entry at a time
-#pragma unroll 1
-                        for (int i = 0; i < 8; ++i) {
-                            if (valid && g == i) {
+                for (int j = 0; j < 4; ++j) w[j] = wr[u][j];
+                load_w(k + kFuAhead, wr[u]);
+                const unsigned char* xs = xst + (size_t)(k % kFuStages) * kFuXBytes;
+                const int2* rvs = reinterpret_cast<const int2*>(rvst + (size_t)(k % kFuStages) * kFuRvBytes);
+                // phase a: the four tiles' products and {row, val} records (independent of each other)
+                float c[4][4];
+                int2 r[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+                    r[j][0] = r[j][1] = make_int2(0, 0);
+                    if (4 * k + j < nt) {
+                        uint32_t a[4];
+                        const int row = (lane & 7) + ((lane >> 3) & 1) * 8, chunk = kb * 2 + (lane >> 4);
+                        ldmatrix_x4(a, smem_u32(xs + j * kTileBytes + tile_off(row, chunk)));
+                        mma_bf16_16816(c[j], a, w[j].x, w[j].y);
+                        r[j][0] = rvs[j * 16 + g];
+                        r[j][1] = rvs[j * 16 + g + 8];
+                    }
+                }
+                // phase b: add val * product into this warp's column slice, slots 0-7 then 8-15 of every tile
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (4 * k + j >= nt) break;
+                    const bool serial = s_rel[4 * k + j] < 0;   // plan flag: two entries of one step share a row
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const bool valid = r[j][half].y != 0;   // padding and zero-weight edges add nothing
+                        const float v = __int_as_float(r[j][half].y), x0 = c[j][2 * half], x1 = c[j][2 * half + 1];
+                        float2* p = reinterpret_cast<float2*>(myslice + (size_t)r[j][half].x * 32);
+                        if (!serial) {
+                            if (valid) {
                                 float2 o = *p;
                                 o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
                                 *p = o;
                             }
-                            __syncwarp();
+                        } else {                                // one entry at a time
+#pragma unroll 1
+                            for (int i = 0; i < 8; ++i) {
+                                if (valid && g == i) {
+                                    float2 o = *p;
+                                    o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
+                                    *p = o;
+                                }
+                                __syncwarp();
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) wc[j] = wn[j];
         }
         cp_async_wait<0>();
         __syncthreads();
@@ -218,12 +251,8 @@ __global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_b
             float4 lo = src[0], hi = src[1];
             const size_t o = (size_t)(row0 + r) * kFuWidth + 8 * w;
             if (!shared_item) {
-                if (A.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * w);
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * w + 1);
-                    lo.x += b0.x; lo.y += b0.y; lo.z += b0.z; lo.w += b0.w;
-                    hi.x += b1.x; hi.y += b1.y; hi.z += b1.z; hi.w += b1.w;
-                }
+                lo.x += bias_lo.x; lo.y += bias_lo.y; lo.z += bias_lo.z; lo.w += bias_lo.w;
+                hi.x += bias_hi.x; hi.y += bias_hi.y; hi.z += bias_hi.z; hi.w += bias_hi.w;
                 if constexpr (sizeof(OT) == 2) {
                     *reinterpret_cast<uint4*>(out + o) = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w),
                                                                     pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));

@@ -71,7 +71,7 @@ class GraphPlan:
         self._fused = []
         if self.fuse_rows > 0:
             assert self.fuse_rows % 16 == 0 and 16 <= self.fuse_rows <= 4096
-            cap = (2 * nnz + 15) // 16 * 16 + 16
+            cap = (2 * nnz + 15) // 16 * 16 + 16 * 1024
             g.fuse_cap, g.fuse_item_tiles = cap, max(1, min(int(fuse_item_tiles), 512))
             g.fuse_order = self.fuse_order = 1 if fuse_order else 0
             NB = (num_nodes + self.fuse_rows - 1) // self.fuse_rows
