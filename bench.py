@@ -51,6 +51,10 @@ WORKLOADS = {
                         decomp={'type': 'basis', 'num_bases': 30}, dtype='f32', vertical=False,
                         label='MUTAG-shaped 2-layer NodeClassifier step (23,644 nodes, R\'=47, nnz=172,098 per layer), '
                               'basis B=30, hidden 16, 2 classes, fp32'),
+    # the DistMult decoder step of the WN18 c-rgcn config (BASELINE configs[3])
+    'wn18_decoder': dict(shape='wn18', kind='decoder', in_f=128, out_f=128, decomp=None, dtype='f32', vertical=False,
+                         label='WN18-shaped DistMult decoder step (40,943 nodes x 128, 18 relations; 141,442 positives + '
+                               '10 negatives each = 1,555,862 scored triples): scores + L2 penalty + BCE loss, fp32'),
     'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
                 vertical=True, raw=True,
                 label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
@@ -507,6 +511,130 @@ def run_model(args):
         flush=True)
 
 
+def run_decoder(args):
+    """DistMult decoder step (reference predict_links.py:132-153 + models.py:239-244): negative sampling, scores of
+    positives and negatives, Schlichtkrull L2 penalty, BCE-with-logits, backward to the node embeddings and the
+    relation embeddings.  CPU baseline: the reference's own torch expressions on the host cores, bounded sample."""
+    import torch.nn.functional as F
+    from torch_rgcn_b200 import _lib
+    from torch_rgcn_b200.decoder import DistMult, negative_sampling
+    from torch_rgcn_b200.synthetic import SHAPES, random_triples
+    wl = WORKLOADS[args.workload]
+    dev = torch.device('cuda', 0)
+    N, R, E = SHAPES[wl['shape']]
+    d, rate = wl['in_f'], 10
+    pos = random_triples(N, R, E, seed=0, device=dev)
+    torch.manual_seed(2)
+    dec = DistMult(R, d, N, R).to(dev)
+    dec.validate_triples = False                       # no per-call host sync inside the timed region
+    nodes = torch.randn(N, d, device=dev, requires_grad=True)
+    labels = torch.cat([torch.ones(E, device=dev), torch.zeros(E * rate, device=dev)])
+
+    def make_batch():
+        neg = pos.clone()[:, None, :].expand(E, rate, 3).contiguous()
+        return torch.cat([pos, negative_sampling(neg, N, 0.5, device=dev)], dim=0)
+
+    def step(batch, ev=None):
+        nodes.grad = None
+        dec.relations.grad = None
+        if ev:
+            ev[0].record()
+        scores = dec(batch, nodes)
+        loss = F.binary_cross_entropy_with_logits(scores, labels) + 0.01 * dec.s_penalty(batch, nodes)
+        if ev:
+            ev[1].record()
+        loss.backward()
+        if ev:
+            ev[2].record()
+        return loss
+
+    batch = make_batch()
+    B = batch.size(0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step(batch)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.lib.rgcn_launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        step(batch, evs[k])
+    torch.cuda.synchronize()
+    launches = _lib.lib.rgcn_launch_count() - l0
+    ms_fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    ms_bwd = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    # e2e: positives arrive from pinned host memory, negatives are sampled on the device, the loss goes back
+    hpos = pos.cpu().pin_memory()
+    dpos = torch.empty_like(pos)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dpos.copy_(hpos, non_blocking=True)
+        neg = dpos.clone()[:, None, :].expand(E, rate, 3).contiguous()
+        step(torch.cat([dpos, negative_sampling(neg, N, 0.5, device=dev)], dim=0)).item()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ms = ms_fwd + ms_bwd
+    # algorithmic bytes: forward reads the triple (24 B) and three embedding rows and writes a score; the penalty
+    # re-reads the rows; backward re-reads them and adds two node rows (the relation gradient stays on chip)
+    b_f = B * (24 + 3 * d * 4 + 4)
+    b_b = B * (24 + 3 * d * 4 + 4 + 2 * d * 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.0)
+    line = {
+        'metric': 'distmult_triples_per_sec_fwd_bwd', 'value': B / (ms * 1e-3), 'unit': 'triples/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'num_relations': R, 'dim': d,
+                   'triples_per_step': B, 'l2': 'L2 flushed (256 MB write) between timed steps; the 21 MB node table is '
+                                                'L2-resident within a step, so the gather model can exceed the HBM peak'},
+        'ms_fwd': ms_fwd, 'ms_bwd': ms_bwd,
+        'e2e': {'value': B / (ms_e2e * 1e-3), 'unit': 'triples/s', 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': hpos.numel() * 8, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'k_distmult_fwd + k_distmult_penalty (forward), k_distmult_bwd + k_distmult_penalty_bwd',
+                     'bound': 'hbm', 'achieved': (b_f + b_b) / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                     'frac': (b_f + b_b) / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                     'note': 'gathered rows come from L2 (node table 21 MB); fraction is of the HBM peak by convention'},
+        'clocks': clocks,
+    }
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        nb = min(B, 200000)
+        cb = batch[:nb].cpu()
+        cn = nodes.detach().cpu().clone().requires_grad_(True)
+        cr = dec.relations.detach().cpu().clone().requires_grad_(True)
+        cl = labels[:nb].cpu()
+
+        def cpu_step():                                 # reference layers.py:77-98 expressions
+            s, p, o = cn[cb[:, 0]], cr[cb[:, 1]], cn[cb[:, 2]]
+            scores = (s * p * o).sum(dim=-1)
+            pen = s.pow(2).mean() + p.pow(2).mean() + o.pow(2).mean()
+            (F.binary_cross_entropy_with_logits(scores, cl) + 0.01 * pen).backward()
+            cn.grad = None
+            cr.grad = None
+        cpu_step()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or time.perf_counter() - t0 < 5.0:
+            cpu_step()
+            n += 1
+        cpu_s = (time.perf_counter() - t0) / n
+        line['cpu_baseline'] = {'value': nb / cpu_s, 'unit': 'triples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                's_per_step': cpu_s, 'steps': n,
+                                'sample': f'first {nb} triples of the batch with the reference\'s torch expressions '
+                                          f'(index, multiply, sum, mean, autograd) on the host cores'}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_gpu(args):
     """Informational: the reference's torch.sparse algorithm (the port) on CUDA tensors at full workload size —
     the north-star's '>= 1.0x the reference GPU path' comparison.  Falls back to a scaled graph on OOM."""
@@ -601,6 +729,8 @@ def main():
         run_reference(args)
     elif WORKLOADS[args.workload]['kind'] == 'nc_model':
         run_model(args)
+    elif WORKLOADS[args.workload]['kind'] == 'decoder':
+        run_decoder(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -266,6 +266,37 @@ int rgcn_backward(const rgcn_graph* graph, const rgcn_params* params, const void
                   const float* grad_out, const rgcn_grads* grads, void* workspace, size_t workspace_bytes,
                   rgcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DistMult decoder of the link-prediction models.
+ * triples: (B, 3) int64 rows (s, p, o); nodes (N, dim) fp32; relations (R, dim) fp32.
+ * status (1 x int32, device, may be NULL) is incremented once per triple with an index out of range; such
+ * triples score 0 and contribute nothing (the reference raises an IndexError / device assert).
+ * ---------------------------------------------------------------------------------------- */
+/* layers.py:86-98  DistMult.forward: scores[b] = sum_d nodes[s,d] relations[p,d] nodes[o,d] (+ the three biases,
+ * all NULL or all given) */
+int rgcn_distmult_forward(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
+                          const float* relations, int64_t num_rels, int64_t dim, const float* sbias,
+                          const float* pbias, const float* obias, float* scores, int32_t* status,
+                          rgcn_stream_t stream);
+/* gradients of the above (autograd upstream); NULL = not wanted, buffers are overwritten */
+int rgcn_distmult_backward(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
+                           const float* relations, int64_t num_rels, int64_t dim, const float* grad_scores,
+                           float* g_nodes, float* g_relations, float* g_sbias, float* g_pbias, float* g_obias,
+                           rgcn_stream_t stream);
+/* layers.py:77-84  DistMult.s_penalty: out[0] = mean(nodes[s]^2) + mean(relations[p]^2) + mean(nodes[o]^2) */
+size_t rgcn_distmult_penalty_workspace_bytes(void);
+int rgcn_distmult_penalty(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
+                          const float* relations, int64_t num_rels, int64_t dim, float* out, int32_t* status,
+                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+/* grad: device scalar (d loss / d penalty) */
+int rgcn_distmult_penalty_backward(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
+                                   const float* relations, int64_t num_rels, int64_t dim, const float* grad,
+                                   float* g_nodes, float* g_relations, rgcn_stream_t stream);
+/* utils/misc.py:174-189  negative_sampling's masked assignment: batch (count, 3) int64 in place,
+ * batch[i, head_mask[i] ? 0 : 2] = corruptions[i] */
+int rgcn_corrupt_triples(int64_t* batch, const uint8_t* head_mask, const int64_t* corruptions, int64_t count,
+                         rgcn_stream_t stream);
+
 /* number of kernels the engine has launched on this process since load (bench.py's gpu_launches) */
 int64_t rgcn_launch_count(void);
 

@@ -19,7 +19,7 @@ import torch
 
 REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
 sys.path.insert(0, REF)
-from torch_rgcn.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP  # noqa: E402
+from torch_rgcn.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP, DistMult  # noqa: E402
 from torch_rgcn.utils import add_inverse_and_self  # noqa: E402
 from torch_rgcn.models import NodeClassifier, EmbeddingNodeClassifier  # noqa: E402
 
@@ -151,7 +151,67 @@ def make_model(name, seed, cls, N, R, E, nclass, **kw):
     save(name, meta, arrays)
 
 
+def make_distmult(name, seed, N, R, d, B, b_init=None, three_d=False):
+    """Reference DistMult (layers.py:9-98): scores, s_penalty and the autograd gradients of both."""
+    gen = torch.Generator().manual_seed(seed)
+    shape = (B // 4, 4) if three_d else (B,)
+    triples = torch.stack([torch.randint(0, N, shape, generator=gen), torch.randint(0, R, shape, generator=gen),
+                           torch.randint(0, N, shape, generator=gen)], dim=-1)
+    flat = triples.view(-1, 3)
+    flat[-B // 4:, 0] = flat[:B // 4, 0]                   # repeated subjects / relations: gradients accumulate
+    flat[-B // 8:, 1] = flat[:B // 8, 1]
+    torch.manual_seed(seed + 2)
+    dec = DistMult(R, d, N, R, w_init='standard-normal', b_init=b_init)
+    nodes = torch.randn(N, d, generator=gen, requires_grad=True)
+    scores = dec(triples, nodes)
+    G = torch.randn(scores.shape, generator=gen)
+    scores.backward(G)
+    arrays = {'triples': triples.numpy(), 'nodes': nodes.detach().numpy(), 'G': G.numpy(), 'out': scores.detach().numpy(),
+              'grad_nodes': nodes.grad.numpy().copy()}
+    for n, p in dec.named_parameters():
+        arrays['param_' + n] = p.detach().numpy().copy()
+        arrays['grad_' + n] = p.grad.numpy().copy()
+    nodes.grad = None
+    dec.zero_grad()
+    pen = dec.s_penalty(triples, nodes)
+    (pen * 3.0).backward()
+    arrays['penalty'] = pen.detach().numpy()
+    arrays['pgrad_nodes'] = nodes.grad.numpy().copy()
+    arrays['pgrad_relations'] = dec.relations.grad.numpy().copy()
+    save(name, dict(kind='distmult', seed=seed, N=N, R=R, d=d, B=B, b_init=b_init, penalty_grad=3.0), arrays)
+
+
+def make_negsample(name, seed, N, bs, ns, head_prob):
+    """Reference negative_sampling (utils/misc.py:174-189).  utils/misc.py imports sacred at module level (absent
+    here), so the import runs with a stub module in its place; the function itself is executed unmodified.  The two
+    random draws are re-drawn from the same seed to record the corruptions and the head mask it used."""
+    import types
+    for m in ('sacred', 'sacred.observers'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['sacred'].Experiment = object
+    sys.modules['sacred.observers'].MongoObserver = object
+    from utils.misc import negative_sampling
+    gen = torch.Generator().manual_seed(seed)
+    pos = torch.stack([torch.randint(0, N, (bs,), generator=gen), torch.randint(0, 5, (bs,), generator=gen),
+                       torch.randint(0, N, (bs,), generator=gen)], dim=1)
+    batch = pos.clone()[:, None, :].expand(bs, ns, 3).contiguous()       # experiments/predict_links.py:132
+    before = batch.numpy().copy()
+    torch.manual_seed(seed + 1)
+    out = negative_sampling(batch, N, head_prob)
+    torch.manual_seed(seed + 1)
+    corruptions = torch.randint(size=(bs * ns,), low=0, high=N, dtype=torch.long)
+    head = torch.bernoulli(torch.empty(size=(bs, ns, 1), dtype=torch.float).fill_(head_prob)).to(torch.bool)
+    save(name, dict(kind='negsample', seed=seed, N=N, bs=bs, ns=ns, head_prob=head_prob),
+         {'batch': before, 'corruptions': corruptions.numpy(), 'head': head.numpy().reshape(-1), 'out': out.numpy()})
+
+
 def main():
+    make_distmult('distmult_plain', 31, 40, 5, 16, 64)
+    make_distmult('distmult_bias', 32, 40, 5, 16, 64, b_init='normal')
+    make_distmult('distmult_3d_odd', 33, 30, 4, 10, 48, b_init='uniform', three_d=True)
+    make_distmult('distmult_wide', 34, 50, 6, 128, 96)
+    make_negsample('negsample_half', 41, 50, 12, 10, 0.5)
+    make_negsample('negsample_heads', 42, 50, 7, 3, 1.0)
     N, R, E = 24, 3, 70
     basis = {'type': 'basis', 'num_bases': 3}
     block = {'type': 'block', 'num_blocks': 2}

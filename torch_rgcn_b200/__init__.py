@@ -9,5 +9,7 @@ from . import _lib                                   # noqa: F401  (fails loudly
 from .graph import GraphPlan                         # noqa: F401
 from .functional import rgcn_propagate               # noqa: F401
 from .layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP   # noqa: F401
+from .decoder import DistMult, negative_sampling      # noqa: F401
 
-__all__ = ['GraphPlan', 'rgcn_propagate', 'RelationalGraphConvolutionNC', 'RelationalGraphConvolutionLP']
+__all__ = ['GraphPlan', 'rgcn_propagate', 'RelationalGraphConvolutionNC', 'RelationalGraphConvolutionLP', 'DistMult',
+           'negative_sampling']

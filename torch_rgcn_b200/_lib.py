@@ -94,6 +94,12 @@ def _load():
         'rgcn_backward': (C.c_int, [C.POINTER(Graph), C.POINTER(Params), _p, C.c_int, _p, C.POINTER(Grads), _p,
                                     C.c_size_t, _p]),
         'rgcn_shard_plan': (C.c_int, [_p, _i64, C.c_int32, _p]),
+        'rgcn_distmult_forward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+        'rgcn_distmult_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+        'rgcn_distmult_penalty_workspace_bytes': (C.c_size_t, []),
+        'rgcn_distmult_penalty': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_distmult_penalty_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
+        'rgcn_corrupt_triples': (C.c_int, [_p, _p, _p, _i64, _p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -106,7 +112,9 @@ lib = _load()
 EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add_inverse_and_self',
            'rgcn_generate_inverses', 'rgcn_lp_triples_plus', 'rgcn_stack_matrices', 'rgcn_sum_sparse',
            'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_fused_items_bound', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
-           'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan']
+           'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan',
+           'rgcn_distmult_forward', 'rgcn_distmult_backward', 'rgcn_distmult_penalty_workspace_bytes',
+           'rgcn_distmult_penalty', 'rgcn_distmult_penalty_backward', 'rgcn_corrupt_triples']
 
 
 class RgcnError(RuntimeError):

@@ -17,6 +17,7 @@ from . import _lib
 from .functional import rgcn_propagate
 from .graph import GraphPlan
 from .utils import select_b_init, select_w_init, schlichtkrull_normal_
+from .decoder import DistMult                      # noqa: F401  (reference layers.py:9 defines it in this module)
 
 # RGCN_FUSED default: '1' routes bf16 64 -> 64 block layers to the fused row-block kernel (propagate_fused.cuh),
 # '0' keeps the two-phase tensor-core kernels (propagate_mma.cuh)
