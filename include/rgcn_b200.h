@@ -283,13 +283,14 @@ int rgcn_distmult_backward(const int64_t* triples, int64_t num_triples, const fl
                            const float* relations, int64_t num_rels, int64_t dim, const float* grad_scores,
                            float* g_nodes, float* g_relations, float* g_sbias, float* g_pbias, float* g_obias,
                            rgcn_stream_t stream);
-/* layers.py:77-84  DistMult.s_penalty: out[0] = mean(nodes[s]^2) + mean(relations[p]^2) + mean(nodes[o]^2) */
-size_t rgcn_distmult_penalty_workspace_bytes(void);
+/* layers.py:77-84  DistMult.s_penalty: out[0] = mean(nodes[s]^2) + mean(relations[p]^2) + mean(nodes[o]^2),
+ * computed from occurrence counts of the nodes / relations in the batch (kept in the workspace for the backward) */
+size_t rgcn_distmult_penalty_workspace_bytes(int64_t num_nodes, int64_t num_rels);
 int rgcn_distmult_penalty(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
                           const float* relations, int64_t num_rels, int64_t dim, float* out, int32_t* status,
                           void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
-/* grad: device scalar (d loss / d penalty) */
-int rgcn_distmult_penalty_backward(const int64_t* triples, int64_t num_triples, const float* nodes, int64_t num_nodes,
+/* workspace: as left by rgcn_distmult_penalty for the same batch; grad: device scalar (d loss / d penalty) */
+int rgcn_distmult_penalty_backward(const void* workspace, int64_t num_triples, const float* nodes, int64_t num_nodes,
                                    const float* relations, int64_t num_rels, int64_t dim, const float* grad,
                                    float* g_nodes, float* g_relations, rgcn_stream_t stream);
 /* utils/misc.py:174-189  negative_sampling's masked assignment: batch (count, 3) int64 in place,

@@ -96,7 +96,7 @@ def _load():
         'rgcn_shard_plan': (C.c_int, [_p, _i64, C.c_int32, _p]),
         'rgcn_distmult_forward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
         'rgcn_distmult_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
-        'rgcn_distmult_penalty_workspace_bytes': (C.c_size_t, []),
+        'rgcn_distmult_penalty_workspace_bytes': (C.c_size_t, [_i64, _i64]),
         'rgcn_distmult_penalty': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, C.c_size_t, _p]),
         'rgcn_distmult_penalty_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
         'rgcn_corrupt_triples': (C.c_int, [_p, _p, _p, _i64, _p]),

@@ -12,6 +12,7 @@
 // One warp per triple, lanes stride over the embedding in 16-byte pieces; the three gathered rows come from a
 // node table that is L2-resident at the reference's sizes (WN18: 40,943 x 128 fp32 = 21 MB), so these kernels are
 // bound by L2 bandwidth / atomic throughput, not HBM.
+#include <algorithm>
 #include "common.cuh"
 
 using namespace rgcn;
@@ -39,6 +40,8 @@ __device__ __forceinline__ bool load_triple(const int64_t* __restrict__ t, long 
     return ok;
 }
 
+// Warp per triple.  U triples per warp iteration were measured on the WN18-shaped batch: U = 1 0.353 ms, U = 4
+// 0.397 ms (the extra registers cost more occupancy than the extra loads in flight buy), so U stays 1.
 template <bool VEC>
 __global__ void __launch_bounds__(kWarps * 32) k_distmult_fwd(const int64_t* __restrict__ t, long long B,
                                                               const float* __restrict__ nodes, long long N,
@@ -47,32 +50,53 @@ __global__ void __launch_bounds__(kWarps * 32) k_distmult_fwd(const int64_t* __r
                                                               const float* __restrict__ pbias,
                                                               const float* __restrict__ obias,
                                                               float* __restrict__ scores, int32_t* status) {
+    constexpr int U = 1;
     const int lane = threadIdx.x & 31;
     const long long nwarp = (long long)gridDim.x * kWarps;
-    for (long long b = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); b < B; b += nwarp) {
-        long long s, p, o;
-        if (!load_triple(t, b, N, R, lane, status, s, p, o)) {
-            if (lane == 0) scores[b] = 0.f;
-            continue;
+    for (long long b0 = ((long long)blockIdx.x * kWarps + (threadIdx.x >> 5)) * U; b0 < B; b0 += nwarp * U) {
+        long long s[U], p[U], o[U];
+        bool ok[U];
+        float acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc[u] = 0.f;
+            ok[u] = b0 + u < B && load_triple(t, b0 + u, N, R, lane, status, s[u], p[u], o[u]);
         }
-        const float* xs = nodes + (size_t)s * dim;
-        const float* xp = rel + (size_t)p * dim;
-        const float* xo = nodes + (size_t)o * dim;
-        float acc = 0.f;
         if constexpr (VEC) {
             for (int j = lane; j < dim / 4; j += 32) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(xs) + j);
-                const float4 r = __ldg(reinterpret_cast<const float4*>(xp) + j);
-                const float4 c = __ldg(reinterpret_cast<const float4*>(xo) + j);
-                acc += a.x * r.x * c.x + a.y * r.y * c.y + a.z * r.z * c.z + a.w * r.w * c.w;
+                float4 a[U], r[U], c[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u]) {
+                        a[u] = __ldg(reinterpret_cast<const float4*>(nodes + (size_t)s[u] * dim) + j);
+                        r[u] = __ldg(reinterpret_cast<const float4*>(rel + (size_t)p[u] * dim) + j);
+                        c[u] = __ldg(reinterpret_cast<const float4*>(nodes + (size_t)o[u] * dim) + j);
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u])
+                        acc[u] += a[u].x * r[u].x * c[u].x + a[u].y * r[u].y * c[u].y + a[u].z * r[u].z * c[u].z +
+                                  a[u].w * r[u].w * c[u].w;
             }
         } else {
-            for (int j = lane; j < dim; j += 32) acc += __ldg(xs + j) * __ldg(xp + j) * __ldg(xo + j);
+            for (int j = lane; j < dim; j += 32)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u])
+                        acc[u] += __ldg(nodes + (size_t)s[u] * dim + j) * __ldg(rel + (size_t)p[u] * dim + j) *
+                                  __ldg(nodes + (size_t)o[u] * dim + j);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            if (sbias) acc += __ldg(sbias + s) + __ldg(pbias + p) + __ldg(obias + o);   // layers.py:95-96
-            scores[b] = acc;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float v = warp_sum(acc[u]);
+            if (lane == 0 && b0 + u < B) {
+                float out = 0.f;
+                if (ok[u]) {
+                    out = v;
+                    if (sbias) out += __ldg(sbias + s[u]) + __ldg(pbias + p[u]) + __ldg(obias + o[u]);   // layers.py:95-96
+                }
+                scores[b0 + u] = out;
+            }
         }
     }
 }
@@ -157,69 +181,76 @@ __global__ void __launch_bounds__(kWarps * 32) k_distmult_bwd(const int64_t* __r
     flush();
 }
 
-// sums[0..2] += sum over this CTA's triples of |nodes[s]|^2, |relations[p]|^2, |nodes[o]|^2 (double accumulators)
-__global__ void __launch_bounds__(kWarps * 32) k_distmult_penalty(const int64_t* __restrict__ t, long long B,
-                                                                  const float* __restrict__ nodes, long long N,
-                                                                  const float* __restrict__ rel, long long R, int dim,
-                                                                  double* __restrict__ sums, int32_t* status) {
-    __shared__ double part[kWarps][3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nwarp = (long long)gridDim.x * kWarps;
-    float as = 0.f, ap = 0.f, ao = 0.f;
-    double ds = 0.0, dp = 0.0, dob = 0.0;
-    int since = 0;
-    for (long long b = (long long)blockIdx.x * kWarps + warp; b < B; b += nwarp) {
-        long long s, p, o;
-        if (!load_triple(t, b, N, R, lane, status, s, p, o)) continue;
-        for (int j = lane; j < dim; j += 32) {
-            const float a = __ldg(nodes + (size_t)s * dim + j), r = __ldg(rel + (size_t)p * dim + j),
-                        c = __ldg(nodes + (size_t)o * dim + j);
-            as += a * a; ap += r * r; ao += c * c;
+// Penalty through occurrence counts: sum_b |nodes[s_b]|^2 + |nodes[o_b]|^2 = sum_v cnt_n[v] |nodes[v]|^2 (likewise
+// for relations), so the 3 B gathered rows of the reference collapse into one histogram over the triples and one
+// pass over the (small) embedding tables.  The counts stay in the workspace for the backward.
+__global__ void __launch_bounds__(256) k_distmult_count(const int64_t* __restrict__ t, long long B, long long N,
+                                                        long long R, int32_t* __restrict__ cnt_n,
+                                                        int32_t* __restrict__ cnt_r, int32_t* status) {
+    extern __shared__ int32_t s_rel[];                   // relation histogram of this CTA (few, hot addresses)
+    const bool smem_hist = R <= 8192;
+    if (smem_hist) {
+        for (int i = threadIdx.x; i < (int)R; i += blockDim.x) s_rel[i] = 0;
+        __syncthreads();
+    }
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const long long s = t[3 * b], p = t[3 * b + 1], o = t[3 * b + 2];
+        if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= R) {
+            if (status) atomicAdd(status, 1);
+            continue;
         }
-        if (++since == 64) { ds += as; dp += ap; dob += ao; as = ap = ao = 0.f; since = 0; }   // bound the fp32 run length
+        atomicAdd(cnt_n + s, 1);
+        atomicAdd(cnt_n + o, 1);
+        if (smem_hist) atomicAdd(s_rel + p, 1); else atomicAdd(cnt_r + p, 1);
     }
-    ds += as; dp += ap; dob += ao;
+    if (smem_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)R; i += blockDim.x)
+            if (s_rel[i]) atomicAdd(cnt_r + i, s_rel[i]);
+    }
+}
+
+// sums[which] += sum_v cnt[v] |table[v]|^2 : warp per row, double accumulation across rows
+__global__ void __launch_bounds__(kWarps * 32) k_distmult_weighted_sq(const float* __restrict__ table, long long rows, int dim,
+                                                                      const int32_t* __restrict__ cnt,
+                                                                      double* __restrict__ sum) {
+    __shared__ double part[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (long long v = (long long)blockIdx.x * kWarps + warp; v < rows; v += (long long)gridDim.x * kWarps) {
+        const int32_t c = __ldg(cnt + v);
+        if (!c) continue;
+        float a = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float x = __ldg(table + (size_t)v * dim + j);
+            a += x * x;
+        }
+        acc += (double)a * (double)c;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ds += __shfl_xor_sync(0xffffffffu, ds, o);
-        dp += __shfl_xor_sync(0xffffffffu, dp, o);
-        dob += __shfl_xor_sync(0xffffffffu, dob, o);
-    }
-    if (lane == 0) { part[warp][0] = ds; part[warp][1] = dp; part[warp][2] = dob; }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) part[warp] = acc;
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x == 0) {
         double v = 0.0;
-        for (int k = 0; k < kWarps; ++k) v += part[k][threadIdx.x];
-        atomicAdd(sums + threadIdx.x, v);
+        for (int k = 0; k < kWarps; ++k) v += part[k];
+        if (v != 0.0) atomicAdd(sum, v);
     }
 }
 
 __global__ void k_distmult_penalty_finish(const double* __restrict__ sums, long long B, int dim, float* __restrict__ out) {
     if (blockIdx.x || threadIdx.x) return;
     const double n = (double)B * (double)dim;
-    out[0] = (float)(sums[0] / n) + (float)(sums[1] / n) + (float)(sums[2] / n);
+    out[0] = (float)(sums[0] / n) + (float)(sums[1] / n);     // nodes (subjects + objects), relations
 }
 
-// d penalty / d nodes[s_b] = 2 nodes[s_b] / (B dim) per occurrence, likewise for o and for relations[p]
-__global__ void __launch_bounds__(kWarps * 32) k_distmult_penalty_bwd(const int64_t* __restrict__ t, long long B,
-                                                                      const float* __restrict__ nodes, long long N,
-                                                                      const float* __restrict__ rel, long long R, int dim,
-                                                                      const float* __restrict__ grad,
-                                                                      float* __restrict__ g_nodes, float* __restrict__ g_rel) {
-    const int lane = threadIdx.x & 31;
-    const long long nwarp = (long long)gridDim.x * kWarps;
+// g[v, :] = 2 grad cnt[v] table[v, :] / (B dim)
+__global__ void k_distmult_penalty_bwd(const float* __restrict__ table, long long rows, int dim, const int32_t* __restrict__ cnt,
+                                       const float* __restrict__ grad, long long B, float* __restrict__ g) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= rows * dim) return;
     const float scale = 2.f * __ldg(grad) / ((float)B * (float)dim);
-    for (long long b = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); b < B; b += nwarp) {
-        long long s, p, o;
-        if (!load_triple(t, b, N, R, lane, nullptr, s, p, o)) continue;
-        for (int j = lane; j < dim; j += 32) {
-            if (g_nodes) {
-                atomicAdd(g_nodes + (size_t)s * dim + j, scale * __ldg(nodes + (size_t)s * dim + j));
-                atomicAdd(g_nodes + (size_t)o * dim + j, scale * __ldg(nodes + (size_t)o * dim + j));
-            }
-            if (g_rel) atomicAdd(g_rel + (size_t)p * dim + j, scale * __ldg(rel + (size_t)p * dim + j));
-        }
-    }
+    g[i] = scale * (float)__ldg(cnt + i / dim) * __ldg(table + i);
 }
 
 // batch[i, head[i] ? 0 : 2] = corruptions[i]  (the masked assignment of utils/misc.py:181-187, row-major order)
@@ -307,36 +338,56 @@ extern "C" int rgcn_distmult_backward(const int64_t* triples, int64_t B, const f
     return RGCN_OK;
 }
 
-extern "C" size_t rgcn_distmult_penalty_workspace_bytes(void) { return align_up(3 * sizeof(double)); }
+extern "C" size_t rgcn_distmult_penalty_workspace_bytes(int64_t N, int64_t R) {
+    return align_up(2 * sizeof(double)) + align_up((size_t)(N > 0 ? N : 0) * sizeof(int32_t)) +
+           align_up((size_t)(R > 0 ? R : 0) * sizeof(int32_t));
+}
+
+namespace {
+struct PenaltyWs { double* sums; int32_t* cnt_n; int32_t* cnt_r; };
+PenaltyWs carve_penalty(void* ws, int64_t N, int64_t R) {
+    Carver c(ws);
+    PenaltyWs w;
+    w.sums = c.take<double>(2); w.cnt_n = c.take<int32_t>((size_t)N); w.cnt_r = c.take<int32_t>((size_t)R);
+    return w;
+}
+}  // namespace
 
 extern "C" int rgcn_distmult_penalty(const int64_t* triples, int64_t B, const float* nodes, int64_t N,
                                      const float* relations, int64_t R, int64_t dim, float* out, int32_t* status,
                                      void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
     int rc = check_args("rgcn_distmult_penalty", triples, B, nodes, N, relations, R, dim);
     if (rc) return rc;
-    RGCN_REQUIRE(out && workspace && workspace_bytes >= rgcn_distmult_penalty_workspace_bytes(), RGCN_ERR_WORKSPACE,
-                 "rgcn_distmult_penalty: out / workspace missing");
+    const size_t need = rgcn_distmult_penalty_workspace_bytes(N, R);
+    RGCN_REQUIRE(out && workspace && workspace_bytes >= need, RGCN_ERR_WORKSPACE,
+                 "rgcn_distmult_penalty: out / workspace missing (%zu < %zu bytes)", workspace_bytes, need);
     RGCN_REQUIRE(B > 0, RGCN_ERR_ARG, "rgcn_distmult_penalty: the mean over an empty batch is undefined");
     const cudaStream_t st = (cudaStream_t)stream;
-    double* sums = static_cast<double*>(workspace);
-    RGCN_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
-    RGCN_LAUNCH(k_distmult_penalty, grid_warps(B, 8), kWarps * 32, 0, st, triples, (long long)B, nodes, (long long)N,
-                relations, (long long)R, (int)dim, sums, status);
-    RGCN_LAUNCH(k_distmult_penalty_finish, 1, 32, 0, st, sums, (long long)B, (int)dim, out);
+    PenaltyWs w = carve_penalty(workspace, N, R);
+    RGCN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    const int cgrid = (int)std::min<int64_t>((B + 255) / 256, (int64_t)kNumSMs * 8);
+    RGCN_LAUNCH(k_distmult_count, cgrid, 256, R <= 8192 ? (size_t)R * sizeof(int32_t) : 0, st, triples, (long long)B,
+                (long long)N, (long long)R, w.cnt_n, w.cnt_r, status);
+    RGCN_LAUNCH(k_distmult_weighted_sq, grid_warps(N, 8), kWarps * 32, 0, st, nodes, (long long)N, (int)dim, w.cnt_n, w.sums);
+    RGCN_LAUNCH(k_distmult_weighted_sq, grid_warps(R, 8), kWarps * 32, 0, st, relations, (long long)R, (int)dim, w.cnt_r,
+                w.sums + 1);
+    RGCN_LAUNCH(k_distmult_penalty_finish, 1, 32, 0, st, w.sums, (long long)B, (int)dim, out);
     return RGCN_OK;
 }
 
-extern "C" int rgcn_distmult_penalty_backward(const int64_t* triples, int64_t B, const float* nodes, int64_t N,
+extern "C" int rgcn_distmult_penalty_backward(const void* workspace, int64_t B, const float* nodes, int64_t N,
                                               const float* relations, int64_t R, int64_t dim, const float* grad,
                                               float* g_nodes, float* g_relations, rgcn_stream_t stream) {
-    int rc = check_args("rgcn_distmult_penalty_backward", triples, B, nodes, N, relations, R, dim);
-    if (rc) return rc;
-    RGCN_REQUIRE(grad && B > 0, RGCN_ERR_ARG, "rgcn_distmult_penalty_backward: grad is NULL or the batch is empty");
+    RGCN_REQUIRE(workspace && nodes && relations && grad && B > 0 && N > 0 && R > 0 && dim > 0, RGCN_ERR_ARG,
+                 "rgcn_distmult_penalty_backward: bad arguments");
     const cudaStream_t st = (cudaStream_t)stream;
-    if (g_nodes) RGCN_CHECK_CUDA(cudaMemsetAsync(g_nodes, 0, (size_t)N * dim * sizeof(float), st));
-    if (g_relations) RGCN_CHECK_CUDA(cudaMemsetAsync(g_relations, 0, (size_t)R * dim * sizeof(float), st));
-    RGCN_LAUNCH(k_distmult_penalty_bwd, grid_warps(B, 8), kWarps * 32, 0, st, triples, (long long)B, nodes, (long long)N,
-                relations, (long long)R, (int)dim, grad, g_nodes, g_relations);
+    PenaltyWs w = carve_penalty(const_cast<void*>(workspace), N, R);
+    if (g_nodes)
+        RGCN_LAUNCH(k_distmult_penalty_bwd, grid_for(N * dim, 256), 256, 0, st, nodes, (long long)N, (int)dim, w.cnt_n, grad,
+                    (long long)B, g_nodes);
+    if (g_relations)
+        RGCN_LAUNCH(k_distmult_penalty_bwd, grid_for(R * dim, 256), 256, 0, st, relations, (long long)R, (int)dim, w.cnt_r,
+                    grad, (long long)B, g_relations);
     return RGCN_OK;
 }
 

@@ -88,7 +88,7 @@ class _Penalty(torch.autograd.Function):
         dev = nodes.device
         out = torch.empty(1, dtype=torch.float32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if validate else None
-        ws_bytes = _lib.lib.rgcn_distmult_penalty_workspace_bytes()
+        ws_bytes = _lib.lib.rgcn_distmult_penalty_workspace_bytes(nodes.size(0), relations.size(0))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.rgcn_distmult_penalty(_lib.ptr(t), t.size(0), _lib.ptr(nodes), nodes.size(0),
@@ -96,18 +96,19 @@ class _Penalty(torch.autograd.Function):
                                                       _lib.ptr(status), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
         if validate:
             _check_status(status, 'penalised', nodes.size(0), relations.size(0))
-        ctx.save_for_backward(t, nodes, relations)
+        ctx.save_for_backward(ws, nodes, relations)      # ws holds the occurrence counts of the batch
+        ctx.num_triples = t.size(0)
         return out.reshape(())
 
     @staticmethod
     def backward(ctx, grad):
-        t, nodes, relations = ctx.saved_tensors
+        ws, nodes, relations = ctx.saved_tensors
         need = ctx.needs_input_grad
         grad = _f32c(grad).reshape(1)
         g_nodes = torch.empty_like(nodes) if need[1] else None
         g_rel = torch.empty_like(relations) if need[2] else None
         with torch.cuda.device(nodes.device):
-            _lib.check(_lib.lib.rgcn_distmult_penalty_backward(_lib.ptr(t), t.size(0), _lib.ptr(nodes), nodes.size(0),
+            _lib.check(_lib.lib.rgcn_distmult_penalty_backward(_lib.ptr(ws), ctx.num_triples, _lib.ptr(nodes), nodes.size(0),
                                                                _lib.ptr(relations), relations.size(0), nodes.size(1),
                                                                _lib.ptr(grad), _lib.ptr(g_nodes), _lib.ptr(g_rel),
                                                                _lib.stream_ptr()))
