@@ -298,6 +298,26 @@ int rgcn_distmult_penalty_backward(const void* workspace, int64_t num_triples, c
 int rgcn_corrupt_triples(int64_t* batch, const uint8_t* head_mask, const int64_t* corruptions, int64_t count,
                          rgcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Filtered ranking evaluation: utils/misc.py:29-110 (generate_true_dict, filter_scores,
+ * evaluate) with DistMult scores, on node embeddings the caller computed once.
+ * ---------------------------------------------------------------------------------------- */
+/* Sorted lists of the known true completions, replacing the Python dictionaries of generate_true_dict:
+ * head != 0: keys[e] = p * N + o, vals[e] = s (true heads of (p, o));  head == 0: keys = p * N + s, vals = o.
+ * Entries are sorted by (key, value); all_triples (M, 3) int64; keys / vals have M entries. */
+size_t rgcn_rank_filter_workspace_bytes(int64_t num_true);
+int rgcn_rank_build_filter(const int64_t* all_triples, int64_t num_true, int64_t num_nodes, int64_t num_rels, int head,
+                           uint64_t* keys, int32_t* vals, int32_t* status, void* workspace, size_t workspace_bytes,
+                           rgcn_stream_t stream);
+/* ranks[i] = #{candidates scoring above the target} + (#{ties, target included} - 1) / 2 + 1 over all num_nodes
+ * head (head != 0) or tail completions of queries[i], other known true completions removed when filter lists are
+ * given (num_true > 0).  Scores are DistMult scores (biases all NULL or all given). */
+size_t rgcn_rank_workspace_bytes(int64_t num_queries, int64_t dim);
+int rgcn_rank_triples(const int64_t* queries, int64_t num_queries, int head, const float* nodes, int64_t num_nodes,
+                      const float* relations, int64_t num_rels, int64_t dim, const float* sbias, const float* pbias,
+                      const float* obias, const uint64_t* filter_keys, const int32_t* filter_vals, int64_t num_true,
+                      int64_t* ranks, int32_t* status, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
 /* number of kernels the engine has launched on this process since load (bench.py's gpu_launches) */
 int64_t rgcn_launch_count(void);
 

@@ -21,7 +21,7 @@ REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
 sys.path.insert(0, REF)
 from torch_rgcn.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP, DistMult  # noqa: E402
 from torch_rgcn.utils import add_inverse_and_self  # noqa: E402
-from torch_rgcn.models import NodeClassifier, EmbeddingNodeClassifier  # noqa: E402
+from torch_rgcn.models import NodeClassifier, EmbeddingNodeClassifier, CompressionRelationPredictor  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -205,7 +205,83 @@ def make_negsample(name, seed, N, bs, ns, head_prob):
          {'batch': before, 'corruptions': corruptions.numpy(), 'head': head.numpy().reshape(-1), 'out': out.numpy()})
 
 
+def make_crp(name, seed, N, R, E, nemb, B):
+    """Reference CompressionRelationPredictor (models.py:208-245) where it runs as shipped: node_embedding ==
+    hidden1_size (the encoder layer is built for the embedding width, models.py:224) and a glorot initialiser.  eval()
+    mode: no self-loop dropout draws."""
+    gen = torch.Generator().manual_seed(seed)
+    graph = rand_triples(gen, N, R, E)
+    batch = torch.stack([torch.randint(0, N, (B,), generator=gen), torch.randint(0, R, (B,), generator=gen),
+                         torch.randint(0, N, (B,), generator=gen)], 1)
+    enc = {'node_embedding': nemb, 'hidden1_size': nemb, 'num_layers': 1, 'weight_init': 'glorot-normal',
+           'bias_init': 'zeros', 'edge_dropout': {'general': 0.5, 'self_loop': 0.2, 'self_loop_type': 'schlichtkrull-dropout'}}
+    dec = {'l2_penalty_type': 'schlichtkrull-l2', 'l2_penalty': 0.01, 'weight_init': 'standard-normal'}
+    torch.manual_seed(seed + 2)
+    model = CompressionRelationPredictor(nnodes=N, nrel=R, encoder_config=enc, decoder_config=dec).eval()
+    scores, penalty = model(graph, batch)
+    G = torch.randn(scores.shape, generator=gen)
+    ((scores * G).sum() + 0.5 * penalty).backward()
+    arrays = {'graph': graph.numpy(), 'batch': batch.numpy(), 'G': G.numpy(), 'out': scores.detach().numpy(),
+              'penalty': penalty.detach().numpy()}
+    for n, p in model.named_parameters():
+        arrays['param_' + n] = p.detach().numpy().copy()
+        arrays['grad_' + n] = p.grad.numpy().copy()
+    save(name, dict(kind='crp', seed=seed, N=N, R=R, nemb=nemb, encoder=enc, decoder=dec, penalty_weight=0.5), arrays)
+
+
+def make_ranking(name, seed, N, R, d, n_known, n_test, integer=False, bias=False, batch_size=7):
+    """Reference evaluate (utils/misc.py:60-110, with filter_scores :39-58 and generate_true_dict :29-37) on fixed node
+    embeddings.  `integer` draws small-integer embeddings: every score is then exact in fp32 whatever the summation
+    order, ties are frequent, and the ranks must match an implementation exactly."""
+    import types
+    for m in ('sacred', 'sacred.observers'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['sacred'].Experiment = object
+    sys.modules['sacred.observers'].MongoObserver = object
+    from utils.misc import evaluate, generate_true_dict
+    gen = torch.Generator().manual_seed(seed)
+    known = torch.stack([torch.randint(0, N, (n_known,), generator=gen), torch.randint(0, R, (n_known,), generator=gen),
+                         torch.randint(0, N, (n_known,), generator=gen)], 1)
+    known[: n_known // 3, 1] = known[0, 1]                   # many completions of a few (p, o) / (s, p) pairs
+    known[: n_known // 3, 2] = known[0, 2]
+    known[n_known // 3: 2 * n_known // 3, 0] = known[1, 0]
+    known[n_known // 3: 2 * n_known // 3, 1] = known[1, 1]
+    known = torch.cat([known, known[:5]], 0)                # repeated known triples
+    test = known[torch.randperm(known.size(0), generator=gen)[:n_test]]
+    torch.manual_seed(seed + 2)
+    dec = DistMult(R, d, N, R, b_init='normal' if bias else None)
+    if integer:
+        x = torch.randint(-2, 3, (N, d), generator=gen).float()
+        with torch.no_grad():
+            dec.relations.copy_(torch.randint(-2, 3, (R, d), generator=gen).float())
+            if bias:
+                for b in (dec.sbias, dec.pbias, dec.obias):
+                    b.copy_(torch.randint(-3, 4, b.shape, generator=gen).float())
+    else:
+        x = torch.randn(N, d, generator=gen)
+    model = lambda graph, triples: (dec(triples, x), None)        # noqa: E731  what LinkPredictor.forward returns
+    true = generate_true_dict(known.tolist())
+    arrays = {'known': known.numpy(), 'test': test.numpy(), 'nodes': x.numpy()}
+    for n, p in dec.named_parameters():
+        arrays['param_' + n] = p.detach().numpy().copy()
+    for filt in (True, False):
+        with torch.no_grad():
+            mrr, hits, ranks = evaluate(model, None, test, true, N, batch_size=batch_size, filter_candidates=filt,
+                                        verbose=False)
+        tag = 'filtered' if filt else 'raw'
+        arrays['ranks_' + tag] = np.array(ranks)
+        arrays['mrr_' + tag] = np.array(mrr)
+        arrays['hits_' + tag] = np.array(hits)
+    save(name, dict(kind='ranking', seed=seed, N=N, R=R, d=d, integer=integer, b_init='normal' if bias else None), arrays)
+
+
 def main():
+    make_crp('lpmodel_crp', 61, 30, 3, 90, 16, 64)
+    make_ranking('ranking_integer', 51, 60, 4, 8, 150, 40, integer=True)
+    make_ranking('ranking_integer_bias', 52, 45, 3, 6, 120, 30, integer=True, bias=True)
+    # the reference's filter_scores raises when a batch has nothing to filter (utils/misc.py:56-58 indexes an empty 1-D
+    # tensor with [:, 0]); one batch over the whole test set avoids that here
+    make_ranking('ranking_float', 53, 80, 5, 16, 200, 50, batch_size=50)
     make_distmult('distmult_plain', 31, 40, 5, 16, 64)
     make_distmult('distmult_bias', 32, 40, 5, 16, 64, b_init='normal')
     make_distmult('distmult_3d_odd', 33, 30, 4, 10, 48, b_init='uniform', three_d=True)

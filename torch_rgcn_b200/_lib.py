@@ -100,6 +100,11 @@ def _load():
         'rgcn_distmult_penalty': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, C.c_size_t, _p]),
         'rgcn_distmult_penalty_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
         'rgcn_corrupt_triples': (C.c_int, [_p, _p, _p, _i64, _p]),
+        'rgcn_rank_filter_workspace_bytes': (C.c_size_t, [_i64]),
+        'rgcn_rank_build_filter': (C.c_int, [_p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_rank_workspace_bytes': (C.c_size_t, [_i64, _i64]),
+        'rgcn_rank_triples': (C.c_int, [_p, _i64, C.c_int, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p,
+                                        C.c_size_t, _p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -114,7 +119,8 @@ EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add
            'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_fused_items_bound', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
            'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan',
            'rgcn_distmult_forward', 'rgcn_distmult_backward', 'rgcn_distmult_penalty_workspace_bytes',
-           'rgcn_distmult_penalty', 'rgcn_distmult_penalty_backward', 'rgcn_corrupt_triples']
+           'rgcn_distmult_penalty', 'rgcn_distmult_penalty_backward', 'rgcn_corrupt_triples',
+           'rgcn_rank_filter_workspace_bytes', 'rgcn_rank_build_filter', 'rgcn_rank_workspace_bytes', 'rgcn_rank_triples']
 
 
 class RgcnError(RuntimeError):

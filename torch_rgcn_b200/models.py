@@ -2,15 +2,24 @@
 
 `NodeClassifier` and `EmbeddingNodeClassifier` keep the constructor arguments, buffers, sub-module and parameter
 names of reference torch_rgcn/models.py:137-200 and :248-296, so checkpoints and the experiment scripts' L2 penalties
-(`model.rgc1.weights` ...) carry over.  The link-prediction models of the reference are broken at this commit
- and are not mirrored; `RelationalGraphConvolutionLP` itself is in layers.py.
+(`model.rgc1.weights` ...) carry over.
+
+`LinkPredictor` and `CompressionRelationPredictor` mirror reference models.py:14-134 and :208-245 (same constructor
+dictionaries, sub-module / parameter names, `forward(graph, triples) -> (scores, penalty)`), with the three upstream
+defects of that commit repaired, because the shipped classes cannot run the shipped configs:
+  1. `schlichtkrull-normal` embeddings are initialised with the required `shape` argument (models.py:55-56 omits it);
+  2. `LinkPredictor.forward` returns instead of printing statistics and calling exit() (models.py:126-132);
+  3. the c-rgcn encoder layer takes the compressed width `hidden1_size` as its input width (models.py:224 passes the
+     embedding width, which only works when the two are equal — the case the parity fixture pins).
+Both add `encode(graph)` (the node embeddings the decoder scores), which evaluation.evaluate calls once.
 """
 import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .layers import RelationalGraphConvolutionNC
-from .utils import add_inverse_and_self
+from .decoder import DistMult
+from .layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP
+from .utils import add_inverse_and_self, select_w_init
 
 
 class NodeClassifier(nn.Module):
@@ -70,3 +79,83 @@ class EmbeddingNodeClassifier(NodeClassifier):
         x = self.rgcn_no_hidden(self.node_embeddings)
         x = F.relu(x)
         return self.rgc1(features=x)
+
+
+class LinkPredictor(nn.Module):
+    """Link prediction with an R-GCN encoder and a DistMult decoder (reference models.py:14-134, repaired)."""
+
+    def __init__(self, nnodes=None, nrel=None, nfeat=None, encoder_config=None, decoder_config=None):
+        super().__init__()
+        enc, dec = encoder_config, decoder_config
+        nemb = enc.get("node_embedding")
+        nhid1, nhid2 = enc.get("hidden1_size"), enc.get("hidden2_size")
+        rgcn_layers = enc.get("num_layers", 2)
+        edge_dropout, decomposition = enc.get("edge_dropout"), enc.get("decomposition")
+        encoder_w_init, encoder_gain = enc.get("weight_init"), enc.get("include_gain", False)
+        encoder_b_init = enc.get("bias_init")
+        assert (nnodes is not None or nrel is not None or nhid1 is not None), \
+            "The following must be specified: number of nodes, number of relations and output dimension!"
+        assert 0 < rgcn_layers < 3, "Only supports the following number of convolution layers: 1 and 2."
+        self.num_nodes, self.num_rels, self.rgcn_layers, self.nemb = nnodes, nrel, rgcn_layers, nemb
+        self.decoder_l2_type, self.decoder_l2 = dec.get("l2_penalty_type"), dec.get("l2_penalty")
+
+        self.node_embeddings = nn.Parameter(torch.FloatTensor(nnodes, nemb))
+        self.node_embeddings_bias = nn.Parameter(torch.zeros(1, nemb))
+        init = select_w_init(encoder_w_init)
+        if 'schlichtkrull-normal' == str(encoder_w_init).lower():
+            init(self.node_embeddings, shape=self.node_embeddings.shape)          # repair 1
+        else:
+            init(self.node_embeddings)
+        in1 = self._encoder_in_width(nemb, nhid1)
+        common = dict(num_nodes=nnodes, num_relations=nrel * 2 + 1, edge_dropout=edge_dropout, decomposition=decomposition,
+                      vertical_stacking=False, w_init=encoder_w_init, w_gain=encoder_gain, b_init=encoder_b_init)
+        self.rgc1 = RelationalGraphConvolutionLP(in_features=in1, out_features=nhid1, **common)
+        if rgcn_layers == 2:
+            self.rgc2 = RelationalGraphConvolutionLP(in_features=nhid1, out_features=nhid2, **common)
+        self.scoring_function = DistMult(nrel, nemb, nnodes, nrel, dec.get("weight_init"), dec.get("include_gain", False),
+                                         dec.get("bias_init"))
+
+    @staticmethod
+    def _encoder_in_width(nemb, nhid1):
+        return nemb
+
+    def compute_penalty(self, batch, x):
+        """reference models.py:94-103"""
+        if self.decoder_l2 == 0.0:
+            return 0
+        if self.decoder_l2_type == 'schlichtkrull-l2':
+            return self.scoring_function.s_penalty(batch, x)
+        return self.scoring_function.relations.pow(2).sum()
+
+    def encode(self, graph):
+        x = F.relu(self.node_embeddings + self.node_embeddings_bias)
+        x = self.rgc1(graph, features=x)
+        if self.rgcn_layers == 2:
+            x = self.rgc2(graph, features=F.relu(x))
+        return x
+
+    def forward(self, graph, triples):
+        x = self.encode(graph)
+        return self.scoring_function(triples, x), self.compute_penalty(triples, x)   # repair 2
+
+
+class CompressionRelationPredictor(LinkPredictor):
+    """c-rgcn: embeddings -> linear bottleneck -> R-GCN -> linear back + residual -> DistMult (reference models.py:208-245)."""
+
+    def __init__(self, nnodes=None, nrel=None, nfeat=None, encoder_config=None, decoder_config=None):
+        nhid, nemb = encoder_config.get("hidden1_size"), encoder_config.get("node_embedding")
+        super().__init__(nnodes, nrel, nhid, encoder_config, decoder_config)
+        self.encoding_layer = torch.nn.Linear(nemb, nhid)
+        self.decoding_layer = torch.nn.Linear(nhid, nemb)
+
+    @staticmethod
+    def _encoder_in_width(nemb, nhid1):
+        return nhid1                                                               # repair 3
+
+    def encode(self, graph):
+        x = F.relu(self.node_embeddings + self.node_embeddings_bias)
+        x = self.encoding_layer(x)
+        x = self.rgc1(graph, features=x)
+        if self.rgcn_layers == 2:
+            x = self.rgc2(graph, features=F.relu(x))
+        return self.node_embeddings + self.decoding_layer(x)
