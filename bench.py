@@ -59,6 +59,11 @@ WORKLOADS = {
     'wn18_ranking': dict(shape='wn18', kind='ranking', in_f=128, out_f=128, decomp=None, dtype='f32', vertical=False,
                          label='WN18-shaped filtered ranking evaluation (40,943 nodes x 128, 18 relations; 5,000 test '
                                'triples x 2 sides x 40,943 candidates; filter over 151,442 known triples), fp32'),
+    # one epoch's inputs of the WN18 rgcn config (configs/rgcn/lp-WN18.yaml: 30,000 positives by
+    # edge-neighbourhood sampling, 10 negatives each, general edge dropout 0.5)
+    'wn18_sampling': dict(shape='wn18', kind='sampling', in_f=0, out_f=0, decomp=None, dtype='i32', vertical=False,
+                          label='WN18-shaped per-step graph construction (141,442 training triples, 40,943 nodes): '
+                                '30,000 edge-neighbourhood picks + 300,000 negatives + edge dropout 0.5'),
     'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
                 vertical=True, raw=True,
                 label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
@@ -759,6 +764,87 @@ def run_ranking(args):
     print(json.dumps(line), flush=True)
 
 
+def run_sampling(args):
+    """Per-step graph construction (reference predict_links.py:123-148 with utils/misc.py:125-172).  `value`: picks per
+    second of training_step_inputs with the training set resident; e2e: the same plus the D2H read of the sampled
+    graph's size / a checksum (the training set is uploaded once per run, like upstream).  CPU baseline: the oracle's
+    restatement of the reference's numpy loop on a bounded number of picks."""
+    from torch_rgcn_b200 import _lib
+    from torch_rgcn_b200.sampling import EdgeNeighborhoodSampler, training_step_inputs
+    from torch_rgcn_b200.synthetic import SHAPES, random_triples
+    wl = WORKLOADS[args.workload]
+    dev = torch.device('cuda', 0)
+    N, R, E = SHAPES[wl['shape']]
+    S, rate = 30000, 10
+    train = random_triples(N, R, E, seed=0, device=dev)
+    t0 = time.perf_counter()
+    sm = EdgeNeighborhoodSampler(train, N)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    torch.manual_seed(1)
+
+    def step():
+        return training_step_inputs(sm, N, graph_batch_size=S, neg_sample_rate=rate, edge_dropout_rate=0.5)
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step()
+    sm.check()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.lib.rgcn_launch_count()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        evs[k][0].record()
+        step()
+        evs[k][1].record()
+    torch.cuda.synchronize()
+    launches = _lib.lib.rgcn_launch_count() - l0
+    ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph, batch, lbl = step()
+        int(graph.sum().item())
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    line = {
+        'metric': 'sampled_positives_per_sec', 'value': S / (ms * 1e-3), 'unit': 'picks/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'i32', 'data': 'synthetic',
+        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'train_triples': E, 'sample_size': S,
+                   'neg_sample_rate': rate, 'edge_dropout': 0.5, 'adjacency_build_s': build_s,
+                   'l2': 'L2 flushed (256 MB write) between timed steps'},
+        'e2e': {'value': S / (ms_e2e * 1e-3), 'unit': 'picks/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 8, 'note': 'training set resident (uploaded once per run, as upstream); a '
+                                                 'checksum of the sampled graph is read back every step'},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'k_sample_edge_neighborhood', 'bound': 'latency', 'achieved': None, 'peak': None,
+                     'unit': 'picks/s', 'frac': None, 'traffic': None,
+                     'note': 'a sequential process (pick i conditions on picks < i) run by one warp with its state in '
+                             'shared memory; bounded by the dependent shared-memory / L2 latency chain per pick, not '
+                             'by HBM or the tensor cores'},
+        'clocks': clocks,
+    }
+    if not args.no_cpu_baseline:
+        import numpy as np
+        from oracle import sampling_oracle as so
+        ct = train.cpu().numpy()
+        picks = 1500
+        t0 = time.perf_counter()
+        so.edge_neighborhood(ct, N, picks, np.random.default_rng(0).random((picks, 2), dtype=np.float32))
+        cpu_s = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': picks / cpu_s, 'unit': 'picks/s', 'cores': 1, 'kind': 'port', 's_total': cpu_s,
+                                'sample': f'{picks} picks of the numpy restatement of the reference loop (adjacency lists '
+                                          f'rebuilt per call and an O(N) weight vector per pick, like upstream)'}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_gpu(args):
     """Informational: the reference's torch.sparse algorithm (the port) on CUDA tensors at full workload size —
     the north-star's '>= 1.0x the reference GPU path' comparison.  Falls back to a scaled graph on OOM."""
@@ -857,6 +943,8 @@ def main():
         run_decoder(args)
     elif WORKLOADS[args.workload]['kind'] == 'ranking':
         run_ranking(args)
+    elif WORKLOADS[args.workload]['kind'] == 'sampling':
+        run_sampling(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -233,11 +233,7 @@ def make_ranking(name, seed, N, R, d, n_known, n_test, integer=False, bias=False
     """Reference evaluate (utils/misc.py:60-110, with filter_scores :39-58 and generate_true_dict :29-37) on fixed node
     embeddings.  `integer` draws small-integer embeddings: every score is then exact in fp32 whatever the summation
     order, ties are frequent, and the ranks must match an implementation exactly."""
-    import types
-    for m in ('sacred', 'sacred.observers'):
-        sys.modules.setdefault(m, types.ModuleType(m))
-    sys.modules['sacred'].Experiment = object
-    sys.modules['sacred.observers'].MongoObserver = object
+    _stub_sacred()
     from utils.misc import evaluate, generate_true_dict
     gen = torch.Generator().manual_seed(seed)
     known = torch.stack([torch.randint(0, N, (n_known,), generator=gen), torch.randint(0, R, (n_known,), generator=gen),
@@ -275,7 +271,38 @@ def make_ranking(name, seed, N, R, d, n_known, n_test, integer=False, bias=False
     save(name, dict(kind='ranking', seed=seed, N=N, R=R, d=d, integer=integer, b_init='normal' if bias else None), arrays)
 
 
+def _stub_sacred():
+    import types
+    for m in ('sacred', 'sacred.observers'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['sacred'].Experiment = object
+    sys.modules['sacred.observers'].MongoObserver = object
+
+
+def make_sampling_hist(name, seed, runs):
+    """Reference edge_neighborhood (utils/misc.py:125-172) run `runs` times on a small graph with a self-loop, a
+    repeated edge and an isolated node: histogram of the ORDERED samples it returns.  The sampler draws from numpy's
+    global generator, so parity of a restatement is statistical."""
+    _stub_sacred()
+    from utils.misc import edge_neighborhood
+    triples = [[0, 0, 1], [1, 1, 2], [2, 0, 0], [3, 1, 3], [0, 1, 1], [4, 0, 2], [1, 0, 4], [0, 0, 1], [2, 1, 3]]
+    N, S = 6, 3                                   # node 5 has no edges
+    entities = {'n%d' % i: i for i in range(N)}
+    np.random.seed(seed)
+    E = len(triples)
+    hist = np.zeros((E,) * S, dtype=np.int64)
+    for _ in range(runs):
+        picked = edge_neighborhood(triples, sample_size=S, entities=entities)
+        idx = []
+        for t in picked:                          # the function returns triples; map back to edge indices (first free match)
+            cands = [i for i, tt in enumerate(triples) if tt == t and i not in idx]
+            idx.append(cands[0])
+        hist[tuple(idx)] += 1
+    save(name, dict(kind='sampling_hist', seed=seed, N=N, S=S, runs=runs), {'triples': np.array(triples), 'hist': hist})
+
+
 def main():
+    make_sampling_hist('sampling_hist', 71, 40000)
     make_crp('lpmodel_crp', 61, 30, 3, 90, 16, 64)
     make_ranking('ranking_integer', 51, 60, 4, 8, 150, 40, integer=True)
     make_ranking('ranking_integer_bias', 52, 45, 3, 6, 120, 30, integer=True, bias=True)

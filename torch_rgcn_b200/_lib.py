@@ -105,6 +105,11 @@ def _load():
         'rgcn_rank_workspace_bytes': (C.c_size_t, [_i64, _i64]),
         'rgcn_rank_triples': (C.c_int, [_p, _i64, C.c_int, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p,
                                         C.c_size_t, _p]),
+        'rgcn_sampler_build_workspace_bytes': (C.c_size_t, [_i64]),
+        'rgcn_sampler_build': (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_sample_workspace_bytes': (C.c_size_t, [_i64, _i64]),
+        'rgcn_sample_edge_neighborhood': (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_take_triples': (C.c_int, [_p, _i64, _p, C.c_int, _i64, _p, _p, _p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -120,7 +125,9 @@ EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add
            'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan',
            'rgcn_distmult_forward', 'rgcn_distmult_backward', 'rgcn_distmult_penalty_workspace_bytes',
            'rgcn_distmult_penalty', 'rgcn_distmult_penalty_backward', 'rgcn_corrupt_triples',
-           'rgcn_rank_filter_workspace_bytes', 'rgcn_rank_build_filter', 'rgcn_rank_workspace_bytes', 'rgcn_rank_triples']
+           'rgcn_rank_filter_workspace_bytes', 'rgcn_rank_build_filter', 'rgcn_rank_workspace_bytes', 'rgcn_rank_triples',
+           'rgcn_sampler_build_workspace_bytes', 'rgcn_sampler_build', 'rgcn_sample_workspace_bytes',
+           'rgcn_sample_edge_neighborhood', 'rgcn_take_triples']
 
 
 class RgcnError(RuntimeError):

@@ -7,7 +7,7 @@
 // Upstream this materialises a (batch, num_nodes, 3) triple tensor and a (batch, num_nodes) score matrix per batch and
 // re-runs the whole encoder for every batch.  Here the node embeddings are computed once by the caller, and
 //   k_rank_queries : q_i = relations[p_i] * nodes[other_i], the target's score t_i
-//   k_rank_count   : a register-tiled fp32 product Q X^T whose epilogue only COUNTS scores > t_i and == t_i
+//   k_rank_count   : a register-tiled (128 x 128 x 8, 8 x 8 per thread) fp32 product Q X^T whose epilogue only COUNTS scores > t_i and == t_i
 //                    (the score matrix is never written)
 //   k_rank_filter  : recomputes the scores of the known true completions of each query (sorted key lists instead of
 //                    Python dictionaries) and takes them out of the counts again
@@ -21,7 +21,7 @@ using namespace rgcn;
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 128, BN = 128, BK = 8;
 
 // (sbias[s] + pbias[p]) + obias[o], the association of layers.py:96
 __device__ __forceinline__ float with_bias(float acc, const float* sb, const float* pb, const float* ob, long long s,
@@ -63,79 +63,110 @@ __global__ void k_rank_queries(const int64_t* __restrict__ q, long long T, int h
 }
 
 // counts[2 i] += #{c : score(i, c) > t_i}, counts[2 i + 1] += #{c : score(i, c) == t_i}
-__global__ void __launch_bounds__(256) k_rank_count(const float* __restrict__ Q, const int64_t* __restrict__ q, long long T,
-                                                    int head, const float* __restrict__ X, long long N, int dim,
-                                                    const float* __restrict__ sb, const float* __restrict__ pb,
-                                                    const float* __restrict__ ob, const float* __restrict__ tscore,
-                                                    int32_t* __restrict__ counts) {
-    __shared__ __align__(16) float Qs[BK][BM + 4], Xs[BK][BN + 4];
+//
+// 128 x 128 (query x candidate) tiles, 256 threads, 8 x 8 accumulators per thread (two 4-wide groups 64 apart in each
+// direction, so the LDS.128 of a half-warp are conflict-free), k-slabs of 8 double-buffered through registers: one
+// __syncthreads per slab, 4 LDS.128 per 64 FFMA.  Each accumulator runs k = 0 .. dim-1 in order (no split-K), which
+// keeps the score of a (query, candidate) pair bit-identical to dot_seq.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2) k_rank_count(const float* __restrict__ Q, const int64_t* __restrict__ q, long long T,
+                                                       int head, const float* __restrict__ X, long long N, int dim,
+                                                       const float* __restrict__ sb, const float* __restrict__ pb,
+                                                       const float* __restrict__ ob, const float* __restrict__ tscore,
+                                                       int32_t* __restrict__ counts) {
+    __shared__ __align__(16) float Qs[2][BK][BM], Xs[2][BK][BN];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const long long i0 = (long long)blockIdx.y * BM;
-    float tq[4];
-    long long qs[4], qp[4], qo[4];
+    const int lr = tid >> 1, lk = (tid & 1) * 4;              // loader role: row lr of the tile, 4 consecutive k
+    const long long qi = i0 + lr;
+    const int nslab = (dim + BK - 1) / BK;
+    float tq[8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const long long i = i0 + ty * 4 + a;
+    for (int a = 0; a < 8; ++a) {
+        const long long i = i0 + (a >> 2) * 64 + ty * 4 + (a & 3);
         tq[a] = i < T ? __ldg(tscore + i) : 0.f;
-        qs[a] = qp[a] = qo[a] = 0;
-        if (sb && i < T) { qs[a] = q[3 * i]; qp[a] = q[3 * i + 1]; qo[a] = q[3 * i + 2]; }
     }
-    int gt[4] = {0, 0, 0, 0}, eq[4] = {0, 0, 0, 0};
-    const int lr = tid >> 2, lk = (tid & 3) * 4;              // loader role: row lr of the tile, 4 consecutive k
+    int gt[8], eq[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) gt[a] = eq[a] = 0;
+
+    auto fetch = [&](const float* __restrict__ base, long long row, long long rows, int k, float (&v)[4]) {
+        if (VEC) {                                              // dim % 4 == 0 and 16-byte aligned rows
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows && k < dim) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * dim + k));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (row < rows && k + e < dim) ? __ldg(base + (size_t)row * dim + k + e) : 0.f;
+        }
+    };
+
     for (long long c0 = (long long)blockIdx.x * BN; c0 < N; c0 += (long long)gridDim.x * BN) {
-        float acc[4][4];
+        float acc[8][8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-        for (int k0 = 0; k0 < dim; k0 += BK) {
-            {
-                const long long qi = i0 + lr, ci = c0 + lr;
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        const long long ci = c0 + lr;
+        float qv[4], xv[4];
+        fetch(Q, qi, T, lk, qv);
+        fetch(X, ci, N, lk, xv);
+        __syncthreads();                                        // the previous tile's readers are done with buffer 0
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + lk + e;
-                    Qs[lk + e][lr] = (qi < T && k < dim) ? __ldg(Q + (size_t)qi * dim + k) : 0.f;
-                    Xs[lk + e][lr] = (ci < N && k < dim) ? __ldg(X + (size_t)ci * dim + k) : 0.f;
-                }
+        for (int e = 0; e < 4; ++e) { Qs[0][lk + e][lr] = qv[e]; Xs[0][lk + e][lr] = xv[e]; }
+        __syncthreads();
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int cur = sl & 1;
+            if (sl + 1 < nslab) {
+                fetch(Q, qi, T, (sl + 1) * BK + lk, qv);
+                fetch(X, ci, N, (sl + 1) * BK + lk, xv);
             }
-            __syncthreads();
+            const int kleft = dim - sl * BK;                    // the zero-padded tail adds no fma steps
 #pragma unroll
             for (int kk = 0; kk < BK; ++kk) {
-                if (k0 + kk < dim) {                             // zero padding must not add fma steps (x + 0 is exact, but
-                    // keep the chain literally identical to dot_seq)
-                    const float4 av = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
-                    const float4 bv = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
-                    const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                if (kk < kleft) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(&Qs[cur][kk][ty * 4]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&Qs[cur][kk][64 + ty * 4]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&Xs[cur][kk][tx * 4]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&Xs[cur][kk][64 + tx * 4]);
+                    const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float b8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+                        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(a8[a], b8[b], acc[a][b]);
                 }
+            }
+            if (sl + 1 < nslab) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { Qs[cur ^ 1][lk + e][lr] = qv[e]; Xs[cur ^ 1][lk + e][lr] = xv[e]; }
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            if (i0 + ty * 4 + a >= T) continue;
+        for (int a = 0; a < 8; ++a) {
+            const long long i = i0 + (a >> 2) * 64 + ty * 4 + (a & 3);
+            if (i >= T) continue;
+            long long qs = 0, qp = 0, qo = 0;
+            if (sb) { qs = q[3 * i]; qp = q[3 * i + 1]; qo = q[3 * i + 2]; }
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const long long c = c0 + tx * 4 + b;
+            for (int b = 0; b < 8; ++b) {
+                const long long c = c0 + (b >> 2) * 64 + tx * 4 + (b & 3);
                 if (c >= N) continue;
-                const float sc = head ? with_bias(acc[a][b], sb, pb, ob, c, qp[a], qo[a])
-                                      : with_bias(acc[a][b], sb, pb, ob, qs[a], qp[a], c);
+                const float sc = head ? with_bias(acc[a][b], sb, pb, ob, c, qp, qo) : with_bias(acc[a][b], sb, pb, ob, qs, qp, c);
                 gt[a] += sc > tq[a];
                 eq[a] += sc == tq[a];
             }
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 8; ++a) {
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {                        // the 16 threads that share these query rows
+        for (int o = 8; o > 0; o >>= 1) {                        // the 16 threads (half a warp) that share these query rows
             gt[a] += __shfl_xor_sync(0xffffffffu, gt[a], o);
             eq[a] += __shfl_xor_sync(0xffffffffu, eq[a], o);
         }
-        const long long i = i0 + ty * 4 + a;
+        const long long i = i0 + (a >> 2) * 64 + ty * 4 + (a & 3);
         if (tx == 0 && i < T) {
             if (gt[a]) atomicAdd(counts + 2 * i, gt[a]);
             if (eq[a]) atomicAdd(counts + 2 * i + 1, eq[a]);
@@ -281,10 +312,15 @@ extern "C" int rgcn_rank_triples(const int64_t* queries, int64_t T, int head, co
                 (long long)R, (int)dim, sbias, pbias, obias, Q, tscore, qclean, status);
     const int ytiles = (int)((T + BM - 1) / BM);
     int64_t xtiles = (N + BN - 1) / BN;
-    const int64_t want = ((int64_t)kNumSMs * 4 + ytiles - 1) / ytiles;       // ~4 CTAs per SM in total
+    const int64_t want = ((int64_t)kNumSMs * 2 + ytiles - 1) / ytiles;       // one wave of 2 CTAs per SM
     if (xtiles > want) xtiles = want;
-    RGCN_LAUNCH(k_rank_count, dim3((unsigned)xtiles, (unsigned)ytiles), 256, 0, st, Q, qclean, (long long)T, head, nodes,
-                (long long)N, (int)dim, sbias, pbias, obias, tscore, counts);
+    const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(nodes) & 15) == 0;     // Q comes from the aligned workspace
+    if (vec)
+        RGCN_LAUNCH(k_rank_count<true>, dim3((unsigned)xtiles, (unsigned)ytiles), 256, 0, st, Q, qclean, (long long)T, head,
+                    nodes, (long long)N, (int)dim, sbias, pbias, obias, tscore, counts);
+    else
+        RGCN_LAUNCH(k_rank_count<false>, dim3((unsigned)xtiles, (unsigned)ytiles), 256, 0, st, Q, qclean, (long long)T, head,
+                    nodes, (long long)N, (int)dim, sbias, pbias, obias, tscore, counts);
     if (num_true > 0)
         RGCN_LAUNCH(k_rank_filter, grid_for(T, 8), 256, 0, st, Q, qclean, (long long)T, head, nodes, (long long)N, (int)dim,
                     sbias, pbias, obias, tscore, filter_keys, filter_vals, (long long)num_true, counts);
