@@ -323,18 +323,18 @@ int rgcn_rank_triples(const int64_t* queries, int64_t num_queries, int head, con
  * :121-123 (uniform_sampling) and experiments/predict_links.py:143-148 (general edge dropout).
  * ---------------------------------------------------------------------------------------- */
 /* Vertex adjacency of the training triples (E, 3) int64 in the reference's order (utils/misc.py:129-132): entries of
- * vertex v = adj_edge / adj_other [adj_ptr[v], adj_ptr[v+1]), by edge index, the subject's entry before the object's.
- * adj_ptr (N + 1), adj_edge / adj_other (2 E).  Built once per training set. */
+ * vertex v = adj[adj_ptr[v] .. adj_ptr[v+1]), by edge index, the subject's entry before the object's; entry k is the
+ * int32 pair adj[2k] = edge index, adj[2k+1] = other end.  adj_ptr (N + 1), adj (2 E, 2), 8-byte aligned.  Built once
+ * per training set. */
 size_t rgcn_sampler_build_workspace_bytes(int64_t num_edges);
-int rgcn_sampler_build(const int64_t* triples, int64_t num_edges, int64_t num_nodes, int32_t* adj_ptr, int32_t* adj_edge,
-                       int32_t* adj_other, int32_t* status, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+int rgcn_sampler_build(const int64_t* triples, int64_t num_edges, int64_t num_nodes, int32_t* adj_ptr, int32_t* adj,
+                       int32_t* status, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 /* Edge-neighbourhood sample of sample_size <= num_edges distinct edges: out_edges[i] = index of the i-th pick.
  * uniforms (sample_size, 2) fp32 in [0, 1): [i, 0] picks the vertex (inverse CDF over count x seen, or over count > 0
  * while no seen vertex has edges left), [i, 1] the not-yet-picked incident edge.  status must be zero on entry and
  * stays zero on success. */
 size_t rgcn_sample_workspace_bytes(int64_t num_edges, int64_t num_nodes);
-int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32_t* adj_edge, const int32_t* adj_other,
-                                  int64_t num_edges, int64_t num_nodes, const float* uniforms, int64_t sample_size,
+int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32_t* adj, int64_t num_edges, int64_t num_nodes, const float* uniforms, int64_t sample_size,
                                   int32_t* out_edges, int32_t* status, void* workspace, size_t workspace_bytes,
                                   rgcn_stream_t stream);
 /* out[k] = triples[index[k]] for k < n (index int32, or int64 when index_is_int64): picked edge numbers, a uniform

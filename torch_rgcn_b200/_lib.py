@@ -106,9 +106,9 @@ def _load():
         'rgcn_rank_triples': (C.c_int, [_p, _i64, C.c_int, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p,
                                         C.c_size_t, _p]),
         'rgcn_sampler_build_workspace_bytes': (C.c_size_t, [_i64]),
-        'rgcn_sampler_build': (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_sampler_build': (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
         'rgcn_sample_workspace_bytes': (C.c_size_t, [_i64, _i64]),
-        'rgcn_sample_edge_neighborhood': (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, C.c_size_t, _p]),
+        'rgcn_sample_edge_neighborhood': (C.c_int, [_p, _p, _i64, _i64, _p, _i64, _p, _p, _p, C.c_size_t, _p]),
         'rgcn_take_triples': (C.c_int, [_p, _i64, _p, C.c_int, _i64, _p, _p, _p]),
     }
     for name, (res, args) in sigs.items():

@@ -105,8 +105,11 @@ __global__ void k_block_diag(const float* __restrict__ b, int64_t R, int64_t nb,
 // ------------------------------------------------------------------------------------------
 enum Ordering { ORD_DST = 0, ORD_SRC = 1, ORD_REL = 2 };
 
-// key layouts: DST (s*R'+p)*N+o, SRC (o*R'+p)*N+s, REL (p*N+o)*N+s (gathers of X[o] walk rows in order)
-__global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int ord,
+// key layouts, bit-packed (nb = bits of a node id, rb = bits of a relation id):
+//   DST  s | p | o      SRC  o | p | s      REL  p | o | s   (gathers of X[o] walk rows in order)
+// Only the two upper fields are sorted on (radix passes over bits [nb, 2 nb + rb)): rows and their (row, relation)
+// segments must be contiguous, the order inside a segment is free (the stable sort keeps the caller's edge order).
+__global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int ord, int nb, int rb,
                             uint64_t* __restrict__ keys, int32_t* __restrict__ idx, int32_t* status) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
@@ -116,55 +119,55 @@ __global__ void k_make_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t 
         s = p = o = 0;                              // keep the walk in bounds; the caller raises on status != 0
     }
     uint64_t k;
-    if (ord == ORD_DST) k = ((uint64_t)s * Rp + p) * N + o;
-    else if (ord == ORD_SRC) k = ((uint64_t)o * Rp + p) * N + s;
-    else k = ((uint64_t)p * N + o) * N + s;
+    if (ord == ORD_DST) k = ((((uint64_t)s << rb) | (uint64_t)p) << nb) | (uint64_t)o;
+    else if (ord == ORD_SRC) k = ((((uint64_t)o << rb) | (uint64_t)p) << nb) | (uint64_t)s;
+    else k = ((((uint64_t)p << nb) | (uint64_t)o) << nb) | (uint64_t)s;
     keys[e] = k;
     idx[e] = (int32_t)e;
 }
 
 // sorted keys -> index arrays + row pointer.  `a` = row id (s / o / p), written only through rowptr.
-__global__ void k_decode(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int64_t Rp, int ord,
+__global__ void k_decode(const uint64_t* __restrict__ keys, int64_t nnz, int ord, int nb, int rb,
                          int64_t nrows, int32_t* __restrict__ rowptr, int32_t* __restrict__ c0,
                          int32_t* __restrict__ c1) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
-    uint64_t k = keys[e];
+    const uint64_t k = keys[e], nmask = (1ull << nb) - 1, rmask = (1ull << rb) - 1;
     int64_t row, prev;
+    c0[e] = (int32_t)(k & nmask);                // REL: dst s; DST / SRC: the other endpoint
     if (ord == ORD_REL) {
-        uint64_t po = k / N;                 // p*N + o
-        row = (int64_t)(po / N);
-        c0[e] = (int32_t)(k % N);            // dst s
-        c1[e] = (int32_t)(po % N);           // src o
-        prev = e ? (int64_t)(keys[e - 1] / N / N) : -1;
+        c1[e] = (int32_t)((k >> nb) & nmask);    // src o
+        row = (int64_t)(k >> (2 * nb));
+        prev = e ? (int64_t)(keys[e - 1] >> (2 * nb)) : -1;
     } else {
-        uint64_t ap = k / N;                 // a*R' + p
-        row = (int64_t)(ap / Rp);
-        c0[e] = (int32_t)(k % N);            // the other endpoint
-        c1[e] = (int32_t)(ap % Rp);          // relation
-        prev = e ? (int64_t)(keys[e - 1] / N / Rp) : -1;
+        c1[e] = (int32_t)((k >> nb) & rmask);    // relation
+        row = (int64_t)(k >> (nb + rb));
+        prev = e ? (int64_t)(keys[e - 1] >> (nb + rb)) : -1;
     }
     for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = (int32_t)e;
     if (e == nnz - 1)
         for (int64_t r = row + 1; r <= nrows; ++r) rowptr[r] = (int32_t)nnz;
 }
 
-// segment = run of equal key / N in the sorted list ((s,p) for DST, (o,p) for SRC)
-__global__ void k_seg_flags(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int32_t* __restrict__ flag) {
+// segment = run of equal upper key part in the sorted list: key >> shift when shift >= 0 ((s,p) for DST, (o,p) for
+// SRC of the bit-packed plan keys), else key / N (mixed-radix keys of the fused row-block lists)
+__device__ __forceinline__ uint64_t seg_of(uint64_t k, int64_t N, int shift) { return shift >= 0 ? k >> shift : k / (uint64_t)N; }
+
+__global__ void k_seg_flags(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int shift, int32_t* __restrict__ flag) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
-    flag[e] = (e == 0 || keys[e] / N != keys[e - 1] / N) ? 1 : 0;
+    flag[e] = (e == 0 || seg_of(keys[e], N, shift) != seg_of(keys[e - 1], N, shift)) ? 1 : 0;
 }
 
-__global__ void k_seg_bounds(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N,
+__global__ void k_seg_bounds(const uint64_t* __restrict__ keys, int64_t nnz, int64_t N, int shift,
                              const int32_t* __restrict__ segid, int32_t* __restrict__ starts,
                              int32_t* __restrict__ ends) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
-    uint64_t k = keys[e] / N;
+    uint64_t k = seg_of(keys[e], N, shift);
     int32_t sgm = segid[e] - 1;
-    if (e == 0 || keys[e - 1] / N != k) starts[sgm] = (int32_t)e;
-    if (e == nnz - 1 || keys[e + 1] / N != k) ends[sgm] = (int32_t)e + 1;
+    if (e == 0 || seg_of(keys[e - 1], N, shift) != k) starts[sgm] = (int32_t)e;
+    if (e == nnz - 1 || seg_of(keys[e + 1], N, shift) != k) ends[sgm] = (int32_t)e + 1;
 }
 
 // count of the segment each edge belongs to, scattered back to the caller's edge order
@@ -193,19 +196,25 @@ __global__ void k_edge_values(int64_t nnz, const int32_t* __restrict__ cnt, int 
 }
 
 // inv[perm[e]] = e : position of every caller-order edge in the sorted list
-__global__ void k_invert_perm(int64_t nnz, const int32_t* __restrict__ perm, int32_t* __restrict__ inv) {
+// out[e] = val[perm[e]] and inv[perm[e]] = e in one pass over the sorted order
+__global__ void k_gather_val_invert(int64_t nnz, const int32_t* __restrict__ perm, const float* __restrict__ val,
+                                    float* __restrict__ out, int32_t* __restrict__ inv) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e < nnz) inv[perm[e]] = (int32_t)e;
+    if (e >= nnz) return;
+    const int32_t o = perm[e];
+    out[e] = val[o];
+    inv[o] = (int32_t)e;
 }
 
 __global__ void k_gather_slots(int64_t nnz, const int32_t* __restrict__ perm, const int32_t* __restrict__ inv_d,
                                const int32_t* __restrict__ inv_s, int32_t* __restrict__ dslot,
-                               int32_t* __restrict__ sslot) {
+                               int32_t* __restrict__ sslot, const float* __restrict__ val, float* __restrict__ oval) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     int32_t o = perm[e];
     dslot[e] = inv_d[o];
     sslot[e] = inv_s[o];
+    oval[e] = val[o];
 }
 
 // chunkptr[p] = number of RGCN_CHUNK_EDGES-sized chunks of relations < p (R' is small: one thread scans)
@@ -219,11 +228,6 @@ __global__ void k_chunkptr(const int32_t* __restrict__ relptr, int64_t Rp, int32
     chunkptr[Rp] = acc;
 }
 
-__global__ void k_gather_val(int64_t nnz, const int32_t* __restrict__ perm, const float* __restrict__ val,
-                             float* __restrict__ out) {
-    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e < nnz) out[e] = val[perm[e]];
-}
 
 
 // ---- super-tiling (L2-resident message ring) ----------------------------------------------------------
@@ -446,10 +450,14 @@ __global__ void k_fused_fill_items(const int32_t* __restrict__ blk_tile, const i
 }
 
 // rows with more than RGCN_LONG_ROW edges (hubs) are listed so that kernels can process them cooperatively
-__global__ void k_long_rows(const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ list, int32_t* count) {
+// blockIdx.y picks the list: 0 destination-major (count[0]), 1 source-major (count[1])
+__global__ void k_long_rows(const int32_t* __restrict__ d_rowptr, const int32_t* __restrict__ s_rowptr, int64_t N,
+                            int32_t* __restrict__ d_list, int32_t* __restrict__ s_list, int32_t* count) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= N) return;
-    if (rowptr[r + 1] - rowptr[r] > RGCN_LONG_ROW) list[atomicAdd(count, 1)] = (int32_t)r;
+    const int32_t* rowptr = blockIdx.y ? s_rowptr : d_rowptr;
+    int32_t* list = blockIdx.y ? s_list : d_list;
+    if (rowptr[r + 1] - rowptr[r] > RGCN_LONG_ROW) list[atomicAdd(count + blockIdx.y, 1)] = (int32_t)r;
 }
 
 int bits_for(unsigned __int128 maxkey) {
@@ -598,8 +606,8 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
                  (long long)nnz, (long long)N, (long long)Rp);
     RGCN_REQUIRE(nnz < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED,
                  "rgcn_graph_build: nnz and num_nodes must fit int32");
-    unsigned __int128 maxkey = (unsigned __int128)N * (unsigned __int128)Rp * (unsigned __int128)N;
-    RGCN_REQUIRE((maxkey >> 63) == 0, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: N*R'*N does not fit a 64-bit sort key");
+    const int nb = bits_for((unsigned __int128)(N > 1 ? N - 1 : 1)), rb = bits_for((unsigned __int128)(Rp > 1 ? Rp - 1 : 1));
+    RGCN_REQUIRE(2 * nb + rb <= 63, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: (node, relation, node) does not fit a 64-bit sort key");
     RGCN_REQUIRE(norm == RGCN_NORM_ROW || norm == RGCN_NORM_COL_SWAPPED || norm == RGCN_NORM_EXPLICIT, RGCN_ERR_ARG,
                  "rgcn_graph_build: unknown normalisation %d", norm);
     if (norm == RGCN_NORM_COL_SWAPPED)
@@ -632,7 +640,6 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         return RGCN_OK;
     }
     const int grid = grid_for(nnz, kBlock);
-    const int key_bits = bits_for(maxkey);
     if (norm == RGCN_NORM_EXPLICIT)
         RGCN_CHECK_CUDA(cudaMemcpyAsync(g->val, val_in, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 
@@ -641,36 +648,37 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
     const int order[3] = {first, first == ORD_DST ? ORD_SRC : ORD_DST, ORD_REL};
     for (int step = 0; step < 3; ++step) {
         const int ord = order[step];
-        RGCN_LAUNCH(k_make_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, ord, b.k0, b.i0,
+        RGCN_LAUNCH(k_make_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, ord, nb, rb, b.k0, b.i0,
                     step == 0 ? g->status : (int32_t*)nullptr);
         size_t cub_bytes = b.cub_bytes;
-        RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, key_bits,
+        const int key_bits = 2 * nb + rb, low = nb;                                    // the lowest field is not sorted on
+        RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, low, key_bits,
                                                         stream));
-        rgcn::g_launches.fetch_add((key_bits + 7) / 8 + 1, std::memory_order_relaxed);
+        rgcn::g_launches.fetch_add((key_bits - low + 7) / 8 + 1, std::memory_order_relaxed);
         int32_t *rowptr, *c0, *c1; float* oval; int64_t nrows;
         if (ord == ORD_DST) { rowptr = g->d_rowptr; c0 = g->d_src; c1 = g->d_rel; oval = g->d_val; nrows = N; }
         else if (ord == ORD_SRC) { rowptr = g->s_rowptr; c0 = g->s_dst; c1 = g->s_rel; oval = g->s_val; nrows = N; }
         else { rowptr = g->r_relptr; c0 = g->r_dst; c1 = g->r_src; oval = g->r_val; nrows = Rp; }
-        RGCN_LAUNCH(k_decode, grid, kBlock, 0, stream, b.k1, nnz, N, Rp, ord, nrows, rowptr, c0, c1);
+        RGCN_LAUNCH(k_decode, grid, kBlock, 0, stream, b.k1, nnz, ord, nb, rb, nrows, rowptr, c0, c1);
         if (step == 0 && norm != RGCN_NORM_EXPLICIT) {
-            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, N, b.flag);
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, N, nb, b.flag);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
             rgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
-            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, N, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, N, nb, b.segid, b.starts, b.ends);
             RGCN_LAUNCH(k_seg_count_scatter, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.i1, b.cnt);
             RGCN_LAUNCH(k_edge_values, grid, kBlock, 0, stream, nnz, b.cnt, norm, n_general, n_self, g->val);
         }
-        RGCN_LAUNCH(k_gather_val, grid, kBlock, 0, stream, nnz, b.i1, g->val, oval);
-        if (ord == ORD_DST) RGCN_LAUNCH(k_invert_perm, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d);
-        else if (ord == ORD_SRC) RGCN_LAUNCH(k_invert_perm, grid, kBlock, 0, stream, nnz, b.i1, b.inv_s);
+        if (ord == ORD_DST) RGCN_LAUNCH(k_gather_val_invert, grid, kBlock, 0, stream, nnz, b.i1, g->val, oval, b.inv_d);
+        else if (ord == ORD_SRC) RGCN_LAUNCH(k_gather_val_invert, grid, kBlock, 0, stream, nnz, b.i1, g->val, oval, b.inv_s);
         else {
-            RGCN_LAUNCH(k_gather_slots, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d, b.inv_s, g->r_dslot, g->r_sslot);
+            RGCN_LAUNCH(k_gather_slots, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d, b.inv_s, g->r_dslot, g->r_sslot, g->val,
+                        oval);
             RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr);
         }
     }
-    RGCN_LAUNCH(k_long_rows, grid_for(N, kBlock), kBlock, 0, stream, g->d_rowptr, N, g->d_long, g->status + 4);
-    RGCN_LAUNCH(k_long_rows, grid_for(N, kBlock), kBlock, 0, stream, g->s_rowptr, N, g->s_long, g->status + 5);
+    RGCN_LAUNCH(k_long_rows, dim3(grid_for(N, kBlock), 2), kBlock, 0, stream, g->d_rowptr, g->s_rowptr, N, g->d_long, g->s_long,
+                g->status + 4);
     if (g->tile_edges > 0) {
         const int64_t te = g->tile_edges;
         const int64_t T = (nnz - 1) / te + 1;
@@ -730,10 +738,10 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
             RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, fbits, stream));
             rgcn::g_launches.fetch_add((fbits + 7) / 8 + 1, std::memory_order_relaxed);
             // runs = (block, relation) segments of the sorted list: equal key / (4 N)
-            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, b.flag);
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, -1, b.flag);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
-            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, -1, b.segid, b.starts, b.ends);
             RGCN_LAUNCH(k_fused_run_tiles, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.cnt);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.cnt, b.inv_d, (int)nnz, stream));

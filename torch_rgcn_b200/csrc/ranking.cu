@@ -312,7 +312,10 @@ extern "C" int rgcn_rank_triples(const int64_t* queries, int64_t T, int head, co
                 (long long)R, (int)dim, sbias, pbias, obias, Q, tscore, qclean, status);
     const int ytiles = (int)((T + BM - 1) / BM);
     int64_t xtiles = (N + BN - 1) / BN;
-    const int64_t want = ((int64_t)kNumSMs * 2 + ytiles - 1) / ytiles;       // one wave of 2 CTAs per SM
+    // One balanced wave: at most 2 CTAs per SM in total (a 1.08-wave grid costs two waves), candidate tiles split
+    // evenly over the grid's x dimension.  More query tiles than CTA slots: one column of CTAs, several waves.
+    int64_t want = ((int64_t)kNumSMs * 2) / ytiles;
+    if (want < 1) want = 1;
     if (xtiles > want) xtiles = want;
     const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(nodes) & 15) == 0;     // Q comes from the aligned workspace
     if (vec)

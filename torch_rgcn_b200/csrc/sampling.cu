@@ -50,8 +50,7 @@ TreeShape tree_shape(int64_t N) {
 
 struct SamplerArgs {
     const int32_t* adj_ptr;                        // (N + 1)
-    const int32_t* adj_edge;                       // (2 E) edge index of each adjacency entry
-    const int32_t* adj_other;                      // (2 E) the other end
+    const int2* adj;                               // (2 E) {edge index, other end} of each adjacency entry
     const float* uniforms;                         // (S, 2)
     int32_t* out;                                  // (S) picked edge indices
     int32_t* g_counts;                             // global fallbacks (NULL when the array is in shared memory)
@@ -100,6 +99,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArg
     for (long long i = tid; i < (a.E + 31) / 32; i += blockDim.x) picked[i] = 0u;
     for (long long v = tid; v < N; v += blockDim.x) counts[v] = a.adj_ptr[v + 1] - a.adj_ptr[v];
     for (int i = tid; i < treeN; i += blockDim.x) treeA[i] = 0;      // nothing is seen yet
+    // pull the adjacency into L2 while all 32 warps are still here: every pick then pays L2, not DRAM, latency
+    for (long long k = (long long)tid * 16; k < 2 * a.E; k += (long long)blockDim.x * 16)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + k));
+    for (long long k = (long long)tid * 32; k <= N; k += (long long)blockDim.x * 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj_ptr + k));
     __syncthreads();
     // tree B bottom-up: level 1 from the leaves, then level by level
     for (int l = 0; l < sh.levels; ++l) {
@@ -125,8 +129,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArg
         WB = __reduce_add_sync(0xffffffffu, b);
     }
 
+    float2 unext = __ldg(reinterpret_cast<const float2*>(a.uniforms));
     for (long long it = 0; it < a.S; ++it) {
-        const float u1 = __ldg(a.uniforms + 2 * it), u2 = __ldg(a.uniforms + 2 * it + 1);
+        const float u1 = unext.x, u2 = unext.y;
+        if (it + 1 < a.S) unext = __ldg(reinterpret_cast<const float2*>(a.uniforms) + it + 1);   // off the critical path
         const bool useB = WA == 0;
         const long long W = useB ? WB : WA;
         if (W <= 0) {                                                   // out of edges: the reference divides by zero here
@@ -166,17 +172,17 @@ __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArg
         int e = -1, other = -1;
         for (int base = lo; base < hi; base += 32) {
             const int k = base + lane;
-            int ek = -1;
+            int2 ent = make_int2(-1, -1);
             bool free_entry = false;
-            if (k < hi) { ek = a.adj_edge[k]; free_entry = !get_bit(picked, ek); }
+            if (k < hi) { ent = a.adj[k]; free_entry = !get_bit(picked, ent.x); }
             const unsigned m = __ballot_sync(0xffffffffu, free_entry);
             const int n = __popc(m);
             if (j < n) {
                 unsigned mm = m;                                         // drop the j lowest set bits
                 for (int r = 0; r < j; ++r) mm &= mm - 1;
                 const int src = __ffs(mm) - 1;
-                e = __shfl_sync(0xffffffffu, ek, src);
-                other = a.adj_other[base + src];
+                e = __shfl_sync(0xffffffffu, ent.x, src);
+                other = __shfl_sync(0xffffffffu, ent.y, src);
                 break;
             }
             j -= n;
@@ -238,15 +244,14 @@ __global__ void k_adj_entries(const int64_t* __restrict__ t, long long E, long l
 }
 
 __global__ void k_adj_decode(const int64_t* __restrict__ t, long long E, long long N, const uint32_t* __restrict__ ids,
-                             int32_t* __restrict__ adj_edge, int32_t* __restrict__ adj_other) {
+                             int2* __restrict__ adj) {
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (k >= 2 * E) return;
     const uint32_t id = ids[k];
     const long long e = id >> 1;
     long long other = t[3 * e + ((id & 1) ? 0 : 2)];
     if (other < 0 || other >= N) other = 0;
-    adj_edge[k] = (int32_t)e;
-    adj_other[k] = (int32_t)other;
+    adj[k] = make_int2((int)e, (int)other);
 }
 
 // adj_ptr[v] = first sorted position with key >= v
@@ -294,8 +299,8 @@ extern "C" size_t rgcn_sampler_build_workspace_bytes(int64_t num_edges) {
     return 4 * align_up(m * sizeof(uint32_t)) + pair_sort_temp_bytes(2 * num_edges);
 }
 
-extern "C" int rgcn_sampler_build(const int64_t* triples, int64_t E, int64_t N, int32_t* adj_ptr, int32_t* adj_edge,
-                                  int32_t* adj_other, int32_t* status, void* ws, size_t ws_bytes, rgcn_stream_t stream) {
+extern "C" int rgcn_sampler_build(const int64_t* triples, int64_t E, int64_t N, int32_t* adj_ptr, int32_t* adj,
+                                  int32_t* status, void* ws, size_t ws_bytes, rgcn_stream_t stream) {
     RGCN_REQUIRE(E >= 0 && N > 0, RGCN_ERR_ARG, "rgcn_sampler_build: bad sizes");
     RGCN_REQUIRE(adj_ptr, RGCN_ERR_ARG, "rgcn_sampler_build: NULL pointer");
     RGCN_REQUIRE(2 * E < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED, "rgcn_sampler_build: sizes must fit int32");
@@ -304,7 +309,8 @@ extern "C" int rgcn_sampler_build(const int64_t* triples, int64_t E, int64_t N, 
         RGCN_CHECK_CUDA(cudaMemsetAsync(adj_ptr, 0, (size_t)(N + 1) * sizeof(int32_t), st));
         return RGCN_OK;
     }
-    RGCN_REQUIRE(triples && adj_edge && adj_other, RGCN_ERR_ARG, "rgcn_sampler_build: NULL pointer");
+    RGCN_REQUIRE(triples && adj, RGCN_ERR_ARG, "rgcn_sampler_build: NULL pointer");
+    RGCN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 7) == 0, RGCN_ERR_ARG, "rgcn_sampler_build: adj must be 8-byte aligned");
     RGCN_REQUIRE(ws && ws_bytes >= rgcn_sampler_build_workspace_bytes(E), RGCN_ERR_WORKSPACE, "rgcn_sampler_build: workspace too small");
     const int64_t M = 2 * E;
     Carver c(ws);
@@ -319,7 +325,7 @@ extern "C" int rgcn_sampler_build(const int64_t* triples, int64_t E, int64_t N, 
     RGCN_LAUNCH(k_adj_entries, grid_for(E, 256), 256, 0, st, triples, (long long)E, (long long)N, k0, v0, status);
     RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cubws, temp, k0, k1, v0, v1, (int)M, 0, bits, st));   // stable
     rgcn::g_launches.fetch_add((bits + 7) / 8 + 1, std::memory_order_relaxed);
-    RGCN_LAUNCH(k_adj_decode, grid_for(M, 256), 256, 0, st, triples, (long long)E, (long long)N, v1, adj_edge, adj_other);
+    RGCN_LAUNCH(k_adj_decode, grid_for(M, 256), 256, 0, st, triples, (long long)E, (long long)N, v1, reinterpret_cast<int2*>(adj));
     RGCN_LAUNCH(k_adj_ptr, grid_for(N + 1, 256), 256, 0, st, k1, (long long)M, (long long)N, adj_ptr);
     return RGCN_OK;
 }
@@ -335,19 +341,20 @@ extern "C" size_t rgcn_sample_workspace_bytes(int64_t num_edges, int64_t num_nod
     return b;
 }
 
-extern "C" int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32_t* adj_edge, const int32_t* adj_other,
-                                             int64_t E, int64_t N, const float* uniforms, int64_t S, int32_t* out_edges,
+extern "C" int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32_t* adj, int64_t E, int64_t N, const float* uniforms, int64_t S, int32_t* out_edges,
                                              int32_t* status, void* ws, size_t ws_bytes, rgcn_stream_t stream) {
     RGCN_REQUIRE(E >= 0 && N > 0 && S >= 0, RGCN_ERR_ARG, "rgcn_sample_edge_neighborhood: bad sizes");
     RGCN_REQUIRE(S <= E, RGCN_ERR_ARG, "rgcn_sample_edge_neighborhood: sample_size %lld exceeds the %lld edges", (long long)S, (long long)E);
     if (S == 0) return RGCN_OK;
-    RGCN_REQUIRE(adj_ptr && adj_edge && adj_other && uniforms && out_edges && status, RGCN_ERR_ARG,
+    RGCN_REQUIRE(adj_ptr && adj && uniforms && out_edges && status, RGCN_ERR_ARG,
                  "rgcn_sample_edge_neighborhood: NULL pointer");
+    RGCN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 7) == 0 && (reinterpret_cast<uintptr_t>(uniforms) & 7) == 0, RGCN_ERR_ARG,
+                 "rgcn_sample_edge_neighborhood: adj and uniforms must be 8-byte aligned");
     RGCN_REQUIRE(2 * E < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX, RGCN_ERR_UNSUPPORTED, "rgcn_sample_edge_neighborhood: sizes must fit int32");
     RGCN_REQUIRE(ws && ws_bytes >= rgcn_sample_workspace_bytes(E, N), RGCN_ERR_WORKSPACE, "rgcn_sample_edge_neighborhood: workspace too small");
     const cudaStream_t st = (cudaStream_t)stream;
     SamplerArgs a{};
-    a.adj_ptr = adj_ptr; a.adj_edge = adj_edge; a.adj_other = adj_other; a.uniforms = uniforms; a.out = out_edges;
+    a.adj_ptr = adj_ptr; a.adj = reinterpret_cast<const int2*>(adj); a.uniforms = uniforms; a.out = out_edges;
     a.status = status; a.N = N; a.E = E; a.S = S;
     a.shape = tree_shape(N);
     const Placement p = place(E, N, a.shape);

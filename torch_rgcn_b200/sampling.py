@@ -49,15 +49,15 @@ class EdgeNeighborhoodSampler:
         self.triples, self.num_nodes, self.num_edges, self.device = t, int(num_nodes), t.size(0), t.device
         E, dev = self.num_edges, t.device
         self.adj_ptr = torch.empty(self.num_nodes + 1, dtype=torch.int32, device=dev)
-        self.adj_edge = torch.empty(max(2 * E, 1), dtype=torch.int32, device=dev)
-        self.adj_other = torch.empty(max(2 * E, 1), dtype=torch.int32, device=dev)
+        self.adj = torch.empty(max(2 * E, 1), 2, dtype=torch.int32, device=dev)       # {edge index, other end} per entry
+        self.adj_edge, self.adj_other = self.adj[:, 0], self.adj[:, 1]
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         ws_bytes = _lib.lib.rgcn_sampler_build_workspace_bytes(E)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.rgcn_sampler_build(_lib.ptr(t), E, self.num_nodes, _lib.ptr(self.adj_ptr),
-                                                   _lib.ptr(self.adj_edge), _lib.ptr(self.adj_other), _lib.ptr(status),
-                                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+                                                   _lib.ptr(self.adj), _lib.ptr(status), _lib.ptr(ws), ws_bytes,
+                                                   _lib.stream_ptr()))
         bad = int(status.item())
         assert bad == 0, f'{bad} training triples index a node >= {num_nodes}'
         self._ws_bytes = _lib.lib.rgcn_sample_workspace_bytes(E, self.num_nodes)
@@ -76,8 +76,8 @@ class EdgeNeighborhoodSampler:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib.rgcn_sample_edge_neighborhood(_lib.ptr(self.adj_ptr), _lib.ptr(self.adj_edge),
-                                                              _lib.ptr(self.adj_other), self.num_edges, self.num_nodes,
+            _lib.check(_lib.lib.rgcn_sample_edge_neighborhood(_lib.ptr(self.adj_ptr), _lib.ptr(self.adj),
+                                                              self.num_edges, self.num_nodes,
                                                               _lib.ptr(u), S, _lib.ptr(out), _lib.ptr(status),
                                                               _lib.ptr(ws), self._ws_bytes, _lib.stream_ptr()))
         self._last_status = status                      # checked lazily: no host sync on the training path
