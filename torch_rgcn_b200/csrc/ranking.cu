@@ -122,20 +122,25 @@ __global__ void __launch_bounds__(256, 2) k_rank_count(const float* __restrict__
                 fetch(X, ci, N, (sl + 1) * BK + lk, xv);
             }
             const int kleft = dim - sl * BK;                    // the zero-padded tail adds no fma steps
+            const float* qrow = &Qs[cur][0][ty * 4];
+            const float* xrow = &Xs[cur][0][tx * 4];
+            auto kstep = [&](int kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(qrow + kk * BM);
+                const float4 a1 = *reinterpret_cast<const float4*>(qrow + kk * BM + 64);
+                const float4 b0 = *reinterpret_cast<const float4*>(xrow + kk * BN);
+                const float4 b1 = *reinterpret_cast<const float4*>(xrow + kk * BN + 64);
+                const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int kk = 0; kk < BK; ++kk) {
-                if (kk < kleft) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(&Qs[cur][kk][ty * 4]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&Qs[cur][kk][64 + ty * 4]);
-                    const float4 b0 = *reinterpret_cast<const float4*>(&Xs[cur][kk][tx * 4]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&Xs[cur][kk][64 + tx * 4]);
-                    const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float b8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
+                    for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(a8[a], b8[b], acc[a][b]);
+            };
+            if (kleft >= BK) {                                  // whole slab: straight-line code, no per-step tests
 #pragma unroll
-                        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(a8[a], b8[b], acc[a][b]);
-                }
+                for (int kk = 0; kk < BK; ++kk) kstep(kk);
+            } else {
+                for (int kk = 0; kk < kleft; ++kk) kstep(kk);
             }
             if (sl + 1 < nslab) {
 #pragma unroll

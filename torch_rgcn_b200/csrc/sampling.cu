@@ -23,13 +23,13 @@ using namespace rgcn;
 
 namespace {
 
-constexpr int kMaxLevels = 7;                      // 32^7 > 2^31
+constexpr int kMaxLevels = 6;                      // upper levels: 32^7 > 2^31 leaves
 constexpr size_t kSmemBudget = 200 * 1024;         // dynamic shared memory the sampler may use
 
 struct TreeShape {
-    int levels;                                    // upper levels (level 1 = sums of 32 leaves ...); 0 when N <= 32
-    int size[kMaxLevels];                          // entries of level l + 1
-    int off[kMaxLevels];                           // offset of level l + 1 inside one tree's array
+    int levels;                                    // upper levels (level 1 = groups of 32 leaves ...); 0 when N <= 32
+    int size[kMaxLevels];                          // entries of upper level l, padded to a multiple of 32
+    int off[kMaxLevels];                           // offset of upper level l inside one tree's array
     int total;                                     // entries of one tree's upper levels
 };
 
@@ -39,9 +39,10 @@ TreeShape tree_shape(int64_t N) {
     int off = 0;
     while (n > 32) {
         n = (n + 31) / 32;
-        t.size[t.levels] = (int)n;
+        const int pad = (int)((n + 31) / 32 * 32);
+        t.size[t.levels] = pad;
         t.off[t.levels] = off;
-        off += (int)n;
+        off += pad;
         ++t.levels;
     }
     t.total = off;
@@ -71,14 +72,135 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
-__device__ __forceinline__ bool get_bit(const uint32_t* b, long long i) { return (b[i >> 5] >> (i & 31)) & 1u; }
+__device__ __forceinline__ bool get_bit(const uint32_t* b, int i) { return (b[i >> 5] >> (i & 31)) & 1u; }
+
+// The S picks, by one warp.  Upper tree levels hold INCLUSIVE PREFIX SUMS inside each group of 32 siblings, so a
+// descent step is one read + ballot (no warp scan) and an update adds the weight change to the siblings at and after
+// the changed child.  LEVELS is a template parameter so every per-level loop unrolls and the level offsets stay in
+// registers (a single warp is instruction-latency bound: ~250 instructions per pick).
+template <int LEVELS>
+__device__ void sampler_picks(const SamplerArgs& a, int32_t* counts, uint32_t* seen, uint32_t* picked, int32_t* treeA,
+                              int32_t* treeB, const int lane) {       // no __restrict__: lanes exchange data through these
+    const int N = (int)a.N;
+    int off[LEVELS > 0 ? LEVELS : 1];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) off[l] = a.shape.off[l];
+    unsigned WA = 0, WB;
+    if (LEVELS == 0) WB = __reduce_add_sync(0xffffffffu, (lane < N && counts[lane] > 0) ? 1 : 0);
+    else WB = (unsigned)treeB[off[LEVELS - 1] + 31];               // the top level is one padded group
+
+    const float2* __restrict__ uni = reinterpret_cast<const float2*>(a.uniforms);
+    float2 unext = __ldg(uni);
+    const int S = (int)a.S;
+    for (int it = 0; it < S; ++it) {
+        const float u1 = unext.x, u2 = unext.y;
+        if (it + 1 < S) unext = __ldg(uni + it + 1);                // off the critical path
+        const bool useB = WA == 0;
+        const unsigned W = useB ? WB : WA;
+        if (W == 0) {                                               // out of edges: the reference divides by zero here
+            if (lane == 0) atomicAdd(a.status, 1);
+            return;
+        }
+        unsigned target = (unsigned)((double)u1 * (double)W);
+        if (target > W - 1) target = W - 1;
+        // ---- descent: the first index whose inclusive prefix sum exceeds target
+        const int32_t* tr = useB ? treeB : treeA;
+        int node = 0;
+#pragma unroll
+        for (int l = LEVELS - 1; l >= 0; --l) {
+            const unsigned p = (unsigned)tr[off[l] + node * 32 + lane];
+            const unsigned hit = __ballot_sync(0xffffffffu, p > target);
+            const int child = hit ? __ffs(hit) - 1 : 31;            // hit != 0 by construction (target < group sum)
+            const unsigned prev = __shfl_sync(0xffffffffu, p, child > 0 ? child - 1 : 0);
+            target -= child > 0 ? prev : 0u;
+            node = node * 32 + child;
+        }
+        int v;
+        {
+            const int idx = node * 32 + lane;
+            int w = 0;
+            if (idx < N) {
+                const int c = counts[idx];
+                w = useB ? (c > 0) : (get_bit(seen, idx) ? c : 0);
+            }
+            const int incl = warp_incl_scan(w, lane);
+            const unsigned hit = __ballot_sync(0xffffffffu, (unsigned)incl > target);
+            v = node * 32 + (hit ? __ffs(hit) - 1 : 31);
+        }
+        if (v >= N) {                                               // cannot happen (tree sums match the leaves)
+            if (lane == 0) atomicAdd(a.status, 1 << 20);
+            return;
+        }
+        // ---- the j-th not-yet-picked entry of adj[v]
+        const int c = counts[v];
+        const int lo = __ldg(a.adj_ptr + v), hi = __ldg(a.adj_ptr + v + 1);
+        int j = (int)((double)u2 * (double)c);
+        if (j > c - 1) j = c - 1;
+        int e = -1, other = -1;
+        for (int base = lo; base < hi; base += 32) {
+            const int k = base + lane;
+            int2 ent = make_int2(-1, -1);
+            bool free_entry = false;
+            if (k < hi) { ent = a.adj[k]; free_entry = !get_bit(picked, ent.x); }
+            const unsigned m = __ballot_sync(0xffffffffu, free_entry);
+            const int n = __popc(m);
+            if (j < n) {
+                const int rank = __popc(m & ((1u << lane) - 1u));   // this lane's position among the free entries
+                const unsigned sel = __ballot_sync(0xffffffffu, free_entry && rank == j);
+                const int src = __ffs(sel) - 1;
+                e = __shfl_sync(0xffffffffu, ent.x, src);
+                other = __shfl_sync(0xffffffffu, ent.y, src);
+                break;
+            }
+            j -= n;
+        }
+        if (e < 0) {                                                // cannot happen (counts[v] == free entries)
+            if (lane == 0) atomicAdd(a.status, 1 << 16);
+            return;
+        }
+        // ---- state update
+        const int cv = c, co = counts[other];
+        const bool sv = get_bit(seen, v), so = get_bit(seen, other);
+        const bool same = other == v;
+        const int cv2 = same ? cv - 2 : cv - 1, co2 = same ? cv2 : co - 1;
+        const int dAv = cv2 - (sv ? cv : 0);                        // v is seen afterwards
+        const int dAo = same ? 0 : co2 - (so ? co : 0);
+        const int dBv = (cv2 > 0) - (cv > 0);
+        const int dBo = same ? 0 : (co2 > 0) - (co > 0);
+        __syncwarp();
+        if (lane == 0) {
+            counts[v] = cv2;
+            if (!same) counts[other] = co2;
+            seen[v >> 5] |= 1u << (v & 31);
+            seen[other >> 5] |= 1u << (other & 31);                 // same word as v's: read after the write above
+            picked[e >> 5] |= 1u << (e & 31);
+            a.out[it] = e;
+        }
+#pragma unroll
+        for (int l = 0; l < LEVELS; ++l) {                          // prefix sums of the siblings at and after the child
+            const int iv = v >> (5 * (l + 1)), io = other >> (5 * (l + 1));
+            const int kv = (iv & ~31) + lane, ko = (io & ~31) + lane;
+            if (kv >= iv) {
+                if (dAv) treeA[off[l] + kv] += dAv;
+                if (dBv) treeB[off[l] + kv] += dBv;
+            }
+            if (ko >= io) {                                         // the same lane as above when the groups coincide
+                if (dAo) treeA[off[l] + ko] += dAo;
+                if (dBo) treeB[off[l] + ko] += dBo;
+            }
+        }
+        WA += (unsigned)(dAv + dAo);
+        WB += (unsigned)(dBv + dBo);
+        __syncwarp();
+    }
+}
 
 // One CTA.  All threads initialise the state; warp 0 then makes the S picks.
 __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const TreeShape& sh = a.shape;
-    const long long N = a.N;
+    const int N = (int)a.N;
     // carve: whatever has no global fallback pointer lives in shared memory, in this order
     size_t off = 0;
     auto carve = [&](void* g, size_t bytes) -> void* {
@@ -89,143 +211,55 @@ __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArg
     };
     const int treeN = sh.total > 0 ? sh.total : 1;
     int32_t* tree = (int32_t*)carve(a.g_tree, 2 * (size_t)treeN * 4);
-    uint32_t* seen = (uint32_t*)carve(a.g_seen, (size_t)((N + 31) / 32) * 4);
+    uint32_t* seen = (uint32_t*)carve(a.g_seen, (size_t)((a.N + 31) / 32) * 4);
     uint32_t* picked = (uint32_t*)carve(a.g_picked, (size_t)((a.E + 31) / 32) * 4);
-    int32_t* counts = (int32_t*)carve(a.g_counts, (size_t)N * 4);
+    int32_t* counts = (int32_t*)carve(a.g_counts, (size_t)a.N * 4);
     int32_t* treeA = tree;
     int32_t* treeB = tree + treeN;
 
-    for (long long i = tid; i < (N + 31) / 32; i += blockDim.x) seen[i] = 0u;
+    for (int i = tid; i < (N + 31) / 32; i += blockDim.x) seen[i] = 0u;
     for (long long i = tid; i < (a.E + 31) / 32; i += blockDim.x) picked[i] = 0u;
-    for (long long v = tid; v < N; v += blockDim.x) counts[v] = a.adj_ptr[v + 1] - a.adj_ptr[v];
+    for (int v = tid; v < N; v += blockDim.x) counts[v] = a.adj_ptr[v + 1] - a.adj_ptr[v];
     for (int i = tid; i < treeN; i += blockDim.x) treeA[i] = 0;      // nothing is seen yet
     // pull the adjacency into L2 while all 32 warps are still here: every pick then pays L2, not DRAM, latency
     for (long long k = (long long)tid * 16; k < 2 * a.E; k += (long long)blockDim.x * 16)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + k));
-    for (long long k = (long long)tid * 32; k <= N; k += (long long)blockDim.x * 32)
+    for (long long k = (long long)tid * 32; k <= a.N; k += (long long)blockDim.x * 32)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj_ptr + k));
     __syncthreads();
-    // tree B bottom-up: level 1 from the leaves, then level by level
+    // tree B bottom-up: raw weights of a level (children with edges left), then the prefix sums inside each group
     for (int l = 0; l < sh.levels; ++l) {
         for (int i = tid; i < sh.size[l]; i += blockDim.x) {
             int s = 0;
-            for (int c = 0; c < 32; ++c) {
-                const long long ch = (long long)i * 32 + c;
-                if (l == 0) { if (ch < N) s += counts[ch] > 0; }
-                else if (ch < sh.size[l - 1]) s += treeB[sh.off[l - 1] + ch];
+            if (l == 0) {
+                for (int c = 0; c < 32; ++c) {
+                    const long long ch = (long long)i * 32 + c;
+                    if (ch < N) s += counts[ch] > 0;
+                }
+            } else if ((long long)i * 32 + 31 < sh.size[l - 1]) {
+                s = treeB[sh.off[l - 1] + i * 32 + 31];              // the child group's total (its last prefix sum)
             }
             treeB[sh.off[l] + i] = s;
         }
         __syncthreads();
+        for (int g = tid; g < sh.size[l] / 32; g += blockDim.x) {
+            int run = 0;
+            for (int c = 0; c < 32; ++c) {
+                run += treeB[sh.off[l] + g * 32 + c];
+                treeB[sh.off[l] + g * 32 + c] = run;
+            }
+        }
+        __syncthreads();
     }
     if (tid >= 32) return;
-
-    // totals (top level has <= 32 entries; with no upper levels the leaves are the top)
-    long long WA = 0, WB = 0;
-    {
-        int b = 0;
-        if (sh.levels == 0) { if (lane < N) b = counts[lane] > 0; }
-        else if (lane < sh.size[sh.levels - 1]) b = treeB[sh.off[sh.levels - 1] + lane];
-        WB = __reduce_add_sync(0xffffffffu, b);
-    }
-
-    float2 unext = __ldg(reinterpret_cast<const float2*>(a.uniforms));
-    for (long long it = 0; it < a.S; ++it) {
-        const float u1 = unext.x, u2 = unext.y;
-        if (it + 1 < a.S) unext = __ldg(reinterpret_cast<const float2*>(a.uniforms) + it + 1);   // off the critical path
-        const bool useB = WA == 0;
-        const long long W = useB ? WB : WA;
-        if (W <= 0) {                                                   // out of edges: the reference divides by zero here
-            if (lane == 0) atomicAdd(a.status, 1);
-            return;
-        }
-        long long target = (long long)((double)u1 * (double)W);
-        if (target > W - 1) target = W - 1;
-        // ---- descent: the first index whose inclusive prefix sum exceeds target
-        const int32_t* tr = useB ? treeB : treeA;
-        long long node = 0;                                             // index inside the current level
-        for (int l = sh.levels - 1; l >= -1; --l) {
-            const long long idx = node * 32 + lane;                     // child index at level l (leaves: l == -1)
-            int w = 0;
-            if (l >= 0) { if (idx < sh.size[l]) w = tr[sh.off[l] + idx]; }
-            else if (idx < N) {
-                const int c = counts[idx];
-                w = useB ? (c > 0) : (get_bit(seen, idx) ? c : 0);
-            }
-            const int incl = warp_incl_scan(w, lane);
-            const unsigned hit = __ballot_sync(0xffffffffu, (long long)incl > target);
-            const int child = hit ? __ffs(hit) - 1 : 31;                // hit != 0 by construction (target < subtree sum)
-            const int before = __shfl_sync(0xffffffffu, incl - w, child);
-            target -= before;
-            node = node * 32 + child;
-        }
-        const long long v = node;
-        if (v >= N) {                                                   // cannot happen (tree sums match the leaves)
-            if (lane == 0) atomicAdd(a.status, 1 << 20);
-            return;
-        }
-        // ---- the j-th not-yet-picked entry of adj[v]
-        const int c = counts[v];
-        int j = (int)((double)u2 * (double)c);
-        if (j > c - 1) j = c - 1;
-        const int lo = a.adj_ptr[v], hi = a.adj_ptr[v + 1];
-        int e = -1, other = -1;
-        for (int base = lo; base < hi; base += 32) {
-            const int k = base + lane;
-            int2 ent = make_int2(-1, -1);
-            bool free_entry = false;
-            if (k < hi) { ent = a.adj[k]; free_entry = !get_bit(picked, ent.x); }
-            const unsigned m = __ballot_sync(0xffffffffu, free_entry);
-            const int n = __popc(m);
-            if (j < n) {
-                unsigned mm = m;                                         // drop the j lowest set bits
-                for (int r = 0; r < j; ++r) mm &= mm - 1;
-                const int src = __ffs(mm) - 1;
-                e = __shfl_sync(0xffffffffu, ent.x, src);
-                other = __shfl_sync(0xffffffffu, ent.y, src);
-                break;
-            }
-            j -= n;
-        }
-        if (e < 0) {                                                    // cannot happen (counts[v] == free entries)
-            if (lane == 0) atomicAdd(a.status, 1 << 16);
-            return;
-        }
-        // ---- state update (lane 0 writes the leaves, lanes 0 .. levels-1 each fix one tree level)
-        const int cv = c, co = counts[other];
-        const bool sv = get_bit(seen, v), so = get_bit(seen, other);
-        const bool same = other == v;
-        const int cv2 = same ? cv - 2 : cv - 1, co2 = same ? cv2 : co - 1;
-        const int dAv = cv2 - (sv ? cv : 0);                            // v is seen afterwards
-        const int dAo = same ? 0 : co2 - (so ? co : 0);
-        const int dBv = (cv2 > 0) - (cv > 0);
-        const int dBo = same ? 0 : (co2 > 0) - (co > 0);
-        __syncwarp();
-        if (lane == 0) {
-            counts[v] = cv2;
-            if (!same) counts[other] = co2;
-            seen[v >> 5] |= 1u << (v & 31);
-            seen[other >> 5] |= 1u << (other & 31);
-            picked[e >> 5] |= 1u << (e & 31);
-            a.out[it] = e;
-        }
-        if (lane < sh.levels) {
-            long long iv = v, io = other;
-            for (int l = 0; l <= lane; ++l) { iv >>= 5; io >>= 5; }
-            const int o = sh.off[lane];
-            if (iv == io) {
-                if (dAv + dAo) treeA[o + iv] += dAv + dAo;
-                if (dBv + dBo) treeB[o + iv] += dBv + dBo;
-            } else {
-                if (dAv) treeA[o + iv] += dAv;
-                if (dAo) treeA[o + io] += dAo;
-                if (dBv) treeB[o + iv] += dBv;
-                if (dBo) treeB[o + io] += dBo;
-            }
-        }
-        WA += dAv + dAo;
-        WB += dBv + dBo;
-        __syncwarp();
+    switch (sh.levels) {
+        case 0: sampler_picks<0>(a, counts, seen, picked, treeA, treeB, lane); break;
+        case 1: sampler_picks<1>(a, counts, seen, picked, treeA, treeB, lane); break;
+        case 2: sampler_picks<2>(a, counts, seen, picked, treeA, treeB, lane); break;
+        case 3: sampler_picks<3>(a, counts, seen, picked, treeA, treeB, lane); break;
+        case 4: sampler_picks<4>(a, counts, seen, picked, treeA, treeB, lane); break;
+        case 5: sampler_picks<5>(a, counts, seen, picked, treeA, treeB, lane); break;
+        default: sampler_picks<6>(a, counts, seen, picked, treeA, treeB, lane); break;
     }
 }
 
