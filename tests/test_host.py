@@ -127,6 +127,47 @@ def test_forward_without_cuda_fails_loudly():
         layer(torch.randn(2, 4))
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_link_prediction_helpers_without_cuda_fail_loudly():
+    """Decoder, ranking evaluation, sampling and the LP models have no CPU path either."""
+    from torch_rgcn_b200 import evaluation, sampling
+    from torch_rgcn_b200.decoder import DistMult
+    from torch_rgcn_b200.models import CompressionRelationPredictor
+    t = torch.tensor([[0, 0, 1], [1, 1, 0], [2, 0, 2]])
+    x = torch.randn(3, 4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        DistMult(2, 4, 3, 2)(t, x)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        evaluation.rank_triples(t, x, torch.randn(2, 4), True)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        evaluation.TrueTripleFilter(t, 3, 2)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        sampling.EdgeNeighborhoodSampler(t, 3)
+    for fn in (sampling.uniform_sampling, sampling.edge_neighborhood):
+        with pytest.raises(RuntimeError, match='CUDA'):
+            fn(t, 2, {0: 0, 1: 1, 2: 2})
+    with pytest.raises(RuntimeError, match='CUDA'):
+        sampling.edge_dropout(t, 0.5)
+    enc = {'node_embedding': 4, 'hidden1_size': 4, 'num_layers': 1, 'weight_init': 'glorot-normal', 'bias_init': 'zeros',
+           'edge_dropout': {'general': 0.5, 'self_loop': 0.2, 'self_loop_type': 'schlichtkrull-dropout'}}
+    dec = {'l2_penalty_type': 'schlichtkrull-l2', 'l2_penalty': 0.01, 'weight_init': 'standard-normal'}
+    model = CompressionRelationPredictor(nnodes=3, nrel=2, encoder_config=enc, decoder_config=dec)
+    assert sorted(n for n, _ in model.named_parameters()) == sorted(
+        ['node_embeddings', 'node_embeddings_bias', 'rgc1.weights', 'rgc1.bias', 'scoring_function.relations',
+         'encoding_layer.weight', 'encoding_layer.bias', 'decoding_layer.weight', 'decoding_layer.bias'])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(t, t)
+
+
+def test_select_sampling_names():
+    """reference utils/misc.py:112-119: the two method names, case-insensitive, anything else NotImplementedError"""
+    from torch_rgcn_b200 import sampling
+    assert sampling.select_sampling('Uniform') is sampling.uniform_sampling
+    assert sampling.select_sampling('edge-neighborhood') is sampling.edge_neighborhood
+    with pytest.raises(NotImplementedError):
+        sampling.select_sampling('snowball')
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'torch_rgcn_b200')
     for fn in os.listdir(pkg):
