@@ -1,15 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-echo "== sampling+ranking tests"; timeout 300 python -m pytest tests/test_gpu_sampling.py tests/test_gpu_ranking.py -q -x 2>&1 | tail -15 | tee $O/test_side.log
-for w in wn18_sampling wn18_ranking; do
-  echo "== bench $w"; timeout 200 python bench.py --workload $w --steps 10 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err
-  python - "$O/bench_$w.json" <<'PY'
-import json,sys
-try:
-    j=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print({k:j.get(k) for k in ['value','unit','ms_per_step','gpu_launches']}, j.get('e2e',{}).get('ms_per_step'), (j.get('roofline') or {}).get('frac'))
-except Exception as e: print('bad line', e)
-PY
-  tail -3 $O/bench_$w.err
-done
+echo "== sampling tests"; timeout 60 python -m pytest tests/test_gpu_sampling.py -q -x 2>&1 | tail -4 | tee $O/test_side.log
+echo "== bench wn18_sampling"; timeout 50 python bench.py --workload wn18_sampling --steps 10 --no-cpu-baseline > $O/bench_wn18_sampling.json 2> $O/bench_wn18_sampling.err
+python -c "
+import json
+j=json.loads(open('$O/bench_wn18_sampling.json').read().strip().splitlines()[-1]); print(j['ms_per_step'], j['value'], j['e2e']['ms_per_step'])"

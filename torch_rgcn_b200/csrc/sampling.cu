@@ -115,25 +115,29 @@ __device__ void sampler_picks(const SamplerArgs& a, int32_t* counts, uint32_t* s
             target -= child > 0 ? prev : 0u;
             node = node * 32 + child;
         }
-        int v;
+        int v, c, lo, hi;
         {
             const int idx = node * 32 + lane;
-            int w = 0;
+            int w = 0, cl = 0, pl = 0, ph = 0;
             if (idx < N) {
-                const int c = counts[idx];
-                w = useB ? (c > 0) : (get_bit(seen, idx) ? c : 0);
+                pl = __ldg(a.adj_ptr + idx);                        // every candidate's list bounds: the L2 latency of the
+                ph = __ldg(a.adj_ptr + idx + 1);                    // chosen one hides behind the scan below
+                cl = counts[idx];
+                w = useB ? (cl > 0) : (get_bit(seen, idx) ? cl : 0);
             }
             const int incl = warp_incl_scan(w, lane);
             const unsigned hit = __ballot_sync(0xffffffffu, (unsigned)incl > target);
-            v = node * 32 + (hit ? __ffs(hit) - 1 : 31);
+            const int child = hit ? __ffs(hit) - 1 : 31;
+            v = node * 32 + child;
+            c = __shfl_sync(0xffffffffu, cl, child);
+            lo = __shfl_sync(0xffffffffu, pl, child);
+            hi = __shfl_sync(0xffffffffu, ph, child);
         }
-        if (v >= N) {                                               // cannot happen (tree sums match the leaves)
+        if (v >= N || c <= 0) {                                     // cannot happen (tree sums match the leaves)
             if (lane == 0) atomicAdd(a.status, 1 << 20);
             return;
         }
         // ---- the j-th not-yet-picked entry of adj[v]
-        const int c = counts[v];
-        const int lo = __ldg(a.adj_ptr + v), hi = __ldg(a.adj_ptr + v + 1);
         int j = (int)((double)u2 * (double)c);
         if (j > c - 1) j = c - 1;
         int e = -1, other = -1;
@@ -252,15 +256,29 @@ __global__ void __launch_bounds__(1024, 1) k_sample_edge_neighborhood(SamplerArg
         __syncthreads();
     }
     if (tid >= 32) return;
-    switch (sh.levels) {
-        case 0: sampler_picks<0>(a, counts, seen, picked, treeA, treeB, lane); break;
-        case 1: sampler_picks<1>(a, counts, seen, picked, treeA, treeB, lane); break;
-        case 2: sampler_picks<2>(a, counts, seen, picked, treeA, treeB, lane); break;
-        case 3: sampler_picks<3>(a, counts, seen, picked, treeA, treeB, lane); break;
-        case 4: sampler_picks<4>(a, counts, seen, picked, treeA, treeB, lane); break;
-        case 5: sampler_picks<5>(a, counts, seen, picked, treeA, treeB, lane); break;
-        default: sampler_picks<6>(a, counts, seen, picked, treeA, treeB, lane); break;
+#define RGCN_SAMPLER_DISPATCH(C, S, P, TA, TB)                                        \
+    switch (sh.levels) {                                                                \
+        case 0: sampler_picks<0>(a, C, S, P, TA, TB, lane); break;                      \
+        case 1: sampler_picks<1>(a, C, S, P, TA, TB, lane); break;                      \
+        case 2: sampler_picks<2>(a, C, S, P, TA, TB, lane); break;                      \
+        case 3: sampler_picks<3>(a, C, S, P, TA, TB, lane); break;                      \
+        case 4: sampler_picks<4>(a, C, S, P, TA, TB, lane); break;                      \
+        case 5: sampler_picks<5>(a, C, S, P, TA, TB, lane); break;                      \
+        default: sampler_picks<6>(a, C, S, P, TA, TB, lane); break;                     \
     }
+    if (!a.g_tree && !a.g_seen && !a.g_picked && !a.g_counts) {
+        // the whole state is in shared memory: re-derive the pointers from the shared array itself, so the compiler
+        // sees the address space and this copy of the pick loop uses LDS / STS instead of generic loads
+        size_t o = 0;
+        int32_t* s_tree = reinterpret_cast<int32_t*>(smem + o);    o += (2 * (size_t)treeN * 4 + 15) / 16 * 16;
+        uint32_t* s_seen = reinterpret_cast<uint32_t*>(smem + o);  o += ((size_t)((a.N + 31) / 32) * 4 + 15) / 16 * 16;
+        uint32_t* s_picked = reinterpret_cast<uint32_t*>(smem + o); o += ((size_t)((a.E + 31) / 32) * 4 + 15) / 16 * 16;
+        int32_t* s_counts = reinterpret_cast<int32_t*>(smem + o);
+        RGCN_SAMPLER_DISPATCH(s_counts, s_seen, s_picked, s_tree, s_tree + treeN)
+    } else {
+        RGCN_SAMPLER_DISPATCH(counts, seen, picked, treeA, treeB)
+    }
+#undef RGCN_SAMPLER_DISPATCH
 }
 
 // adjacency entries before sorting: entry 2 i = (s_i, edge i, other o_i), entry 2 i + 1 = (o_i, edge i, other s_i)
