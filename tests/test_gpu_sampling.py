@@ -36,6 +36,7 @@ def test_adjacency_matches_reference_order(cuda_device):
 @pytest.mark.parametrize('N,E,S,hub,loops', [
     (20, 60, 67, False, 4),            # no upper tree level (N <= 32), sample == every edge (incl. the repeats)
     (700, 2500, 900, True, 20),        # one upper level, a 800-entry adjacency list
+    (5000, 8000, 2500, False, 30),     # two upper levels
     (40943, 30000, 6000, False, 50),   # WN18-sized node set: three upper levels, state in shared memory
     (40943, 30000, 3000, True, 0),
     (300000, 20000, 2500, False, 10),  # counts do not fit in shared memory: workspace placement
