@@ -162,7 +162,7 @@ def run_ours(args):
     import torch.distributed as dist
     from torch_rgcn_b200 import _lib
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC, RelationalGraphConvolutionLP
-    from torch_rgcn_b200.parallel import RelationShardedNC
+    from torch_rgcn_b200.parallel import RelationShardedNC, RowShardedNC
     from torch_rgcn_b200.utils import add_inverse_and_self
 
     rank, world, local = dist_info()
@@ -181,7 +181,7 @@ def run_ours(args):
         layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
                                              decomposition=wl['decomp'], vertical_stacking=wl['vertical']).to(dev)
         if world > 1:
-            layer = RelationShardedNC(layer)
+            layer = RowShardedNC(layer) if args.shard == 'rows' else RelationShardedNC(layer)
         call = lambda x: layer(x)                                            # noqa: E731
     else:
         layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
@@ -345,7 +345,9 @@ def run_ours(args):
         'config': {'workload': wl['label'] + (' [skewed: cubic node skew, Zipf relations]' if args.skew else ''),
                    'name': args.workload, 'num_nodes': N, 'num_relations': Rp, 'nnz': nnz,
                    'l2': 'L2 flushed (256 MB write) between timed steps; flush outside the event pairs',
-                   'parallelism': f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)'
+                   'parallelism': ((f'row-sharded x{world} (experimental), one all-gather of out rows (fwd) and of '
+                                    f'grad_features rows (bwd)') if args.shard == 'rows' else
+                                   f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)')
                    if world > 1 else 'single GPU',
                    'kernels': 'fused row-block (RGCN_FUSED=1)' if fused else 'two-phase (messages through HBM)',
                    'graph_plan': 'built once at first call (outside timed region)' if wl['kind'] == 'nc'
@@ -932,6 +934,9 @@ def main():
     ap.add_argument('--ref-scale', type=float, default=1.0, help='graph scale for --impl reference-gpu')
     ap.add_argument('--skew', action='store_true', help='power-law node degrees + Zipf relation sizes (hub rows)')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--shard', default='relations', choices=['relations', 'rows'],
+                    help='multi-GPU partition of an NC layer: relations + all-reduce (default, the north-star design) or '
+                         'rows + all-gather (experimental, parallel.RowShardedNC)')
     args = ap.parse_args()
     if args.impl == 'reference-gpu':
         run_reference_gpu(args)

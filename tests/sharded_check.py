@@ -5,6 +5,7 @@
 
 Every rank builds the same layer, runs the single-GPU engine on the full graph and the sharded engine on its relations,
 and checks that output, feature gradient and (after sync_parameter_grads) parameter gradients agree.
+SHARD=rows in the environment checks the experimental row-sharded layer (parallel.RowShardedNC) instead.
 """
 import os
 import sys
@@ -17,7 +18,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
-    from torch_rgcn_b200.parallel import RelationShardedNC
+    from torch_rgcn_b200.parallel import RelationShardedNC, RowShardedNC
+    Sharded = RowShardedNC if os.environ.get('SHARD') == 'rows' else RelationShardedNC
     from torch_rgcn_b200.synthetic import random_triples
     from torch_rgcn_b200.utils import add_inverse_and_self
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -46,7 +48,7 @@ def main():
         with torch.no_grad():
             ref.bias.normal_()
             lay.bias.copy_(ref.bias)
-        sh = RelationShardedNC(lay)
+        sh = Sharded(lay)
         g = torch.Generator(device=dev).manual_seed(7)
         x1 = x2 = None
         if c['in_f'] is not None:

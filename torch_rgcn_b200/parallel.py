@@ -143,3 +143,167 @@ class RelationShardedNC(torch.nn.Module):
         for name, p in self.layer.named_parameters():
             if p.grad is not None and name != 'bias':      # the bias gradient is already complete on every rank
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Row sharding (experimental; host logic covered by a gloo test, GPU parity through tests/sharded_check.py with
+# SHARD=rows — not yet run on B200s).
+#
+# Relation sharding all-reduces a full (N, O) output per direction whatever the world size.  Sharding ROWS instead
+# needs no reduction of node data: the forward partitions edges by destination row (rank k produces complete output
+# rows [lo_k, hi_k) from ALL relations), the backward partitions them by source row (rank k produces complete
+# feature-gradient rows), and the row blocks are all-gathered — half the bytes of an all-reduce, and exact (every row
+# comes from one rank).  Only the parameter gradients (small) are all-reduced.
+# ------------------------------------------------------------------------------------------------------
+def plan_row_shards(num_nodes, world):
+    """Equal row blocks (all_gather needs equal chunks): rows_per = ceil(N / world); rank k owns
+    [k * rows_per, min(N, (k + 1) * rows_per))."""
+    rows_per = (int(num_nodes) + int(world) - 1) // int(world)
+    return rows_per, [(min(k * rows_per, num_nodes), min((k + 1) * rows_per, num_nodes)) for k in range(world)]
+
+
+def partition_edges_by_rows(triples_plus, column, lo, hi):
+    """Mask of the rows of `triples_plus` whose `column` entry (0 = destination s, 2 = source o) lies in [lo, hi)."""
+    c = triples_plus[:, column]
+    return (c >= lo) & (c < hi)
+
+
+def gather_row_blocks(x, num_nodes, rows_per, lo, hi, group=None, comm_dtype=None):
+    """x (N, d) with rows [lo, hi) valid on this rank -> (N, d) with every rank's rows, by ONE all-gather."""
+    world = dist.get_world_size(group)
+    d = x.size(1)
+    dt = comm_dtype if comm_dtype is not None else x.dtype
+    mine = torch.zeros(rows_per, d, dtype=dt, device=x.device)
+    mine[: hi - lo] = x[lo:hi].to(dt)
+    full = torch.empty(world * rows_per, d, dtype=dt, device=x.device)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:num_nodes].to(x.dtype)
+
+
+class _RowShardedApply(torch.autograd.Function):
+    """forward: local rows by `shard.forward_local`, all-gather; backward: local feature-gradient rows by
+    `shard.backward_local`, all-gather, all-reduce of the parameter gradients (bias excluded: every rank computes it
+    from the replicated upstream gradient)."""
+
+    @staticmethod
+    def forward(ctx, shard, features, *params):
+        out = shard.forward_local(features, params)
+        ctx.shard = shard
+        ctx.n_params = len(params)
+        ctx.save_for_backward(features, *params)
+        return gather_row_blocks(out, shard.num_nodes, shard.rows_per, shard.lo, shard.hi, shard.group, shard.out_comm_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        shard = ctx.shard
+        features, *params = ctx.saved_tensors
+        need = ctx.needs_input_grad                       # (shard, features, *params)
+        g_feat, g_params = shard.backward_local(features, params, grad_out.contiguous(), need[1], need[2:])
+        if g_feat is not None:
+            g_feat = gather_row_blocks(g_feat, shard.num_nodes, shard.rows_per, shard.lo, shard.hi, shard.group,
+                                       shard.grad_comm_dtype)
+        for name, g in zip(shard.param_names, g_params):
+            if g is not None and name != 'bias':
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=shard.group)
+        return (None, g_feat, *g_params)
+
+
+class RowShardedNC(torch.nn.Module):
+    """Runs a RelationalGraphConvolutionNC with the OUTPUT ROWS sharded over the ranks (see the block comment above).
+
+    Same contract as RelationShardedNC: every rank constructs the same layer and passes the same features; the output
+    and, after backward, all gradients are identical on all ranks (no sync_parameter_grads needed)."""
+
+    def __init__(self, layer, group=None):
+        super().__init__()
+        self.layer = layer
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.num_nodes = layer.num_nodes
+        self.rows_per, ranges = plan_row_shards(layer.num_nodes, self.world)
+        self.lo, self.hi = ranges[self.rank]
+        self.out_comm_dtype = self.grad_comm_dtype = None
+        self._plans = None
+
+    def sync_parameter_grads(self):
+        """Nothing to do (kept for interface parity with RelationShardedNC)."""
+
+    def _local_plans(self, device, features):
+        L = self.layer
+        tile_edges = L._tile_edges(features)
+        kw = dict(tile_edges=tile_edges, ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')),
+                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
+                  fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
+        key = (str(device), tile_edges, kw['fuse_rows'])
+        if self._plans is None or self._plans[0] != key:
+            tp = L.triples.to(device)
+            full = L._plan(device)                               # per-edge weights of the FULL graph, caller order
+            val = full.val[:full.nnz]
+            fwd_mask = partition_edges_by_rows(tp, 0, self.lo, self.hi)
+            bwd_mask = partition_edges_by_rows(tp, 2, self.lo, self.hi)
+            plan_f = GraphPlan(tp[fwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[fwd_mask],
+                               validate=False, **kw)
+            plan_b = GraphPlan(tp[bwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[bwd_mask],
+                               validate=False, **kw)
+            L._plan_cache = None
+            self._plans = (key, plan_f, plan_b)
+        return self._plans[1], self._plans[2]
+
+    # -- what _RowShardedApply calls ------------------------------------------------------------------
+    def _named(self, params):
+        d = dict(weights=None, bases=None, comps=None, blocks=None, bias=None)
+        d.update(dict(zip(self.param_names, params)))
+        return d
+
+    def forward_local(self, features, params):
+        p = self._named(params)
+        with torch.no_grad():
+            return _Propagate.apply(self._plan_f, self._form, self._in_dim, self.layer.out_features, features,
+                                    p['weights'], p['bases'], p['comps'], p['blocks'], None, p['bias'], None, True)
+
+    def backward_local(self, features, params, grad_out, need_features, need_params):
+        """The engine's backward over the source-row shard, through _Propagate.backward with a stand-in context (the
+        engine keeps no forward state: it needs the plan, the inputs and the upstream gradient only)."""
+        from types import SimpleNamespace
+        from .functional import _f32c
+        p = self._named(params)
+        needs = dict(zip(self.param_names, need_params))
+        if features is not None:                                 # what _Propagate.forward does before saving its inputs
+            if features.dtype not in (torch.float32, torch.bfloat16):
+                features = features.float()
+            features = features.contiguous()
+        saved = tuple(_f32c(p[k]) for k in ('weights', 'bases', 'comps', 'blocks')) + (None, _f32c(p['bias']), None)
+        ctx = SimpleNamespace(
+            saved_tensors=(features,) + saved, plan=self._plan_b, form=self._form,
+            dims=(self._in_dim, self.layer.out_features),
+            in_dtypes=[None if t is None else t.dtype
+                       for t in (features, p['weights'], p['bases'], p['comps'], p['blocks'], None, p['bias'])],
+            needs_input_grad=(False, False, False, False, bool(need_features and features is not None),
+                              needs.get('weights', False), needs.get('bases', False), needs.get('comps', False),
+                              needs.get('blocks', False), False, needs.get('bias', False), False, False))
+        grads = _Propagate.backward(ctx, grad_out)
+        by_name = dict(weights=grads[5], bases=grads[6], comps=grads[7], blocks=grads[8], bias=grads[10])
+        return grads[4], [by_name[n] for n in self.param_names]
+
+    def forward(self, features=None):
+        L = self.layer
+        assert (features is None) == (L.in_features is None), "in_features not provided!"
+        lead = L._decomposed()[0]
+        self._plan_f, self._plan_b = self._local_plans(lead.device, features)
+        self._in_dim = L.in_features if L.in_features is not None else L.num_nodes
+        if L.diag_weight_matrix:
+            self._form, names = 'diag', ['weights']
+        elif L.weight_decomp is None:
+            self._form, names = 'dense', ['weights']
+        elif L.weight_decomp == 'basis':
+            self._form, names = 'basis', ['bases', 'comps']
+        else:
+            self._form, names = 'block', ['blocks']
+        if L.bias is not None:
+            names = names + ['bias']
+        self.param_names = names
+        bf16 = features is not None and features.dtype == torch.bfloat16
+        self.out_comm_dtype = torch.bfloat16 if bf16 else None       # like RelationShardedNC: bf16 layers send bf16
+        self.grad_comm_dtype = None                                  # the feature gradient already has the feature dtype
+        return _RowShardedApply.apply(self, features, *[getattr(L, n) for n in names])
