@@ -20,6 +20,12 @@ explicit scatter-adds in float64.
 """
 import numpy as np
 
+
+def _f64(a):
+    """float64 ndarray view / copy (np.float64(a) turns one-element arrays into scalars)."""
+    return np.asarray(a, dtype=np.float64)
+
+
 I64 = np.int64
 
 
@@ -136,13 +142,13 @@ def effective_weights(params):
     diag:  weights (R', I) read as diag  layers.py:147-151, 290-291
     """
     if 'bases' in params:
-        return np.einsum('rb,bio->rio', np.float64(params['comps']), np.float64(params['bases']))
+        return np.einsum('rb,bio->rio', _f64(params['comps']), _f64(params['bases']))
     if 'blocks' in params:
         w = block_diag(params['blocks'])
         if 'blocks_self' in params:
-            w = np.concatenate([w, np.float64(params['blocks_self'])[None]], axis=0)
+            w = np.concatenate([w, _f64(params['blocks_self'])[None]], axis=0)
         return w
-    w = np.float64(params['weights'])
+    w = _f64(params['weights'])
     if w.ndim == 2:
         out = np.zeros((w.shape[0], w.shape[1], w.shape[1]))
         ar = np.arange(w.shape[1])
@@ -164,8 +170,8 @@ def propagate(triples_plus, val, W, X=None, bias=None, num_nodes=None, self_mask
     multiplied element-wise by the dropout mask before aggregation.
     """
     t = np.asarray(triples_plus, dtype=I64).reshape(-1, 3)
-    val = np.float64(val)
-    W = np.float64(W)
+    val = _f64(val)
+    W = _f64(W)
     N = num_nodes if num_nodes is not None else X.shape[0]
     O = W.shape[2]
     out = np.zeros((N, O))
@@ -175,12 +181,12 @@ def propagate(triples_plus, val, W, X=None, bias=None, num_nodes=None, self_mask
         if X is None:
             msg = W[r][o[m]]
         else:
-            msg = np.float64(X)[o[m]] @ W[r]
+            msg = _f64(X)[o[m]] @ W[r]
         if self_mask is not None and r == mask_rel:
-            msg = msg * np.float64(self_mask)[o[m]]
+            msg = msg * _f64(self_mask)[o[m]]
         np.add.at(out, s[m], msg * val[m, None])
     if bias is not None:
-        out = out + np.float64(bias)
+        out = out + _f64(bias)
     return out
 
 
@@ -192,9 +198,9 @@ def propagate_backward(triples_plus, val, W, G, X=None, self_mask=None, mask_rel
     Returns (gX or None, gW (R', I, O)).
     """
     t = np.asarray(triples_plus, dtype=I64).reshape(-1, 3)
-    val = np.float64(val)
-    W = np.float64(W)
-    G = np.float64(G)
+    val = _f64(val)
+    W = _f64(W)
+    G = _f64(G)
     s, p, o = t[:, 0], t[:, 1], t[:, 2]
     gW = np.zeros_like(W)
     gX = None if X is None else np.zeros((X.shape[0], W.shape[1]))
@@ -202,11 +208,11 @@ def propagate_backward(triples_plus, val, W, G, X=None, self_mask=None, mask_rel
         m = p == r
         g = G[s[m]] * val[m, None]
         if self_mask is not None and r == mask_rel:
-            g = g * np.float64(self_mask)[o[m]]
+            g = g * _f64(self_mask)[o[m]]
         if X is None:
             np.add.at(gW[r], o[m], g)
         else:
-            x = np.float64(X)[o[m]]
+            x = _f64(X)[o[m]]
             gW[r] += x.T @ g
             np.add.at(gX, o[m], g @ W[r].T)
     return gX, gW
@@ -216,8 +222,8 @@ def project_weight_grad(gW, params):
     """Map the dense gW (R', I, O) onto the parameters of each decomposition."""
     out = {}
     if 'bases' in params:
-        out['comps'] = np.einsum('rio,bio->rb', gW, np.float64(params['bases']))
-        out['bases'] = np.einsum('rb,rio->bio', np.float64(params['comps']), gW)
+        out['comps'] = np.einsum('rio,bio->rb', gW, _f64(params['bases']))
+        out['bases'] = np.einsum('rb,rio->bio', _f64(params['comps']), gW)
     elif 'blocks' in params:
         r, nb, bi, bo = params['blocks'].shape
         gb = np.zeros((r, nb, bi, bo))
@@ -250,7 +256,7 @@ def nc_layer(triples_plus, num_nodes, num_rels, params, X=None, vertical_stackin
     gX, gW = propagate_backward(triples_plus, val, W, G, X)
     grads = project_weight_grad(gW, params)
     if params.get('bias') is not None:
-        grads['bias'] = np.float64(G).sum(0)
+        grads['bias'] = _f64(G).sum(0)
     grads['features'] = gX
     return out, grads
 
@@ -273,6 +279,6 @@ def lp_layer(triples, num_nodes, num_rels_total, params, X, vertical_stacking=Fa
     gX, gW = propagate_backward(tp, val, W, G, X, self_mask, num_rels_total - 1)
     grads = project_weight_grad(gW, params)
     if params.get('bias') is not None:
-        grads['bias'] = np.float64(G).sum(0)
+        grads['bias'] = _f64(G).sum(0)
     grads['features'] = gX
     return out, grads
