@@ -101,3 +101,79 @@ def test_lp_oracle_matches_live_reference(seed):
     np.testing.assert_allclose(og['features'], x.grad.numpy(), atol=3e-5, rtol=1e-4)
     for n, p in layer.named_parameters():
         np.testing.assert_allclose(og[n], p.grad.numpy(), atol=3e-5, rtol=1e-4, err_msg=n)
+
+
+# ---- decoder, ranking evaluation --------------------------------------------------------------------------------
+def _stub_sacred():
+    import types
+    for m in ('sacred', 'sacred.observers'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['sacred'].Experiment = object
+    sys.modules['sacred.observers'].MongoObserver = object
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_distmult_oracle_matches_live_reference(seed):
+    from oracle import distmult_oracle as dm
+    layers, _ = _ref()
+    rng = np.random.default_rng(300 + seed)
+    N, R, d, B = int(rng.integers(3, 40)), int(rng.integers(1, 6)), int(rng.integers(1, 20)), int(rng.integers(1, 80))
+    bias = seed % 2 == 1
+    torch.manual_seed(seed)
+    dec = layers.DistMult(R, d, N, R, b_init='normal' if bias else None)
+    t = torch.as_tensor(_triples(rng, N, R, B))
+    if seed % 3 == 2:
+        t = t.reshape(B, 1, 3).expand(B, 2, 3).contiguous()          # the (batch, negatives, 3) form
+    x = torch.randn(N, d, requires_grad=True)
+    out = dec(t, x)
+    G = torch.randn(out.shape)
+    pen = dec.s_penalty(t, x)
+    ((out * G).sum() + 0.7 * pen).backward()
+    p = {n: q.detach().numpy() for n, q in dec.named_parameters()}
+    b = [p.get(k) for k in ('sbias', 'pbias', 'obias')]
+    np.testing.assert_allclose(dm.score(t.numpy(), x.detach().numpy(), p['relations'], *b), out.detach().numpy(),
+                               atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(dm.penalty(t.numpy(), x.detach().numpy(), p['relations']), pen.item(), rtol=1e-6)
+    g = dm.score_backward(t.numpy(), x.detach().numpy(), p['relations'], G.numpy(), with_bias=bias)
+    pg = dm.penalty_backward(t.numpy(), x.detach().numpy(), p['relations'], 0.7)
+    np.testing.assert_allclose(g['nodes'] + pg['nodes'], x.grad.numpy(), atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(g['relations'] + pg['relations'], dec.relations.grad.numpy(), atol=1e-5, rtol=1e-4)
+    if bias:
+        for k in ('sbias', 'pbias', 'obias'):
+            np.testing.assert_allclose(g[k], getattr(dec, k).grad.numpy(), atol=1e-5, rtol=1e-4, err_msg=k)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_ranking_oracle_matches_live_reference(seed):
+    """Integer-valued embeddings: scores are exact in fp32, so ranks and ties must agree exactly."""
+    from oracle import ranking_oracle as ro
+    layers, _ = _ref()
+    _stub_sacred()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from utils.misc import evaluate, generate_true_dict
+    rng = np.random.default_rng(700 + seed)
+    N, R, d = int(rng.integers(10, 60)), int(rng.integers(1, 5)), int(rng.integers(2, 10))
+    known = _triples(rng, N, R, int(rng.integers(20, 150)))
+    known[: len(known) // 3, 1:] = known[0, 1:]                  # many heads for one (p, o)
+    test = known[rng.permutation(len(known))[: max(4, len(known) // 4)]]
+    bias = seed % 2 == 1
+    dec = layers.DistMult(R, d, N, R, b_init='normal' if bias else None)
+    x = torch.as_tensor(rng.integers(-2, 3, (N, d))).float()
+    with torch.no_grad():
+        dec.relations.copy_(torch.as_tensor(rng.integers(-2, 3, (R, d))).float())
+        if bias:
+            for b in (dec.sbias, dec.pbias, dec.obias):
+                b.copy_(torch.as_tensor(rng.integers(-3, 4, tuple(b.shape))).float())
+    p = {n: q.detach().numpy() for n, q in dec.named_parameters()}
+    b = {k: p.get(k) for k in ('sbias', 'pbias', 'obias')}
+    model = lambda graph, triples: (dec(triples, x), None)              # noqa: E731
+    true = generate_true_dict(known.tolist())
+    for filt in (True, False):
+        with torch.no_grad():
+            # one batch over the whole test set: filter_scores raises on a batch with nothing to filter (utils/misc.py:56-58)
+            mrr, hits, ranks = evaluate(model, None, torch.as_tensor(test), true, N, batch_size=len(test),
+                                        filter_candidates=filt, verbose=False)
+        got = ro.ranks(test, x.numpy(), p['relations'], known if filt else None, **b)
+        assert got == [int(r) for r in ranks], ('filtered' if filt else 'raw')
+        np.testing.assert_allclose(ro.metrics(got)[0], mrr, rtol=1e-12)
