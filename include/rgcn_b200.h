@@ -31,14 +31,16 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 11
+#define RGCN_ABI_VERSION 12
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
 #define RGCN_MAX_RING_DEPTH 64        /* upper bound on rgcn_graph.ring_depth */
 #define RGCN_LONG_ROW 512             /* rows with more edges are listed in d_long / s_long and processed cooperatively */
 #define RGCN_FUSE_TILE 16             /* entries per MMA tile of the fused row-block lists (one relation per tile) */
-#define RGCN_FUSE_MAX_ITEM_TILES 512  /* upper bound on rgcn_graph.fuse_item_tiles */
+#define RGCN_FUSE_REC_WORDS 36        /* int32 words per tile record of rgcn_fused.rec (144 bytes) */
+#define RGCN_FUSE_AHEAD 8             /* a tile record names the relation of the tile this many places later */
+#define RGCN_FUSE_MAX_ITEM_TILES (1 << 20)  /* upper bound on rgcn_graph.fuse_item_tiles */
 
 typedef void* rgcn_stream_t;
 
@@ -138,21 +140,25 @@ typedef struct rgcn_tile_item {
 
 /* Optional fused row-block lists (bf16 features, four 16x16 blocks): rows are cut into blocks of `fuse_rows`
  * consecutive rows whose fp32 output tile lives in shared memory; the edges of a block are sorted by
- * (relation, row) and every (block, relation) run is padded to whole 16-entry tiles, so that one MMA tile never
- * mixes relations.  Blocks with more than fuse_item_tiles tiles are split into several work items, which then
- * add their partial tiles into the output with atomics ("shared" items). */
+ * (relation, row parity, row) and every (block, relation) run is dealt over whole 16-entry tiles, so that one MMA
+ * tile never mixes relations.  Tiles are numbered block by block; a block with more than fuse_item_tiles tiles is
+ * split into several work items, which then add their partial sums into the output with atomics ("shared"
+ * items).  Work items are consecutive in tile order: item q covers tiles [items[4q+1], items[4q+2]). */
 typedef struct rgcn_fused {
-    int32_t* col;           /* cap: row of the gathered matrix, -1 = padding */
-    int32_t* rv;            /* 2 x cap: per entry {row - first row of its block, bits of the fp32 edge weight};
-                               padding is {0, 0} */
-    int32_t* tile_rel;      /* cap / 16: relation of every tile; bit 31 set if two entries that the kernel would add
-                               in the same step (slots 0-7, then slots 8-15) share a row: the kernel then adds the
-                               tile's entries one at a time */
+    int32_t* col;           /* cap: row of the gathered matrix per entry (tile * 16 + slot), -1 = padding */
+    int32_t* rec;           /* cap / 16 tile records of RGCN_FUSE_REC_WORDS words, streamed to shared memory as they
+                               are.  Slot s of a tile: word 4 (s % 8) + 2 (s / 8) = byte offset of the entry's row
+                               in the block's accumulators, 256 * local row + 64 * (local row & 1), plus (low 4 bits)
+                               the entry's rank among the entries of the same row in this tile; next word = bits of
+                               the fp32 edge weight, 0 = padding.  Word 32: relation of the tile RGCN_FUSE_AHEAD
+                               places later | (largest rank in this tile) << 24 (non-zero: entries share rows and
+                               the kernel adds them rank by rank).  Word 33: relation of this tile.  Word 34:
+                               largest rank. */
     int32_t* blk_tile;      /* NB + 1: first tile of every row block, NB = ceil(N / fuse_rows) */
     int32_t* items;         /* 4 x int32 per work item {block, first tile, end tile, shared};
                                capacity rgcn_fused_items_bound() */
-    int32_t* meta;          /* 4 x int32: [0] work items, [1] tiles, [2] 1 if the tiles do not fit cap (list unusable),
-                               [3] row blocks that were split */
+    int32_t* meta;          /* 8 x int32: [0] work items, [1] tiles, [2] 1 if the tiles do not fit cap (list unusable),
+                               [3] row blocks that were split, [4] tiles in which entries share a row */
 } rgcn_fused;
 
 typedef struct rgcn_graph {
@@ -194,15 +200,11 @@ typedef struct rgcn_graph {
     rgcn_tiling bt;         /* backward tiling (source rows) */
     int64_t fuse_rows;      /* 0: no fused row-block lists (ff / fb unused); else rows per block (multiple of 16) */
     int64_t fuse_cap;       /* entries allocated per list (multiple of 16) */
-    int64_t fuse_item_tiles;/* tiles per work item, 1 .. RGCN_FUSE_MAX_ITEM_TILES */
-    int64_t fuse_order;     /* placement of a run's edges in its tiles.  0: in row order.  1: sorted by (row % 4, row),
-                               dealt round-robin over the run's tiles, consecutive edges alternating between the
-                               two halves of a tile, so that edges with the same row are added in different steps
-                               and the four rows one shared-memory access phase touches fall into different
-                               bank groups (row % 4) whenever the run has them */
+    int64_t fuse_item_tiles;/* largest work item in tiles, 1 .. RGCN_FUSE_MAX_ITEM_TILES */
     int64_t fuse_items[2];  /* host copies of ff / fb meta[0] filled by the caller after the build;
                                0 = list unusable (overflow or not read back): the kernels fall back */
     int64_t fuse_split[2];  /* host copies of ff / fb meta[3] */
+    int64_t fuse_tiles[2];  /* host copies of ff / fb meta[1] */
     rgcn_fused ff;          /* forward lists (blocks of destination rows, gathers X[o]) */
     rgcn_fused fb;          /* backward lists (blocks of source rows, gathers grad_out[s]) */
 } rgcn_graph;

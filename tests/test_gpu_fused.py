@@ -10,14 +10,13 @@ import pytest
 import torch
 
 from oracle import rgcn_oracle as orc
-from fused_ref import expected_lists as _expected_lists
+from fused_ref import expected_lists as _expected_lists, records as _records
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('order', [0, 1])
-@pytest.mark.parametrize('FR,item_tiles,skew', [(64, 512, False), (512, 512, False), (32, 3, True)])
-def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew, order):
+@pytest.mark.parametrize('FR,item_tiles,skew', [(64, 4096, False), (512, 4096, False), (32, 3, True)])
+def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew):
     from torch_rgcn_b200 import _lib
     from torch_rgcn_b200.graph import GraphPlan
     from torch_rgcn_b200.synthetic import random_triples
@@ -25,27 +24,24 @@ def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew, order):
     t = random_triples(N, R, E, seed=11, rel_dist='zipf' if skew else 'uniform', node_skew=skew)
     tp = orc.add_inverse_and_self(t.numpy(), N, R)
     Rp = 2 * R + 1
-    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles,
-                     fuse_order=order)
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles)
     val = plan.val[:plan.nnz].cpu().numpy()
     for d in (0, 1):
-        exp = _expected_lists(tp, N, Rp, val, FR, item_tiles, backward=bool(d), order=order)
+        exp = _expected_lists(tp, N, Rp, val, FR, item_tiles, backward=bool(d))
         arrs = {k: v.cpu().numpy() for k, v in plan._fused[d].items()}
-        n_items, tiles, overflow, split = arrs['meta'].tolist()
+        n_items, tiles, overflow, split, flagged = arrs['meta'].tolist()[:5]
         assert overflow == 0 and plan.fused_ok[d]
         assert tiles == exp['total'], (d, tiles, exp['total'])
         n = tiles * 16
         np.testing.assert_array_equal(arrs['col'][:n], exp['col'], err_msg=f'col d={d}')
-        np.testing.assert_array_equal(arrs['rv'][:n, 0], exp['row'], err_msg=f'row d={d}')
-        np.testing.assert_array_equal(np.ascontiguousarray(arrs['rv'][:n, 1]).view(np.float32), exp['val'], err_msg=f'val d={d}')
-        np.testing.assert_array_equal(arrs['tile_rel'][:tiles] & 0x7fffffff, exp['tile_rel'], err_msg=f'tile_rel d={d}')
-        np.testing.assert_array_equal(arrs['tile_rel'][:tiles] < 0, exp['serial'], err_msg=f'serial flags d={d}')
+        np.testing.assert_array_equal(arrs['rec'][:tiles], _records(exp), err_msg=f'rec d={d}')
+        assert flagged == int(exp['serial'].sum())
         np.testing.assert_array_equal(arrs['blk_tile'], exp['blk_tile'], err_msg=f'blk_tile d={d}')
         assert n_items == len(exp['items']), (d, n_items, len(exp['items']))
         np.testing.assert_array_equal(arrs['items'][:n_items], exp['items'], err_msg=f'items d={d}')
         assert split == exp['split']
-        assert np.all(arrs['col'][n:] == -1) and np.all(arrs['rv'][n:] == 0)       # untouched padding
-        assert plan.c.fuse_items[d] == n_items and plan.c.fuse_split[d] == split
+        assert np.all(arrs['col'][n:] == -1) and np.all(arrs['rec'][tiles:] == 0)       # untouched padding
+        assert plan.c.fuse_items[d] == n_items and plan.c.fuse_split[d] == split and plan.c.fuse_tiles[d] == tiles
 
 
 def _params_np(layer):
@@ -64,13 +60,13 @@ def _graph(kind, N, R, E):
     return t
 
 
-def _run(cuda_device, monkeypatch, fused, N, R, t, vertical, grads, fuse_rows='512', item_tiles='512', seed=8, order='1'):
+def _run(cuda_device, monkeypatch, fused, N, R, t, vertical, grads, fuse_rows='512', item_tiles='4096', seed=8, tma='gather4'):
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
     monkeypatch.setenv('RGCN_FUSED', '1' if fused else '0')
     monkeypatch.setenv('RGCN_FUSE_ROWS', fuse_rows)
     monkeypatch.setenv('RGCN_FUSE_ITEM_TILES', item_tiles)
     monkeypatch.setenv('RGCN_TILE_MB', '0')
-    monkeypatch.setenv('RGCN_FUSE_ORDER', order)
+    monkeypatch.setenv('RGCN_FUSED_TMA', tma)
     tp = torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, R))
     torch.manual_seed(seed)
     layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=64,
@@ -105,14 +101,14 @@ def _close(got, ref, name, tol=1e-2):
 
 @pytest.mark.parametrize('kind,N,R,E', [('uniform', 3000, 9, 40000), ('hub', 3000, 9, 40000), ('multi', 1500, 4, 30000),
                                         ('uniform', 50, 2, 40)])
-@pytest.mark.parametrize('fuse_rows,item_tiles,order', [('512', '512', '1'), ('64', '512', '0'), ('128', '2', '1')])
+@pytest.mark.parametrize('fuse_rows,item_tiles', [('640', '4096'), ('64', '4096'), ('128', '2')])
 @pytest.mark.parametrize('grads', ['all', 'features_only'])
-def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows, item_tiles, order, grads):
+def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows, item_tiles, grads):
     """bf16 tolerance of the tensor-core paths: 1e-2 of the tensor's scale (features and MMA operands are bf16,
     products and sums fp32)."""
     t = _graph(kind, N, R, E)
     vertical = kind != 'hub'                       # hub graph also exercises the horizontal (permuted) weights
-    layer, tp, feats, out, G, plan = _run(cuda_device, monkeypatch, True, N, R, t, vertical, grads, fuse_rows, item_tiles, order=order)
+    layer, tp, feats, out, G, plan = _run(cuda_device, monkeypatch, True, N, R, t, vertical, grads, fuse_rows, item_tiles)
     if item_tiles == '2' and E > 1000:
         assert plan.c.fuse_split[0] > 0 and plan.c.fuse_split[1] > 0, 'expected split row blocks'
     ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().float().cpu().numpy(),
@@ -123,6 +119,21 @@ def test_fused_matches_oracle(cuda_device, monkeypatch, kind, N, R, E, fuse_rows
     if grads == 'all':
         _close(layer.blocks.grad.cpu().numpy(), ref_g['blocks'], 'blocks')
         np.testing.assert_allclose(layer.bias.grad.cpu().numpy(), ref_g['bias'], atol=1e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize('stages', ['2', '3', '4'])
+def test_fused_bulk_copy_variant_and_shallow_pipelines(cuda_device, monkeypatch, stages):
+    """The per-row cp.async.bulk build of the kernel and short pipelines (1 - 4 producer warps) give the same sums."""
+    N, R, E = 3000, 9, 40000
+    t = _graph('uniform', N, R, E)
+    monkeypatch.setenv('RGCN_FUSED_STAGES', stages)
+    la, tp, fa, out_a, G, _ = _run(cuda_device, monkeypatch, True, N, R, t, True, 'all', fuse_rows='256', tma='gather4')
+    lb, _, fb, out_b, _, _ = _run(cuda_device, monkeypatch, True, N, R, t, True, 'all', fuse_rows='256', tma='bulk')
+    assert torch.equal(out_a, out_b) and torch.equal(fa.grad, fb.grad)
+    ref_out, ref_g = orc.nc_layer(tp.numpy(), N, 2 * R + 1, _params_np(la), fa.detach().float().cpu().numpy(), True,
+                                  G.cpu().numpy())
+    _close(out_a.detach().cpu().numpy(), ref_out, 'out')
+    _close(fa.grad.float().cpu().numpy(), ref_g['features'], 'features')
 
 
 def test_fused_is_reproducible_and_agrees_with_two_phase(cuda_device, monkeypatch):

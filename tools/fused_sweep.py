@@ -1,5 +1,6 @@
-"""Time the am64 layer (forward / backward, CUDA events, L2 flushed between steps) for a list of
-RGCN_FUSED / RGCN_FUSE_ROWS settings.  Usage: python tools/fused_sweep.py [0 512 384 256 ...] (0 = two-phase)."""
+"""Time the am64 layer (forward / backward, CUDA events, L2 flushed between steps) for a list of fused-kernel
+settings.  Usage: python tools/fused_sweep.py [0 640 512/s4 320/c2 640/bulk ...]
+  0 = two-phase kernels; ROWS[/sSTAGES][/cCTAS_PER_SM][/bulk] = fused row-block kernel."""
 import os
 import sys
 
@@ -26,9 +27,19 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
     for s in settings:
-        os.environ['RGCN_FUSED'] = '0' if s == '0' else '1'
-        if s != '0':
-            os.environ['RGCN_FUSE_ROWS'] = s
+        parts = s.split('/')
+        os.environ['RGCN_FUSED'] = '0' if parts[0] == '0' else '1'
+        for k in ('RGCN_FUSED_STAGES', 'RGCN_FUSED_CTAS', 'RGCN_FUSED_TMA'):
+            os.environ.pop(k, None)
+        if parts[0] != '0':
+            os.environ['RGCN_FUSE_ROWS'] = parts[0]
+        for q in parts[1:]:
+            if q == 'bulk':
+                os.environ['RGCN_FUSED_TMA'] = 'bulk'
+            elif q[0] == 's':
+                os.environ['RGCN_FUSED_STAGES'] = q[1:]
+            elif q[0] == 'c':
+                os.environ['RGCN_FUSED_CTAS'] = q[1:]
         torch.manual_seed(2)
         layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=2 * R + 1, in_features=64,
                                              out_features=64, decomposition={'type': 'block', 'num_blocks': 4}).to(dev)
@@ -51,7 +62,7 @@ def main():
         info = ''
         if plan.fuse_rows:
             metas = [a['meta'].tolist() for a in plan._fused]
-            info = f' fused_ok={plan.fused_ok} meta(items,tiles,overflow,split)={metas} fill={plan.nnz / (16.0 * metas[0][1]):.3f}'
+            info = f' fused_ok={plan.fused_ok} meta(items,tiles,overflow,split,flagged)={[m[:5] for m in metas]} fill={plan.nnz / (16.0 * metas[0][1]):.3f}'
         if ref is None:
             ref = (out.detach().clone(), x.grad.detach().float().clone())
             diff = ''

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call B: optimised fused row-block kernel: parity tests, A/B sweep, L2 reduction probe, one full ncu capture
+cd "$(dirname "$0")/.."
+O=gpurun_out; mkdir -p $O
+echo "== fused tests"; timeout 900 python -m pytest tests/test_gpu_fused.py -q -x 2>&1 | tail -5 | tee $O/r2b_test_fused.log
+echo "== sweep"; timeout 900 python tools/fused_sweep.py 0 640 624/s8 512 320/c2 288/c2 352/c2 2>&1 | tail -12 | tee $O/r2b_sweep.log
+echo "== probe"; timeout 120 tools/probes/l2_red_probe 2>&1 | tee $O/r2b_l2_red_probe.log
+echo "== ncu"
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_rowblock -s 2 -c 1 -f -o $O/r2b_rowblock_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/r2b_ncu_full.log 2>&1
+timeout 120 ncu -i $O/r2b_rowblock_full.ncu-rep --page raw --csv > $O/r2b_rowblock_full_raw.csv 2>/dev/null
+timeout 120 ncu -i $O/r2b_rowblock_full.ncu-rep --page source --csv > $O/r2b_rowblock_full_source.csv 2>/dev/null
+rm -f $O/r2b_rowblock_full.ncu-rep
+ls -la $O | tail -8

@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 NORM_ROW, NORM_COL_SWAPPED, NORM_EXPLICIT = 0, 1, 2
 W_DENSE, W_BASIS, W_BLOCK, W_DIAG = 0, 1, 2, 3
 F32, BF16 = 0, 1
+FUSE_REC_WORDS = 36          # RGCN_FUSE_REC_WORDS
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -26,7 +27,7 @@ class Tiling(C.Structure):
 
 
 class Fused(C.Structure):
-    _fields_ = [('col', _p), ('rv', _p), ('tile_rel', _p), ('blk_tile', _p), ('items', _p), ('meta', _p)]
+    _fields_ = [('col', _p), ('rec', _p), ('blk_tile', _p), ('items', _p), ('meta', _p)]
 
 
 class Graph(C.Structure):
@@ -38,8 +39,8 @@ class Graph(C.Structure):
                 ('val', _p), ('status', _p), ('d_long', _p), ('s_long', _p), ('num_long_dst', _i64), ('num_long_src', _i64),
                 ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ring_depth', _i64),
                 ('ft', Tiling), ('bt', Tiling),
-                ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64), ('fuse_order', _i64),
-                ('fuse_items', _i64 * 2), ('fuse_split', _i64 * 2), ('ff', Fused), ('fb', Fused)]
+                ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64),
+                ('fuse_items', _i64 * 2), ('fuse_split', _i64 * 2), ('fuse_tiles', _i64 * 2), ('ff', Fused), ('fb', Fused)]
 
 
 class Params(C.Structure):

@@ -342,20 +342,20 @@ __global__ void k_fill_items(const int32_t* __restrict__ stepptr, const int32_t*
 }
 
 // ---- fused row-block lists (rgcn_fused) ----------------------------------------------------------------
-// key = ((block * R' + p) * 4 + c) * N + a,  a = block-side endpoint, block = a / fuse_rows,
-// c = a % 4 (bank group of the row's slice in the shared-memory tile) for fuse_order 1, else 0
+// key = ((block * R' + p) * 2 + (a & 1)) * N + a,  a = block-side endpoint, block = a / fuse_rows: a (block, relation)
+// run lists its even rows first, then its odd rows
 __global__ void k_make_block_keys(const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
-                                  int64_t fuse_rows, int order, uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+                                  int64_t fuse_rows, uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     int64_t s = t[3 * e], p = t[3 * e + 1], o = t[3 * e + 2];
     if (s < 0 || s >= N || o < 0 || o >= N || p < 0 || p >= Rp) s = p = o = 0;
     const int64_t a = backward ? o : s;
-    keys[e] = (((uint64_t)(a / fuse_rows) * Rp + p) * 4 + (order ? (a & 3) : 0)) * N + a;
+    keys[e] = (((uint64_t)(a / fuse_rows) * Rp + p) * 2 + (uint64_t)(a & 1)) * N + a;
     idx[e] = (int32_t)e;
 }
 
-// cnt[g] = 16-entry tiles of run g (runs = segments of equal key / N), 0 beyond the last run
+// cnt[g] = 16-entry tiles of run g (runs = segments of equal key / (2 N)), 0 beyond the last run
 __global__ void k_fused_run_tiles(int64_t nnz, const int32_t* __restrict__ segid, const int32_t* __restrict__ starts,
                                   const int32_t* __restrict__ ends, int32_t* __restrict__ cnt) {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -363,53 +363,57 @@ __global__ void k_fused_run_tiles(int64_t nnz, const int32_t* __restrict__ segid
     cnt[g] = g < segid[nnz - 1] ? (ends[g] - starts[g] + RGCN_FUSE_TILE - 1) / RGCN_FUSE_TILE : 0;
 }
 
-// Sorted edge e is edge i = e - starts[g] of run g, which owns tiles tbase[g] .. tbase[g] + cnt[g] - 1:
-//   order 0: tile i / 16, slot i % 16;
-//   order 1: tile i % cnt[g]; the tile's w-th edge (w = i / cnt[g]) takes slot 8 (w & 1) + 4 (w >> 1 & 1) + (w >> 2):
-//            odd / even w alternate between the two halves of the tile (two edges with the same row are
-//            neighbours in w, so they are added in different steps), and each group of four consecutive
-//            slots holds w, w + 4, w + 8, w + 12, i.e. one row of every bank group when the run has them.
-// A tile in which two edges with the same row would be added in the same step is flagged (bit 31 of tile_rel):
-// order 0: any pair inside the tile; order 1: a pair inside one half, i.e. a row with three or more edges.  The first edge of a
-// run also labels the run's tiles and, for the first run of a row block, the block's first tile.
+// Sorted edge e is edge i = e - starts[g] of run g (n edges), which owns tiles tbase[g] .. tbase[g] + cnt[g] - 1.
+// The run is dealt round-robin over its tiles: tile i % cnt[g], where it is the tile's w-th entry (w = i / cnt[g]) of
+// m = ceil((n - tile) / cnt[g]).  Entries w < h = ceil(m / 2) take the even slots 2 w, the others the odd slots
+// 2 (w - h) + 1: the slot pairs (2 q, 2 q + 1) that one shared-memory access phase of the kernel touches then hold
+// an even and an odd row whenever the run has them (the row's parity picks the bank half of its accumulators), and
+// the tile's entries fill slots 0 .. m - 1.  Record layout of a tile (RGCN_FUSE_REC_WORDS int32):
+//   word 4 (s % 8) + 2 (s / 8)     = accumulator offset of slot s: 256 * local row + 64 * (local row & 1), plus the
+//                                    entry's rank among the entries of the same row in this tile (0 .. 15)
+//   word 4 (s % 8) + 2 (s / 8) + 1 = bits of the fp32 edge weight (0 = padding)
+//   word 32 = relation of tile + RGCN_FUSE_AHEAD | (largest rank in the tile) << 24 (k_fused_headers)
+//   word 33 = relation of the tile, word 34 = largest rank in the tile, word 35 = 0
+// The first edge of a run also labels the run's tiles and, for the first run of a row block, the block's first tile.
 __global__ void k_fused_scatter(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
                                 const int64_t* __restrict__ t, int64_t nnz, int64_t N, int64_t Rp, int backward,
-                                int64_t fuse_rows, int order, int64_t NB, const int32_t* __restrict__ segid,
-                                const int32_t* __restrict__ starts, const int32_t* __restrict__ tbase,
-                                const int32_t* __restrict__ cnt, const float* __restrict__ val, int64_t cap,
-                                int32_t* __restrict__ col, int32_t* __restrict__ rv, int32_t* __restrict__ tile_rel,
-                                int32_t* __restrict__ blk_tile, int32_t* __restrict__ meta) {
+                                int64_t fuse_rows, int64_t NB, const int32_t* __restrict__ segid,
+                                const int32_t* __restrict__ starts, const int32_t* __restrict__ ends,
+                                const int32_t* __restrict__ tbase, const int32_t* __restrict__ cnt,
+                                const float* __restrict__ val, int64_t cap, int32_t* __restrict__ col,
+                                int32_t* __restrict__ rec, int32_t* __restrict__ blk_tile, int32_t* __restrict__ meta) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     const uint64_t k = keys[e];
     const int64_t a = (int64_t)(k % N);
-    const uint64_t grp = k / N / 4;
+    const uint64_t grp = k / N / 2;
     const int64_t p = (int64_t)(grp % Rp), blk = (int64_t)(grp / Rp);
     const int32_t g = segid[e] - 1;
     const int32_t orig = perm[e];
     int64_t s = t[3 * (int64_t)orig], pp = t[3 * (int64_t)orig + 1], o = t[3 * (int64_t)orig + 2];
     if (s < 0 || s >= N || o < 0 || o >= N || pp < 0 || pp >= Rp) s = o = 0;
-    const int64_t first_tile = tbase[g], ntile = cnt[g];
+    const int64_t first_tile = tbase[g], ntile = cnt[g], n = ends[g] - starts[g];
     const int64_t i = e - starts[g];
-    int64_t tile_i, slot, twin;                      // twin: nearest earlier edge of the run that shares the tile
-    if (order) {
-        tile_i = i % ntile; twin = 2 * ntile;
-        const int64_t w = i / ntile;
-        slot = (w & 1) * 8 + ((w >> 1) & 1) * 4 + (w >> 2);
-    } else {
-        tile_i = i / RGCN_FUSE_TILE; slot = i % RGCN_FUSE_TILE; twin = slot ? 1 : 0;
-    }
-    const int64_t pos = (first_tile + tile_i) * RGCN_FUSE_TILE + slot;
-    if (pos < cap) {
-        col[pos] = (int32_t)(backward ? s : o);
-        rv[2 * pos] = (int32_t)(a - blk * fuse_rows);
-        rv[2 * pos + 1] = __float_as_int(val[orig]);
-        // equal rows of a run are neighbours in the sorted list, so one look-back finds any pair inside a tile
-        if (twin && i >= twin && (int64_t)(keys[e - twin] % N) == a) atomicOr(tile_rel + first_tile + tile_i, (int)0x80000000);
+    const int64_t tile_i = i % ntile, w = i / ntile;
+    const int64_t m = (n - tile_i + ntile - 1) / ntile, h = (m + 1) / 2;
+    const int64_t slot = w < h ? 2 * w : 2 * (w - h) + 1;
+    const int64_t tile = first_tile + tile_i;
+    if ((tile + 1) * RGCN_FUSE_TILE <= cap) {
+        col[tile * RGCN_FUSE_TILE + slot] = (int32_t)(backward ? s : o);
+        const int64_t rloc = a - blk * fuse_rows;
+        int32_t* r = rec + tile * RGCN_FUSE_REC_WORDS + 4 * (slot & 7) + 2 * (slot >> 3);
+        // equal rows of a run are neighbours in the sorted list and land in the same tile every ntile places: the entry's
+        // rank among the entries of its row in this tile (a tile has 16 slots, so at most 15)
+        int rank = 0;
+        while (rank < 15 && i >= (rank + 1) * ntile && (int64_t)(keys[e - (rank + 1) * ntile] % N) == a) ++rank;
+        r[0] = (int32_t)(rloc * 256 + (rloc & 1) * 64 + rank);
+        r[1] = __float_as_int(val[orig]);
+        if (rank) atomicMax(rec + tile * RGCN_FUSE_REC_WORDS + 34, rank);
     }
     if (e == starts[g]) {
-        for (int64_t q = first_tile; q < first_tile + ntile && q * RGCN_FUSE_TILE < cap; ++q) atomicOr(tile_rel + q, (int)p);
-        const int64_t prev = e ? (int64_t)(keys[e - 1] / N / 4 / Rp) : -1;    // block of the previous run
+        for (int64_t q = first_tile; q < first_tile + ntile && (q + 1) * RGCN_FUSE_TILE <= cap; ++q)
+            rec[q * RGCN_FUSE_REC_WORDS + 33] = (int32_t)p;
+        const int64_t prev = e ? (int64_t)(keys[e - 1] / N / 2 / Rp) : -1;    // block of the previous run
         for (int64_t b = prev + 1; b <= blk; ++b) blk_tile[b] = (int32_t)first_tile;
     }
     if (e == nnz - 1) {
@@ -418,6 +422,20 @@ __global__ void k_fused_scatter(const uint64_t* __restrict__ keys, const int32_t
         meta[1] = (int32_t)total;
         meta[2] = total * RGCN_FUSE_TILE > cap ? 1 : 0;
     }
+}
+
+// word 32 of every tile record: relation of the tile RGCN_FUSE_AHEAD places later (the kernel requests that tile's
+// weight fragments while it works on this one) and the largest rank of the tile (0 = all rows different);
+// meta[4] counts the tiles with shared rows
+__global__ void k_fused_headers(int32_t* __restrict__ rec, int64_t cap, int32_t* __restrict__ meta) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = meta[1];
+    if (q >= total || (q + 1) * RGCN_FUSE_TILE > cap) return;
+    int64_t ahead = q + RGCN_FUSE_AHEAD;
+    if (ahead >= total || (ahead + 1) * RGCN_FUSE_TILE > cap) ahead = q;
+    const int32_t maxrank = rec[q * RGCN_FUSE_REC_WORDS + 34];
+    rec[q * RGCN_FUSE_REC_WORDS + 32] = rec[ahead * RGCN_FUSE_REC_WORDS + 33] | (maxrank << 24);
+    if (maxrank) atomicAdd(meta + 4, 1);
 }
 
 __global__ void k_fused_item_counts(const int32_t* __restrict__ blk_tile, int64_t NB, int item_tiles,
@@ -720,34 +738,35 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
                      "rgcn_graph_build: fuse_cap must be a positive multiple of 16 that fits int32");
         RGCN_REQUIRE(item_tiles >= 1 && item_tiles <= RGCN_FUSE_MAX_ITEM_TILES, RGCN_ERR_ARG,
                      "rgcn_graph_build: fuse_item_tiles %d out of range", item_tiles);
-        const int order = g->fuse_order ? 1 : 0;
-        const unsigned __int128 fkey = (unsigned __int128)NB * (unsigned __int128)Rp * 4 * (unsigned __int128)N;
+        RGCN_REQUIRE(Rp < (1 << 24), RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: fused lists need fewer than 2^24 relations");
+        const unsigned __int128 fkey = (unsigned __int128)NB * (unsigned __int128)Rp * 2 * (unsigned __int128)N;
         RGCN_REQUIRE((fkey >> 63) == 0, RGCN_ERR_UNSUPPORTED, "rgcn_graph_build: row-block key does not fit 64 bits");
         const int fbits = bits_for(fkey);
         const int64_t bound = rgcn_fused_items_bound(N, FR, cap, item_tiles);
+        const int64_t cap_tiles = cap / RGCN_FUSE_TILE;
         for (int backward = 0; backward < 2; ++backward) {
             rgcn_fused& fl = backward ? g->fb : g->ff;
-            RGCN_REQUIRE(fl.col && fl.rv && fl.tile_rel && fl.blk_tile && fl.items && fl.meta, RGCN_ERR_ARG,
+            RGCN_REQUIRE(fl.col && fl.rec && fl.blk_tile && fl.items && fl.meta, RGCN_ERR_ARG,
                          "rgcn_graph_build: NULL fused list array");
-            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.meta, 0, 4 * sizeof(int32_t), stream));
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.meta, 0, 8 * sizeof(int32_t), stream));
             RGCN_CHECK_CUDA(cudaMemsetAsync(fl.col, 0xFF, (size_t)cap * sizeof(int32_t), stream));
-            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.rv, 0, (size_t)cap * 2 * sizeof(int32_t), stream));
-            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.tile_rel, 0, (size_t)(cap / RGCN_FUSE_TILE) * sizeof(int32_t), stream));
-            RGCN_LAUNCH(k_make_block_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, FR, order, b.k0, b.i0);
+            RGCN_CHECK_CUDA(cudaMemsetAsync(fl.rec, 0, (size_t)cap_tiles * RGCN_FUSE_REC_WORDS * sizeof(int32_t), stream));
+            RGCN_LAUNCH(k_make_block_keys, grid, kBlock, 0, stream, triples, nnz, N, Rp, backward, FR, b.k0, b.i0);
             size_t cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.cub, cub_bytes, b.k0, b.k1, b.i0, b.i1, (int)nnz, 0, fbits, stream));
             rgcn::g_launches.fetch_add((fbits + 7) / 8 + 1, std::memory_order_relaxed);
-            // runs = (block, relation) segments of the sorted list: equal key / (4 N)
-            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, -1, b.flag);
+            // runs = (block, relation) segments of the sorted list: equal key / (2 N)
+            RGCN_LAUNCH(k_seg_flags, grid, kBlock, 0, stream, b.k1, nnz, 2 * N, -1, b.flag);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(b.cub, cub_bytes, b.flag, b.segid, (int)nnz, stream));
-            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, 4 * N, -1, b.segid, b.starts, b.ends);
+            RGCN_LAUNCH(k_seg_bounds, grid, kBlock, 0, stream, b.k1, nnz, 2 * N, -1, b.segid, b.starts, b.ends);
             RGCN_LAUNCH(k_fused_run_tiles, grid, kBlock, 0, stream, nnz, b.segid, b.starts, b.ends, b.cnt);
             cub_bytes = b.cub_bytes;
             RGCN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(b.cub, cub_bytes, b.cnt, b.inv_d, (int)nnz, stream));
             rgcn::g_launches.fetch_add(2, std::memory_order_relaxed);
-            RGCN_LAUNCH(k_fused_scatter, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, FR, order, NB,
-                        b.segid, b.starts, b.inv_d, b.cnt, g->val, cap, fl.col, fl.rv, fl.tile_rel, fl.blk_tile, fl.meta);
+            RGCN_LAUNCH(k_fused_scatter, grid, kBlock, 0, stream, b.k1, b.i1, triples, nnz, N, Rp, backward, FR, NB,
+                        b.segid, b.starts, b.ends, b.inv_d, b.cnt, g->val, cap, fl.col, fl.rec, fl.blk_tile, fl.meta);
+            RGCN_LAUNCH(k_fused_headers, grid_for(cap_tiles, kBlock), kBlock, 0, stream, fl.rec, cap, fl.meta);
             // work items: every row block, split into pieces of at most item_tiles tiles
             RGCN_LAUNCH(k_fused_item_counts, grid_for(NB + 1, kBlock), kBlock, 0, stream, fl.blk_tile, NB, item_tiles, b.flag);
             cub_bytes = b.cub_bytes;

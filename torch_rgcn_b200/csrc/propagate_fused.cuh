@@ -1,71 +1,176 @@
-// Fused row-block kernel for bf16 features and four 16x16 weight blocks (64 -> 64, the AM-shaped layer).
+// Fused row-block kernel for bf16 features and four 16x16 weight blocks (64 -> 64, the AM-shaped layer):
+// ONE pass over the edges, no per-edge message ever leaves the SM.
 //
 // The two-phase kernels of propagate_mma.cuh write one bf16 message per edge to HBM and read it back in the row
 // sum: 256 B per edge of round trip on top of the 128 B gather.  Here a CTA owns a block of `fuse_rows`
-// consecutive output rows and keeps their fp32 sums in shared memory, so an edge costs its gather and nothing
-// else:
+// consecutive output rows and keeps their fp32 sums in shared memory, so an edge costs its gather and nothing else.
 //
-//   work item  = (row block, range of 16-entry tiles) from the plan's rgcn_fused list: the block's edges sorted by
-//                (relation, row), every (block, relation) run padded to whole tiles -> one relation per MMA tile
-//   pipeline   = 64-entry stages (4 tiles): the gathered rows (64 x 128 B, XOR-swizzled like propagate_mma.cuh) and
-//                the {row, val} records land through cp.async, kFuAhead stages in flight; the gather indices and
-//                the weight slices are requested equally early into register rings (see the note in the kernel)
-//   ownership  = warp w owns output columns [8w, 8w + 8): per tile it runs ONE mma.sync.m16n8k16 (A = the 16
-//                inputs of block w / 2 of the 16 gathered rows, B = its 16 x 8 weight slice, prefetched from the
-//                packed table one stage ahead) and adds val * result into its private column slice of the
-//                shared-memory tile.  No two warps ever touch the same address, so the accumulation needs no
-//                atomics and its order is fixed by the plan: results are run-to-run deterministic.
-//   duplicates = tiles in which two entries share a row (a (row, relation) segment longer than one edge) are
-//                flagged by the plan (bit 31 of tile_rel) and accumulated one entry at a time
-//   banks      = a row's 32-byte slice sits in bank group row % 4; with fuse_order 1 the plan places a run's
-//                edges so that the four rows of one access phase come from different groups when possible
-//   flush      = out[row] = bias + sum, 256-byte coalesced rows (fp32, or bf16 for a bf16 feature gradient); items
-//                of a split (hub) block add into rows pre-set by k_fused_init_shared with fp32 atomics
+//   lists      = rgcn_fused of the plan: the block's edges sorted by (relation, row parity, row), every
+//                (block, relation) run dealt over whole 16-entry tiles -> one relation per MMA tile.  Tiles are
+//                numbered block by block, so a CTA streams ONE contiguous range of tiles (a static, tile-balanced
+//                cut of the work items) and switches accumulators when the tile index crosses an item boundary.
+//   producers  = warps 8-11.  Per stage of 4 tiles: the 64 gathered rows arrive through TMA
+//                (cp.async.bulk.tensor.2d tile::gather4, 128-byte swizzle, one instruction per four rows) or, in the
+//                fallback build, through one cp.async.bulk per row; the stage's 4 tile records (576 B, row offsets,
+//                edge weights, relation of the tile 8 places ahead) through one cp.async.bulk.  Everything
+//                completes on the stage's "full" mbarrier; a stage is refilled when the four consumer warps that
+//                read it have arrived on its "empty" mbarrier.  No thread ever computes a per-lane gather address.
+//   consumers  = warps 0-7 = 4 column blocks x 2.  The pair (b, 0), (b, 1) owns weight block b = output columns
+//                [16 b, 16 b + 16) and takes the stages in turn.  A stage has two phases:
+//                  front: per tile one ldmatrix.x4 (the 16 inputs of block b of the 16 gathered rows), two
+//                         mma.sync.m16n8k16 against register-resident B fragments, the tile record; afterwards the
+//                         stage's slot holds nothing the warp still needs and goes back to the producers;
+//                  back : for the two rows a lane holds, a 16-byte read-modify-write of the fp32 accumulators:
+//                         acc[row][4 t .. 4 t + 3] += val * product (the B fragments are packed with permuted columns
+//                         so that a lane's four values are consecutive).
+//                While one warp of the pair runs back(s), the other runs front(s + 1); a 64-thread named barrier per
+//                stage hands the accumulators over, so the read-modify-write chains of a column block stay serial (a
+//                row that two tiles share is updated correctly) while every load / MMA latency hides behind them.
+//                Column blocks are disjoint, so the accumulation needs no atomics and its order is fixed by the
+//                plan: results are run-to-run deterministic on unsplit blocks.
+//   weights    = the fragments of the tile RGCN_FUSE_AHEAD places ahead (the warp's next stage) are requested
+//                (16 B per lane, L1/L2 resident table packed by k_pack_wfrag4) while the current tile is processed;
+//                plain loads are not queued behind the gathers because those do not pass through the LSU.
+//   banks      = a row's 64-byte slice of block b sits in bank half (b + row) % 2; the plan pairs an even and an
+//                odd row in the two entries a quarter-warp touches, so the 16-byte accesses are conflict-free
+//                whenever a run has both parities.
+//   duplicates = tiles in which entries share a row (a (row, relation) segment longer than its run's tile count)
+//                carry per-entry ranks from the plan and are accumulated rank by rank.
+//   flush      = out[row] = sums (the accumulators start from the bias), 256-byte coalesced rows (fp32, or bf16 for a
+//                bf16 feature gradient); items of a split (hub) block start from zero and add into rows pre-set by
+//                k_fused_init_shared with 16-byte fp32 reductions.
 //
 // The same kernel serves the forward (gather X[o], W) and the feature gradient (gather the bf16 copy of
 // grad_out[s], W^T) on the plan's ff / fb lists.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "propagate_fast.cuh"
 #include "propagate_mma.cuh"
 
 namespace rgcn {
 
-constexpr int kFuAhead = 5;                            // stages in flight (gathers, indices, weight slices)
-constexpr int kFuStages = kFuAhead + 1;
-constexpr int kFuStageEntries = 64;
-constexpr int kFuXBytes = kFuStageEntries * 128;       // gathered rows of one stage
-constexpr int kFuRvBytes = kFuStageEntries * 8;        // {row, val} records of one stage
-constexpr int kFuWidth = 64;                           // I == O == 4 blocks of 16
+constexpr int kRbStageTiles = 4;                        // tiles per pipeline stage
+constexpr int kRbRecBytes = RGCN_FUSE_REC_WORDS * 4;    // 144
+constexpr int kRbStageRecBytes = kRbStageTiles * kRbRecBytes;
+constexpr int kRbBlocks = 4;                            // 16-column weight blocks = consumer warps that read one stage
+constexpr int kRbTurns = 2;                             // consumer warps per column block, taking the stages in turn
+constexpr int kRbConsumers = kRbBlocks * kRbTurns;      // warps 0-7: warp = turn * 4 + block
+constexpr int kRbProducers = 4;                         // warps 8-11
+constexpr int kRbThreads = (kRbConsumers + kRbProducers) * 32;
+constexpr int kRbWidth = 64;                            // I == O == 4 blocks of 16
+static_assert(kRbStageTiles * kRbTurns == RGCN_FUSE_AHEAD, "a tile record names the relation of the warp's next stage");
 
-struct FusedArgs {
-    rgcn_fused fl;
-    int n_items;               // host copy of fl.meta[0]
-    int fuse_rows;
-    long long N;
-    const uint2* wslice;       // [(p * 8 + w) * 32 + lane]: the two B-operand registers of warp w's 16 x 8 slice
-    const float* bias;         // added at the flush of unshared items
-    int32_t* counter;          // work-queue head, zeroed by the launcher
+// gathered rows in shared memory: 128-byte rows with the TMA 128-byte swizzle, or 144-byte rows (linear copies)
+template <bool kGather4> struct RbX {
+    static constexpr int row_bytes = kGather4 ? 128 : 144;
+    static constexpr int tile_bytes = 16 * row_bytes;
+    static constexpr int stage_bytes = kRbStageTiles * tile_bytes;
 };
 
-__host__ __device__ inline size_t fused_slice_stride(int fuse_rows) { return (size_t)fuse_rows * 32 + 16; }
-__host__ __device__ inline size_t fused_tile_bytes(int fuse_rows) { return 8 * fused_slice_stride(fuse_rows); }   // multiple of 128
-inline size_t fused_smem_bytes(int fuse_rows) {
-    return fused_tile_bytes(fuse_rows) + (size_t)kFuStages * (kFuXBytes + kFuRvBytes) +
-           RGCN_FUSE_MAX_ITEM_TILES * sizeof(int32_t) + 16;
+struct RbArgs {
+    const int32_t* col;        // rgcn_fused.col
+    const int32_t* rec;        // rgcn_fused.rec
+    const int32_t* items;      // rgcn_fused.items
+    int n_items;               // host copy of meta[0]
+    int total_tiles;           // host copy of meta[1]
+    int fuse_rows;
+    int nstage;                // pipeline depth
+    long long N;
+    const uint4* wfrag;        // [(p * 4 + b) * 32 + lane]: B fragments of the two n8 halves of block b
+    const float* bias;         // initial value of the accumulators of unshared items, or NULL
+    const unsigned char* src;  // the gathered bf16 matrix (N, 64), used by the cp.async.bulk fallback
+};
+
+__host__ __device__ inline size_t rb_smem_bytes(int fuse_rows, int nstage, bool gather4) {
+    const size_t xs = gather4 ? RbX<true>::stage_bytes : RbX<false>::stage_bytes;
+    return 1024 /* alignment slack */ + (size_t)nstage * xs + (size_t)fuse_rows * 256 + (size_t)nstage * kRbStageRecBytes +
+           (size_t)nstage * 16;
 }
 
-// slices[(p * 8 + w) * 32 + lane] = {b0, b1} of lane (g = lane / 4, t = lane % 4) for the 16 x 8 slice of block
-// w / 2, output columns 8 (w % 2) .. + 7.  transpose = 0: B[k][n] = W[k][n] (forward); 1: B[k][n] = W[n][k].
-__global__ void k_pack_wslice(const float* __restrict__ W, int Rp, int transpose, uint2* __restrict__ slices) {
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+// Waits for the phase with the given parity.  try_wait suspends the warp in hardware for a bounded time, so the loop
+// turns over slowly; a wait that outlasts ~2^24 attempts (seconds: a lost copy, a plan that disagrees with the kernel)
+// traps instead of hanging the device or running on with incomplete data.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_test(bar, parity)) return;
+#pragma unroll 1
+    for (uint32_t spin = 0; !mbar_test(bar, parity); ++spin) {
+        __nanosleep(20);
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int r0, int r1, int r2,
+                                            int r3) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// named barriers: 1 + turn = the four warps of one turn (flush), 3 = all consumers, 4 + block = the pair of a column block
+__device__ __forceinline__ void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816_z(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};\n"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+// wfrag[(p * 4 + b) * 32 + lane] = {b0, b1 of half 0, b0, b1 of half 1} for lane (g = lane / 4, t = lane % 4):
+// half h multiplies by the 16 x 8 matrix whose column n is column 4 (n / 2) + 2 h + (n % 2) of block b, so that after
+// the two MMAs a lane holds columns 4 t .. 4 t + 3 of rows g and g + 8.  transpose = 0: B[k][c] = W[k][c] (forward);
+// 1: B[k][c] = W[c][k] (feature gradient).
+__global__ void k_pack_wfrag4(const float* __restrict__ W, int Rp, int transpose, uint4* __restrict__ frag) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)Rp * 256) return;
-    const int lane = (int)(i & 31), w = (int)((i >> 5) & 7);
-    const long long p = i >> 8;
-    const int g = lane >> 2, t = lane & 3, n = (w & 1) * 8 + g;
-    const float* wb = W + ((size_t)p * 4 + (w >> 1)) * 256;
-    auto at = [&](int k) { return transpose ? wb[n * 16 + k] : wb[k * 16 + n]; };
-    slices[i] = make_uint2(pack_bf16x2(at(2 * t), at(2 * t + 1)), pack_bf16x2(at(2 * t + 8), at(2 * t + 9)));
+    if (i >= (long long)Rp * 128) return;
+    const int lane = (int)(i & 31), b = (int)((i >> 5) & 3);
+    const long long p = i >> 7;
+    const int g = lane >> 2, t = lane & 3;
+    const float* wb = W + ((size_t)p * 4 + b) * 256;
+    auto at = [&](int k, int c) { return transpose ? wb[c * 16 + k] : wb[k * 16 + c]; };
+    uint32_t r[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = 4 * (g >> 1) + 2 * h + (g & 1);
+        r[2 * h] = pack_bf16x2(at(2 * t, c), at(2 * t + 1, c));
+        r[2 * h + 1] = pack_bf16x2(at(2 * t + 8, c), at(2 * t + 9, c));
+    }
+    frag[i] = make_uint4(r[0], r[1], r[2], r[3]);
 }
 
 // rows of split blocks start from the bias (or zero): their items add partial sums with atomics
@@ -78,204 +183,365 @@ __global__ void k_fused_init_shared(const int32_t* __restrict__ items, int n_ite
     if (!it.w || it.y != __ldg(blk_tile + it.x)) return;        // only the first item of a split block
     const long long row0 = (long long)it.x * fuse_rows;
     const int nrows = (int)min((long long)fuse_rows, N - row0);
-    for (int i = threadIdx.x; i < nrows * (kFuWidth / 4); i += blockDim.x) {
-        const int c4 = i % (kFuWidth / 4);
+    for (int i = threadIdx.x; i < nrows * (kRbWidth / 4); i += blockDim.x) {
+        const int c4 = i % (kRbWidth / 4);
         const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(out + (size_t)row0 * kFuWidth)[i] = b;
+        reinterpret_cast<float4*>(out + (size_t)row0 * kRbWidth)[i] = b;
     }
 }
 
-template <typename OT>
-__global__ void __launch_bounds__(256, 1) k_fused_rows(FusedArgs A, const __nv_bfloat16* __restrict__ X,
-                                                       OT* __restrict__ out) {
-    extern __shared__ __align__(128) unsigned char smem_fused[];
-    const int FR = A.fuse_rows;
-    const size_t slice_stride = fused_slice_stride(FR);
-    const size_t tile_bytes = fused_tile_bytes(FR);
-    unsigned char* tile = smem_fused;
-    unsigned char* xst = tile + tile_bytes;
-    unsigned char* rvst = xst + (size_t)kFuStages * kFuXBytes;
-    int32_t* s_rel = reinterpret_cast<int32_t*>(rvst + (size_t)kFuStages * kFuRvBytes);
-    int32_t* s_item = s_rel + RGCN_FUSE_MAX_ITEM_TILES;
+template <typename OT, bool kGather4>
+__global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constant__ CUtensorMap tmap, RbArgs A,
+                                                            OT* __restrict__ out) {
+    using XL = RbX<kGather4>;
+    extern __shared__ unsigned char smem_rb[];
+    const uint32_t base = (smem_u32(smem_rb) + 1023u) & ~1023u;
+    const int NS = A.nstage;
+    const uint32_t xs0 = base;                                          // NS stages of gathered rows (1024-aligned)
+    const uint32_t acc0 = xs0 + (uint32_t)NS * XL::stage_bytes;         // fuse_rows x 256 B accumulators (256-aligned)
+    const uint32_t rec0 = acc0 + (uint32_t)A.fuse_rows * 256u;          // NS stages of 4 tile records
+    const uint32_t full0 = rec0 + (uint32_t)NS * kRbStageRecBytes;      // NS "full" barriers, then NS "empty" barriers
+    const uint32_t empty0 = full0 + (uint32_t)NS * 8u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int kb = warp >> 1;                                   // weight block of this warp's columns
-    const int j0 = tid >> 3, ch = tid & 7;                      // gather role: entries j0, j0 + 32 of a stage, 16-byte piece ch
-    const unsigned char* Xb = reinterpret_cast<const unsigned char*>(X);
-    const uint2* wmine = A.wslice + (size_t)warp * 32 + lane;
-    unsigned char* myslice = tile + (size_t)warp * slice_stride + t * 8;
-    float4 bias_lo = make_float4(0.f, 0.f, 0.f, 0.f), bias_hi = bias_lo;   // flush role: columns 8 (tid % 8) .. + 7
-    if (A.bias) {
-        bias_lo = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * (tid & 7));
-        bias_hi = __ldg(reinterpret_cast<const float4*>(A.bias) + 2 * (tid & 7) + 1);
+    // ---- this CTA's share: a contiguous range of work items holding ~1/gridDim of the tiles
+    const int4* items = reinterpret_cast<const int4*>(A.items);
+    auto first_item_at = [&](long long tile) {                          // first item whose first tile is >= tile
+        int lo = 0, hi = A.n_items;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)__ldg(&items[mid].y) < tile) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int G = gridDim.x, c = blockIdx.x;
+    const int i0 = first_item_at((long long)A.total_tiles * c / G);
+    const int i1 = (c == G - 1) ? A.n_items : first_item_at((long long)A.total_tiles * (c + 1) / G);
+    const int tile_begin = i0 < A.n_items ? __ldg(&items[i0].y) : A.total_tiles;
+    const int tile_end = i1 < A.n_items ? __ldg(&items[i1].y) : A.total_tiles;
+    const int n_stages = (tile_end - tile_begin + kRbStageTiles - 1) / kRbStageTiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kRbBlocks);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= kRbConsumers) {
+        // =========================== producers ===========================
+        // Producer warp pw owns the pipeline slots == pw (mod NP); NP divides the pipeline depth, so a warp's
+        // successive visits to a slot are exactly one lap apart and the parity waits below cannot alias.
+        const int NP = (NS % 4 == 0) ? 4 : (NS % 3 == 0) ? 3 : (NS % 2 == 0) ? 2 : 1;
+        const int pw = warp - kRbConsumers;
+        if (pw >= NP) return;
+        const int q = lane & 15;                                        // quad of four rows: tile q / 4 of the stage
+        auto load_idx = [&](int s) {
+            const long long tile = (long long)tile_begin + (long long)s * kRbStageTiles + (q >> 2);
+            int4 v = make_int4(-1, -1, -1, -1);
+            if (lane < 16 && tile < tile_end) v = __ldg(reinterpret_cast<const int4*>(A.col + tile * RGCN_FUSE_TILE) + (q & 3));
+            return v;
+        };
+        int4 idx = load_idx(pw);
+        int slot = pw;                                                  // pw < NP <= NS
+        uint32_t par = 0;
+        for (int s = pw; s < n_stages; s += NP) {
+            const int4 cur = idx;
+            idx = load_idx(s + NP);                                     // lands while this stage's slot frees up
+            const int tile0 = tile_begin + s * kRbStageTiles;
+            const int nt = min(kRbStageTiles, tile_end - tile0);
+            mbar_wait(empty0 + 8 * slot, par ^ 1u);
+            const uint32_t fb = full0 + 8 * slot;
+            const uint32_t xdst = xs0 + (uint32_t)slot * XL::stage_bytes + (uint32_t)(q >> 2) * XL::tile_bytes;
+            if constexpr (kGather4) {
+                const bool go = lane < 16 && cur.x >= 0;                // padding fills a tile from its tail
+                const unsigned m = __ballot_sync(0xffffffffu, go);
+                if (lane == 0) {
+                    mbar_expect_tx(fb, (uint32_t)__popc(m) * 512u + (uint32_t)nt * kRbRecBytes);
+                    bulk_g2s(rec0 + (uint32_t)slot * kRbStageRecBytes, A.rec + (size_t)tile0 * RGCN_FUSE_REC_WORDS,
+                             (uint32_t)nt * kRbRecBytes, fb);
+                }
+                __syncwarp();
+                if (go) tma_gather4(xdst + (uint32_t)(q & 3) * 512u, &tmap, fb, 0, cur.x, cur.y, cur.z, cur.w);
+            } else {
+                const int rows[4] = {cur.x, cur.y, cur.z, cur.w};
+                int n = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) n += (lane < 16 && rows[k] >= 0) ? 1 : 0;
+                const int total = __reduce_add_sync(0xffffffffu, n);
+                if (lane == 0) {
+                    mbar_expect_tx(fb, (uint32_t)total * 128u + (uint32_t)nt * kRbRecBytes);
+                    bulk_g2s(rec0 + (uint32_t)slot * kRbStageRecBytes, A.rec + (size_t)tile0 * RGCN_FUSE_REC_WORDS,
+                             (uint32_t)nt * kRbRecBytes, fb);
+                }
+                __syncwarp();
+                if (lane < 16) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (rows[k] >= 0)
+                            bulk_g2s(xdst + (uint32_t)((q & 3) * 4 + k) * XL::row_bytes, A.src + (size_t)rows[k] * 128, 128u, fb);
+                }
+            }
+            slot += NP;
+            if (slot >= NS) { slot -= NS; par ^= 1u; }
+        }
+        return;
     }
 
-    while (true) {
-        if (tid == 0) *s_item = atomicAdd(A.counter, 1);
-        __syncthreads();
-        const int q = *s_item;
-        if (q >= A.n_items) break;
-        const int4 item = __ldg(reinterpret_cast<const int4*>(A.fl.items) + q);
-        const int blk = item.x, t0 = item.y, nt = item.z - item.y, shared_item = item.w;
-        const int nst = (nt + 3) >> 2;
-        const int n_ent = nt * RGCN_FUSE_TILE;
-        const int32_t* colp = A.fl.col + (size_t)t0 * RGCN_FUSE_TILE;
-        const unsigned char* rvp = reinterpret_cast<const unsigned char*>(A.fl.rv) + (size_t)t0 * RGCN_FUSE_TILE * 8;
+    // =========================== consumers ===========================
+    const int b = warp & (kRbBlocks - 1), turn = warp / kRbBlocks, g = lane >> 2, t = lane & 3;
+    const int ctid = tid & (kRbBlocks * 32 - 1);                        // 0 .. 127 within the four warps of a turn
+    const uint32_t lane_c = (uint32_t)((b << 6) | (t << 4));
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lchunk = 2 * b + (lane >> 4);
+    const uint32_t ldm_off = kGather4 ? (uint32_t)(lrow * 128 + ((lchunk ^ (lrow & 7)) << 4))
+                                      : (uint32_t)(lrow * 144 + lchunk * 16);
+    const uint4* wmine = A.wfrag + (size_t)b * 32 + lane;
+    const int FR = A.fuse_rows;
 
-        for (int i = tid; i < (int)(tile_bytes / 16); i += 256)
-            reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < nt; i += 256) s_rel[i] = __ldg(A.fl.tile_rel + t0 + i);
+    // accumulator (re)initialisation and flush: 16 consecutive threads handle one 256-byte row
+    const int fc4 = ctid & 15;                                          // float4 column of this thread in a row
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias) + fc4);
+    auto acc_addr = [&](int r) {                                        // un-swizzled float4 fc4 of local row r
+        return acc0 + (uint32_t)r * 256u + (uint32_t)((((fc4 >> 2) ^ (r & 1)) << 6) | ((fc4 & 3) << 4));
+    };
+    int cur = i0;
+    int4 it = cur < i1 ? __ldg(&items[cur]) : make_int4(0, 0x7fffffff, 0x7fffffff, 0);
+    if (turn == 0)
+        for (int r = ctid >> 4; r < FR; r += 8) sts128(acc_addr(r), it.w ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4);
+    named_sync(3, kRbConsumers * 32);
 
-        auto load_cols = [&](int k, int& c0, int& c1) {         // gather indices of stage k (-1: nothing to gather)
-            const int e0 = k * kFuStageEntries + j0, e1 = e0 + 32;
-            c0 = e0 < n_ent ? __ldg(colp + e0) : -1;
-            c1 = e1 < n_ent ? __ldg(colp + e1) : -1;
-        };
-        auto issue = [&](int k, int c0, int c1) {
-            if (k < nst) {
-                unsigned char* xs = xst + (size_t)(k % kFuStages) * kFuXBytes;
-                cp_async16(xs + (j0 >> 4) * kTileBytes + tile_off(j0 & 15, ch),
-                           Xb + (size_t)(c0 >= 0 ? c0 : 0) * 128 + ch * 16, c0 >= 0);
-                cp_async16(xs + ((j0 >> 4) + 2) * kTileBytes + tile_off(j0 & 15, ch),
-                           Xb + (size_t)(c1 >= 0 ? c1 : 0) * 128 + ch * 16, c1 >= 0);
-                if (tid < 32) {                                  // 64 records of 8 bytes = 32 pieces of 16 bytes
-                    const int ent = k * kFuStageEntries + tid * 2;
-                    const bool ok = ent < n_ent;
-                    cp_async16(rvst + (size_t)(k % kFuStages) * kFuRvBytes + tid * 16,
-                               ok ? rvp + (size_t)ent * 8 : reinterpret_cast<const unsigned char*>(A.fl.rv), ok);
-                }
-            }
-            cp_async_commit();
-        };
-        auto load_w = [&](int k, uint2 (&w)[4]) {                // weight slices of the four tiles of stage k
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ti = 4 * k + j;
-                const int rel = ti < nt ? (s_rel[ti] & 0x7fffffff) : 0;
-                w[j] = __ldg(wmine + (size_t)rel * 256);
-            }
-        };
-
-        // Everything the loop reads from global memory is requested kFuAhead stages early: the L1 returns data in
-        // request order, so a plain load issued now completes only after every gather already in flight -- a load
-        // consumed one stage later would stall for the whole depth of the gather pipeline.
-        //   colr[u] : gather indices of stage k + kFuAhead   (k % kFuAhead == u), refilled for stage k + 2 kFuAhead
-        //   wr[u]   : weight slices of stage k,               refilled for stage k + kFuAhead
-        int colr[kFuAhead][2];
-        uint2 wr[kFuAhead][4];
-        {
-            int pc[kFuAhead][2];
-#pragma unroll
-            for (int d = 0; d < kFuAhead; ++d) load_cols(d, pc[d][0], pc[d][1]);
-#pragma unroll
-            for (int d = 0; d < kFuAhead; ++d) load_cols(kFuAhead + d, colr[d][0], colr[d][1]);
-            __syncthreads();                                    // tile zeroed, s_rel filled
-#pragma unroll
-            for (int d = 0; d < kFuAhead; ++d) load_w(d, wr[d]);
-#pragma unroll
-            for (int d = 0; d < kFuAhead; ++d) issue(d, pc[d][0], pc[d][1]);
-        }
-
-        for (int k0 = 0; k0 < nst; k0 += kFuAhead) {
-#pragma unroll
-            for (int u = 0; u < kFuAhead; ++u) {
-                const int k = k0 + u;
-                if (k >= nst) break;
-                cp_async_wait<kFuAhead - 1>();                  // stage k has landed (this thread's copies)
-                __syncthreads();                                // ... everyone's, and stage k - 1 is fully consumed
-                issue(k + kFuAhead, colr[u][0], colr[u][1]);    // refills the buffer of stage k - 1
-                load_cols(k + 2 * kFuAhead, colr[u][0], colr[u][1]);
-                uint2 w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = wr[u][j];
-                load_w(k + kFuAhead, wr[u]);
-                const unsigned char* xs = xst + (size_t)(k % kFuStages) * kFuXBytes;
-                const int2* rvs = reinterpret_cast<const int2*>(rvst + (size_t)(k % kFuStages) * kFuRvBytes);
-                // phase a: the four tiles' products and {row, val} records (independent of each other)
-                float c[4][4];
-                int2 r[4][2];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
-                    r[j][0] = r[j][1] = make_int2(0, 0);
-                    if (4 * k + j < nt) {
-                        uint32_t a[4];
-                        const int row = (lane & 7) + ((lane >> 3) & 1) * 8, chunk = kb * 2 + (lane >> 4);
-                        ldmatrix_x4(a, smem_u32(xs + j * kTileBytes + tile_off(row, chunk)));
-                        mma_bf16_16816(c[j], a, w[j].x, w[j].y);
-                        r[j][0] = rvs[j * 16 + g];
-                        r[j][1] = rvs[j * 16 + g + 8];
-                    }
-                }
-                // phase b: add val * product into this warp's column slice, slots 0-7 then 8-15 of every tile
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (4 * k + j >= nt) break;
-                    const bool serial = s_rel[4 * k + j] < 0;   // plan flag: two entries of one step share a row
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const bool valid = r[j][half].y != 0;   // padding and zero-weight edges add nothing
-                        const float v = __int_as_float(r[j][half].y), x0 = c[j][2 * half], x1 = c[j][2 * half + 1];
-                        float2* p = reinterpret_cast<float2*>(myslice + (size_t)r[j][half].x * 32);
-                        if (!serial) {
-                            if (valid) {
-                                float2 o = *p;
-                                o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
-                                *p = o;
-                            }
-                        } else {                                // one entry at a time
-#pragma unroll 1
-                            for (int i = 0; i < 8; ++i) {
-                                if (valid && g == i) {
-                                    float2 o = *p;
-                                    o.x = fmaf(x0, v, o.x); o.y = fmaf(x1, v, o.y);
-                                    *p = o;
-                                }
-                                __syncwarp();
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-        cp_async_wait<0>();
-        __syncthreads();
-
-        // ---- flush: 8 consecutive threads write one 256-byte row
-        const long long row0 = (long long)blk * FR;
+    // writes item `item` out and prepares the accumulators for an item that is shared or not; called by the four
+    // warps of one turn while the other four only run front phases
+    auto flush = [&](const int4& item, int nxt_shared) {
+        named_sync(1 + turn, kRbBlocks * 32);                           // every column block has added its last tile
+        const long long row0 = (long long)item.x * FR;
         const int nrows = (int)min((long long)FR, A.N - row0);
-        for (int idx = tid; idx < nrows * 8; idx += 256) {
-            const int r = idx >> 3, w = idx & 7;
-            const float4* src = reinterpret_cast<const float4*>(tile + (size_t)w * slice_stride + (size_t)r * 32);
-            float4 lo = src[0], hi = src[1];
-            const size_t o = (size_t)(row0 + r) * kFuWidth + 8 * w;
-            if (!shared_item) {
-                lo.x += bias_lo.x; lo.y += bias_lo.y; lo.z += bias_lo.z; lo.w += bias_lo.w;
-                hi.x += bias_hi.x; hi.y += bias_hi.y; hi.z += bias_hi.z; hi.w += bias_hi.w;
-                if constexpr (sizeof(OT) == 2) {
-                    *reinterpret_cast<uint4*>(out + o) = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w),
-                                                                    pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+        const float4 init = nxt_shared ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4;
+        for (int r = ctid >> 4; r < FR; r += 8) {
+            const uint32_t a = acc_addr(r);
+            if (r < nrows) {
+                const float4 v = lds128(a);
+                const size_t o = (size_t)(row0 + r) * kRbWidth + 4 * fc4;
+                if (!item.w) {
+                    if constexpr (sizeof(OT) == 2) {
+                        *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                    } else {
+                        *reinterpret_cast<float4*>(out + o) = v;
+                    }
                 } else {
-                    float4* dst = reinterpret_cast<float4*>(out + o);
-                    dst[0] = lo; dst[1] = hi;
+                    if constexpr (sizeof(OT) == 4)                      // split blocks are never routed to a bf16 output
+                        atomicAdd(reinterpret_cast<float4*>(out + o), v);
                 }
-            } else {
-                if constexpr (sizeof(OT) == 4) {                 // split blocks are never routed to a bf16 output
-                    float* dst = reinterpret_cast<float*>(out) + o;
-                    atomicAdd(dst, lo.x); atomicAdd(dst + 1, lo.y); atomicAdd(dst + 2, lo.z); atomicAdd(dst + 3, lo.w);
-                    atomicAdd(dst + 4, hi.x); atomicAdd(dst + 5, hi.y); atomicAdd(dst + 6, hi.z); atomicAdd(dst + 7, hi.w);
+            }
+            sts128(a, init);
+        }
+        named_sync(1 + turn, kRbBlocks * 32);
+    };
+    auto next_item = [&]() {
+        ++cur;
+        it = cur < i1 ? __ldg(&items[cur]) : make_int4(0, 0x7fffffff, 0x7fffffff, 0);
+    };
+
+    // weight fragments of this warp's first stage; afterwards every tile requests those of the tile 8 places ahead
+    uint4 wr[kRbStageTiles];
+#pragma unroll
+    for (int j = 0; j < kRbStageTiles; ++j) {
+        const long long tile = (long long)tile_begin + turn * kRbStageTiles + j;
+        const int rel = tile < tile_end ? __ldg(A.rec + tile * RGCN_FUSE_REC_WORDS + 33) : 0;
+        wr[j] = __ldg(wmine + (size_t)rel * 128);
+    }
+
+    uint4 rv[kRbStageTiles];            // per tile {offset of row g | rank, val, offset of row g + 8 | rank, val}
+    float d[kRbStageTiles][8];          // products: row g columns 4 t .. 4 t + 3, then row g + 8
+    int hd[kRbStageTiles];              // header word: relation 8 tiles ahead | (largest rank in the tile) << 24
+
+    int fslot = turn;                   // pipeline slot and phase parity of this warp's next front stage (NS >= 2)
+    uint32_t fpar = 0;
+    const unsigned char* wbytes = reinterpret_cast<const unsigned char*>(wmine);
+    auto front_tile = [&](uint32_t xs, uint32_t rs, int j) {
+        rv[j] = lds128u(rs + j * kRbRecBytes + g * 16);
+        hd[j] = lds32(rs + j * kRbRecBytes + 128);
+        uint32_t a[4];
+        ldmatrix_x4(a, xs + j * XL::tile_bytes);
+        float d0[4], d1[4];
+        mma_bf16_16816_z(d0, a, wr[j].x, wr[j].y);
+        mma_bf16_16816_z(d1, a, wr[j].z, wr[j].w);
+        d[j][0] = d0[0]; d[j][1] = d0[1]; d[j][2] = d1[0]; d[j][3] = d1[1];
+        d[j][4] = d0[2]; d[j][5] = d0[3]; d[j][6] = d1[2]; d[j][7] = d1[3];
+        wr[j] = __ldg(reinterpret_cast<const uint4*>(wbytes + (size_t)((uint32_t)(hd[j] & 0xffffff) * 2048u)));
+    };
+    auto front = [&](int s) {
+        const int slot = fslot;
+        const uint32_t par = fpar;
+        fslot += kRbTurns;
+        if (fslot >= NS) { fslot -= NS; fpar ^= 1u; }
+        const int nt = min(kRbStageTiles, tile_end - (tile_begin + s * kRbStageTiles));
+        mbar_wait(full0 + 8 * slot, par);
+        const uint32_t xs = xs0 + (uint32_t)slot * XL::stage_bytes + ldm_off;
+        const uint32_t rs = rec0 + (uint32_t)slot * kRbStageRecBytes;
+        if (nt == kRbStageTiles) {
+#pragma unroll
+            for (int j = 0; j < kRbStageTiles; ++j) front_tile(xs, rs, j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kRbStageTiles; ++j) {
+                if (j < nt) {
+                    front_tile(xs, rs, j);
+                } else {
+                    rv[j] = make_uint4(0u, 0u, 0u, 0u);
+                    hd[j] = 0;
                 }
             }
         }
-        // the barrier at the top of the loop separates this flush from the next item's zero fill
+        __syncwarp();
+        // lane 0 releases the slot; the operands tie the arrive to the completion of this stage's shared-memory loads
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+                     ::"r"(empty0 + 8 * slot), "r"(lane), "r"(rv[0].x), "r"(rv[1].x), "r"(rv[2].x), "r"(rv[3].x),
+                       "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "f"(d[0][7]), "f"(d[1][7]), "f"(d[2][7]), "f"(d[3][7])
+                     : "memory");
+    };
+    // acc[row g / g + 8][4 t .. 4 t + 3] += val * product of one tile whose rows are all different
+    auto rmw = [&](const uint4& r, const float (&dd)[8]) {
+        const float v0 = __uint_as_float(r.y), v1 = __uint_as_float(r.w);
+        const uint32_t p0 = acc0 + (r.x ^ lane_c), p1 = acc0 + (r.z ^ lane_c);
+        float4 x0, x1;
+        if (r.y) x0 = lds128(p0);
+        if (r.w) x1 = lds128(p1);
+        if (r.y) {
+            x0.x = fmaf(v0, dd[0], x0.x); x0.y = fmaf(v0, dd[1], x0.y);
+            x0.z = fmaf(v0, dd[2], x0.z); x0.w = fmaf(v0, dd[3], x0.w);
+            sts128(p0, x0);
+        }
+        if (r.w) {
+            x1.x = fmaf(v1, dd[4], x1.x); x1.y = fmaf(v1, dd[5], x1.y);
+            x1.z = fmaf(v1, dd[6], x1.z); x1.w = fmaf(v1, dd[7], x1.w);
+            sts128(p1, x1);
+        }
+    };
+    // the same for a tile in which entries share rows: the plan ranks the entries of one row 0, 1, ... (low 4 bits of
+    // the offset word); pass q adds the entries of rank q, whose rows are all different
+    auto rmw_ranked = [&](const uint4& r, const float (&dd)[8], int maxrank) {
+        const float v0 = __uint_as_float(r.y), v1 = __uint_as_float(r.w);
+        const uint32_t p0 = acc0 + ((r.x & ~15u) ^ lane_c), p1 = acc0 + ((r.z & ~15u) ^ lane_c);
+        const uint32_t k0 = r.x & 15u, k1 = r.z & 15u;
+#pragma unroll 1
+        for (uint32_t q = 0; q <= (uint32_t)maxrank; ++q) {
+            const bool a0 = r.y && k0 == q, a1 = r.w && k1 == q;
+            float4 x0, x1;
+            if (a0) x0 = lds128(p0);
+            if (a1) x1 = lds128(p1);
+            if (a0) {
+                x0.x = fmaf(v0, dd[0], x0.x); x0.y = fmaf(v0, dd[1], x0.y);
+                x0.z = fmaf(v0, dd[2], x0.z); x0.w = fmaf(v0, dd[3], x0.w);
+                sts128(p0, x0);
+            }
+            if (a1) {
+                x1.x = fmaf(v1, dd[4], x1.x); x1.y = fmaf(v1, dd[5], x1.y);
+                x1.z = fmaf(v1, dd[6], x1.z); x1.w = fmaf(v1, dd[7], x1.w);
+                sts128(p1, x1);
+            }
+        }
+    };
+    auto back = [&](int s) {
+        const int tile0 = tile_begin + s * kRbStageTiles;
+        const int nt = min(kRbStageTiles, tile_end - tile0);
+        // item boundaries before this stage were handled by the other turn
+        while (it.z < tile0 && cur < i1) next_item();
+        if (nt == kRbStageTiles && tile0 + kRbStageTiles <= it.z) {         // whole stage inside the current item
+            if (((hd[0] | hd[1] | hd[2] | hd[3]) >> 24) == 0) {             // ... and no shared rows
+#pragma unroll
+                for (int j = 0; j < kRbStageTiles; ++j) rmw(rv[j], d[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kRbStageTiles; ++j) {
+                    if ((hd[j] >> 24) == 0) rmw(rv[j], d[j]); else rmw_ranked(rv[j], d[j], hd[j] >> 24);
+                }
+            }
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < kRbStageTiles; ++j) {
+            if (j < nt) {
+                const int tile = tile0 + j;
+                while (tile == it.z && cur < i1) {                      // the tile opens the next work item
+                    const int4 done = it;
+                    next_item();
+                    flush(done, it.w);
+                }
+                if ((hd[j] >> 24) == 0) rmw(rv[j], d[j]); else rmw_ranked(rv[j], d[j], hd[j] >> 24);
+            }
+        }
+    };
+
+    // stage s belongs to turn s % 2: between two pair barriers one warp runs back(s) and the other front(s + 1)
+    int pair_bar = 4 + b;
+    asm volatile("" : "+r"(pair_bar));                                  // keep the barrier id in a register
+    auto pair_sync = [&]() { named_sync(pair_bar, kRbTurns * 32); };
+    if (turn == 0) {
+        if (n_stages > 0) front(0);
+        for (int s = 0; s < n_stages; s += 2) {
+            back(s);
+            pair_sync();
+            if (s + 1 < n_stages) {
+                if (s + 2 < n_stages) front(s + 2);
+                pair_sync();
+            }
+        }
+    } else {
+        for (int s = 1; s < n_stages; s += 2) {
+            front(s);
+            pair_sync();
+            back(s);
+            pair_sync();
+        }
+        if (n_stages & 1) pair_sync();
+    }
+    // the last item(s), empty blocks included: flushed by the turn that ran the last back phase
+    if (turn == (n_stages > 0 ? (n_stages - 1) & 1 : 0)) {
+        while (it.z < tile_end && cur < i1) next_item();
+        while (cur < i1) {
+            const int4 done = it;
+            next_item();
+            flush(done, it.w);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-inline size_t fused_ws_bytes(int64_t Rp) { return align_up((size_t)Rp * 256 * sizeof(uint2)) + align_up(sizeof(int32_t)); }
+inline size_t fused_ws_bytes(int64_t Rp) { return align_up((size_t)Rp * 128 * sizeof(uint4)); }
+
+typedef CUresult (*rb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library does not link libcuda
+inline rb_encode_fn rb_encoder() {
+    static rb_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<rb_encode_fn>(p);
+    }();
+    return fn;
+}
+
+// tuning knobs (read at every launch): RGCN_FUSED_TMA = gather4 (default) | bulk, RGCN_FUSED_STAGES = pipeline depth
+struct RbTuning { bool gather4; int stages; };
+inline RbTuning rb_tuning() {
+    RbTuning r{true, 0};
+    const char* e = getenv("RGCN_FUSED_TMA");
+    if (e && e[0] == 'b') r.gather4 = false;
+    e = getenv("RGCN_FUSED_STAGES");
+    if (e) r.stages = atoi(e);
+    return r;
+}
 
 // W: (R', 4, 16, 16) blocks.  out: (N, 64) fp32 or bf16 (bf16 only when the list has no split blocks).
 template <typename OT>
@@ -284,33 +550,59 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
     const rgcn_fused& fl = backward ? g->fb : g->ff;
     const int n_items = (int)g->fuse_items[backward ? 1 : 0];
     const int n_split = (int)g->fuse_split[backward ? 1 : 0];
+    const int total_tiles = (int)g->fuse_tiles[backward ? 1 : 0];
     const int FR = (int)g->fuse_rows;
     RGCN_REQUIRE(n_items > 0, RGCN_ERR_ARG, "fused rows: the plan has no usable fused list");
     RGCN_REQUIRE(n_split == 0 || sizeof(OT) == 4, RGCN_ERR_ARG, "fused rows: split blocks need an fp32 output");
-    const size_t smem = fused_smem_bytes(FR);
-    RGCN_REQUIRE(smem <= 227 * 1024, RGCN_ERR_UNSUPPORTED, "fused rows: fuse_rows %d needs %zu bytes of shared memory", FR, smem);
+    const RbTuning tune = rb_tuning();
+    const size_t xstage = tune.gather4 ? RbX<true>::stage_bytes : RbX<false>::stage_bytes;
+    const size_t fixed = rb_smem_bytes(FR, 0, tune.gather4);
+    const size_t per_sm = 228 * 1024, reserve = 1024, stage = xstage + kRbStageRecBytes + 16;   // 1 KB per CTA is the system's
+    RGCN_REQUIRE(fixed + 2 * stage <= per_sm - reserve, RGCN_ERR_UNSUPPORTED,
+                 "fused rows: fuse_rows %d leaves no room for the gather pipeline", FR);
+    const int ctas = 1;                                   // 12 warps x 168 registers: one CTA owns the SM
+    const size_t limit = per_sm / ctas - reserve;
+    int nstage = tune.stages > 0 ? tune.stages : (limit > fixed ? (int)((limit - fixed) / stage) : 0);
+    if (nstage > 12) nstage = 12;
+    if (nstage < 2) nstage = 2;
+    if (nstage == 5 || nstage == 7 || nstage == 10 || nstage == 11) --nstage;      // keep >= 2 producer warps busy
+    const size_t smem = rb_smem_bytes(FR, nstage, tune.gather4);
+    RGCN_REQUIRE(smem <= per_sm - reserve, RGCN_ERR_UNSUPPORTED,
+                 "fused rows: %d stages with fuse_rows %d need %zu bytes of shared memory", nstage, FR, smem);
     Carver carve(ws);
-    uint2* slices = carve.take<uint2>((size_t)g->num_rels * 256);
-    int32_t* counter = carve.take<int32_t>(1);
-    RGCN_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
-    RGCN_LAUNCH(k_pack_wslice, grid_for(g->num_rels * 256, 256), 256, 0, st, W, (int)g->num_rels, backward ? 1 : 0, slices);
+    uint4* frag = carve.take<uint4>((size_t)g->num_rels * 128);
+    RGCN_LAUNCH(k_pack_wfrag4, grid_for(g->num_rels * 128, 256), 256, 0, st, W, (int)g->num_rels, backward ? 1 : 0, frag);
     if (n_split > 0) {
         if constexpr (sizeof(OT) == 4)
             RGCN_LAUNCH(k_fused_init_shared, n_items, 256, 0, st, fl.items, n_items, fl.blk_tile, FR, (long long)g->num_nodes,
                         bias, reinterpret_cast<float*>(out));
     }
-    static size_t attr_smem[2] = {0, 0};
-    size_t& cur = attr_smem[sizeof(OT) == 2 ? 1 : 0];
-    if (cur < smem) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_fused_rows<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (tune.gather4) {
+        rb_encode_fn enc = rb_encoder();
+        RGCN_REQUIRE(enc, RGCN_ERR_CUDA, "fused rows: cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t gdim[2] = {(cuuint64_t)kRbWidth, (cuuint64_t)g->num_nodes};
+        const cuuint64_t gstr[1] = {(cuuint64_t)kRbWidth * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)kRbWidth, 1};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(src), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RGCN_REQUIRE(r == CUDA_SUCCESS, RGCN_ERR_CUDA, "fused rows: cuTensorMapEncodeTiled failed with %d", (int)r);
     }
-    FusedArgs A{};
-    A.fl = fl; A.n_items = n_items; A.fuse_rows = FR; A.N = (long long)g->num_nodes;
-    A.wslice = slices; A.bias = bias; A.counter = counter;
-    const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-    RGCN_LAUNCH(k_fused_rows<OT>, grid, 256, smem, st, A, src, out);
-    return RGCN_OK;
+    RbArgs A{};
+    A.col = fl.col; A.rec = fl.rec; A.items = fl.items; A.n_items = n_items; A.total_tiles = total_tiles;
+    A.fuse_rows = FR; A.nstage = nstage; A.N = (long long)g->num_nodes;
+    A.wfrag = frag; A.bias = bias; A.src = reinterpret_cast<const unsigned char*>(src);
+    int grid = kNumSMs * ctas;
+    if (grid > n_items) grid = n_items;
+    auto go = [&](auto kernel) -> int {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_LAUNCH(kernel, grid, kRbThreads, smem, st, tm, A, out);
+        return RGCN_OK;
+    };
+    return tune.gather4 ? go(k_rowblock<OT, true>) : go(k_rowblock<OT, false>);
 }
 
 }  // namespace rgcn

@@ -19,7 +19,7 @@ class GraphPlan:
     """
 
     def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True,
-                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=512, fuse_order=1):
+                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=4096):
         _lib.require_cuda(triples_plus)
         assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
         t = triples_plus.contiguous()
@@ -65,21 +65,20 @@ class GraphPlan:
                 for k, v in arrs.items():
                     setattr(tl, k, v.data_ptr())
         # optional fused row-block lists (see include/rgcn_b200.h: rgcn_fused): the edges of every block of
-        # `fuse_rows` rows sorted by (relation, row), runs padded to 16-entry tiles; capacity 2 * nnz entries
+        # `fuse_rows` rows sorted by (relation, row parity, row), runs dealt over 16-entry tiles; capacity 2 * nnz entries
         self.fuse_rows = int(fuse_rows) if nnz > 0 else 0
         g.fuse_rows = self.fuse_rows
         self._fused = []
         if self.fuse_rows > 0:
             assert self.fuse_rows % 16 == 0 and 16 <= self.fuse_rows <= 4096
             cap = (2 * nnz + 15) // 16 * 16 + 16 * 1024
-            g.fuse_cap, g.fuse_item_tiles = cap, max(1, min(int(fuse_item_tiles), 512))
-            g.fuse_order = self.fuse_order = 1 if fuse_order else 0
+            g.fuse_cap, g.fuse_item_tiles = cap, max(1, min(int(fuse_item_tiles), 1 << 20))
             NB = (num_nodes + self.fuse_rows - 1) // self.fuse_rows
             n_items = _lib.lib.rgcn_fused_items_bound(num_nodes, self.fuse_rows, cap, g.fuse_item_tiles)
             for fl in (g.ff, g.fb):
-                arrs = dict(col=torch.empty(cap, **i32), rv=torch.empty(cap, 2, **i32),
-                            tile_rel=torch.empty(cap // 16, **i32), blk_tile=torch.empty(NB + 1, **i32),
-                            items=torch.empty(n_items, 4, **i32), meta=torch.zeros(4, **i32))
+                arrs = dict(col=torch.empty(cap, **i32), rec=torch.empty(cap // 16, _lib.FUSE_REC_WORDS, **i32),
+                            blk_tile=torch.empty(NB + 1, **i32), items=torch.empty(n_items, 4, **i32),
+                            meta=torch.zeros(8, **i32))
                 self._fused.append(arrs)
                 for k, v in arrs.items():
                     setattr(fl, k, v.data_ptr())
@@ -95,12 +94,15 @@ class GraphPlan:
                                                  int(n_self), _lib.ptr(val), C.byref(g), _lib.ptr(ws), ws_bytes,
                                                  _lib.stream_ptr()))
         self.fused_ok = [False, False]
+        self.fused_flagged = [0, 0]
         if self.fuse_rows > 0:                       # host copies of the list sizes; an overflowing list is not used
             for d, arrs in enumerate(self._fused):
-                items, _tiles, overflow, split = arrs['meta'].tolist()
+                items, tiles, overflow, split, flagged = arrs['meta'].tolist()[:5]
                 self.fused_ok[d] = overflow == 0 and items > 0
                 g.fuse_items[d] = items if self.fused_ok[d] else 0
                 g.fuse_split[d] = split
+                g.fuse_tiles[d] = tiles
+                self.fused_flagged[d] = flagged
         if self.tile_edges > 0 or validate:
             st = self.status.tolist()               # one host sync per plan build (the reference's asserts sync too)
             g.tile_capacity = self.tile_capacity = max(st[1], st[2])

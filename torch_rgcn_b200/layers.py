@@ -21,7 +21,7 @@ from .decoder import DistMult                      # noqa: F401  (reference laye
 
 # RGCN_FUSED default: '1' routes bf16 64 -> 64 block layers to the fused row-block kernel (propagate_fused.cuh),
 # '0' keeps the two-phase tensor-core kernels (propagate_mma.cuh)
-_FUSED_DEFAULT = '0'
+_FUSED_DEFAULT = '1'
 
 
 def _unpack_decomposition(decomposition):
@@ -141,14 +141,14 @@ class RelationalGraphConvolutionNC(Module):
     def _fuse_rows(self, features):
         """Rows per block of the fused row-block kernel (bf16 features, four 16x16 blocks, i.e. 64 -> 64), 0 = off.
 
-        RGCN_FUSED=0 disables it, RGCN_FUSE_ROWS overrides the block height (a multiple of 16; 512 rows x 64 fp32
-        columns = 128 KB of the CTA's shared memory)."""
+        RGCN_FUSED=0 disables it, RGCN_FUSE_ROWS overrides the block height (a multiple of 16; 640 rows x 64 fp32
+        columns = 160 KB of the CTA's shared memory)."""
         if (features is None or features.dtype != torch.bfloat16 or self.weight_decomp != 'block' or
                 self.in_features != 64 or self.out_features != 64 or self.num_blocks != 4):
             return 0
         if os.environ.get('RGCN_FUSED', _FUSED_DEFAULT) == '0':
             return 0
-        return int(os.environ.get('RGCN_FUSE_ROWS', '512'))
+        return int(os.environ.get('RGCN_FUSE_ROWS', '640'))
 
     def _plan(self, device, features=None):
         t = self.triples
@@ -162,8 +162,7 @@ class RelationalGraphConvolutionNC(Module):
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
                              validate=self.validate_triples, tile_edges=tile_edges,
                              ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), fuse_rows=fuse_rows,
-                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
-                             fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
+                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

@@ -92,8 +92,7 @@ class RelationShardedNC(torch.nn.Module):
     def _local_plan(self, device, features=None):
         tile_edges = self.layer._tile_edges(features)
         fuse = dict(fuse_rows=self.layer._fuse_rows(features),
-                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
-                             fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
+                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
         if (self._local is None or self._local.device != device or self._local.tile_edges != tile_edges or
                 self._local.fuse_rows != fuse['fuse_rows']):
             L = self.layer
@@ -233,8 +232,7 @@ class RowShardedNC(torch.nn.Module):
         L = self.layer
         tile_edges = L._tile_edges(features)
         kw = dict(tile_edges=tile_edges, ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')),
-                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '512')),
-                  fuse_order=int(os.environ.get('RGCN_FUSE_ORDER', '1')))
+                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
         key = (str(device), tile_edges, kw['fuse_rows'])
         if self._plans is None or self._plans[0] != key:
             tp = L.triples.to(device)
