@@ -70,6 +70,34 @@ WORKLOADS = {
 }
 
 
+def _synthetic():
+    """torch_rgcn_b200/synthetic.py loaded by path: importing the package would dlopen librgcn_b200.so, which the
+    reference arm must never map."""
+    import importlib.util
+    if 'rgcn_bench_synthetic' not in sys.modules:
+        spec = importlib.util.spec_from_file_location('rgcn_bench_synthetic',
+                                                      os.path.join(ROOT, 'torch_rgcn_b200', 'synthetic.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules['rgcn_bench_synthetic'] = mod
+    return sys.modules['rgcn_bench_synthetic']
+
+
+def load_reference():
+    """The UNMODIFIED reference package, pip-installed from /root/reference into baseline/_ref by
+    __graft_entry__.build() (git-ignored, travels to the GPU box).  None if that install is absent."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'torch_rgcn')):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        import torch_rgcn.layers as ref_layers
+    return ref_layers
+
+
 def dist_info():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -81,7 +109,8 @@ def dist_info():
 # workload construction
 # ------------------------------------------------------------------------------------------------------
 def build_triples(wl, device, scale=1.0, seed=0, skew=False):
-    from torch_rgcn_b200.synthetic import SHAPES, random_triples as _rt
+    syn = _synthetic()
+    SHAPES, _rt = syn.SHAPES, syn.random_triples
 
     def random_triples(*a, **k):
         return _rt(*a, rel_dist='zipf' if skew else 'uniform', node_skew=skew, **k)
@@ -317,6 +346,13 @@ def run_ours(args):
     bb_rank = (b_b - N * O * 4 - N * I * 4) / world + N * O * 4 + N * I * 4
     ach_f = bf_rank / (ms_fwd * 1e-3) / 1e9
     ach_b = bb_rank / (ms_bwd * 1e-3) / 1e9
+    # tight byte model of what the backward kernels actually have to move (bf16 layers gather X[o] AND the bf16 copy
+    # of grad_out[s] once per edge, 16 B of indices / weight per edge, one cast pass over grad_out, one write of the
+    # feature gradient in the feature dtype) -- SURVEY's B_b assumes an fp32 grad_out gather plus a second X gather
+    bx = 2 if wl['dtype'] == 'bf16' else 4
+    w_bytes = (b_b - nnz * (O * 4 + 12) - nnz * (I * bx + 8) - N * O * 4 - N * I * 4) / 2
+    bb_tight = nnz * (I * bx + O * bx + 16) / world + N * O * (4 + (bx if bx == 2 else 0)) + N * I * bx + 2 * w_bytes
+    ach_b_tight = bb_tight / (ms_bwd * 1e-3) / 1e9
     ach_s = (bf_rank + bb_rank) / (ms_step * 1e-3) / 1e9
     # which kernels served the step: the fused row-block kernel (propagate_fused.cuh) or the two-phase kernels
     plan = None
@@ -325,18 +361,20 @@ def run_ours(args):
         plan = inner._plan_cache[1]
     if getattr(layer, '_local', None) is not None:
         plan = layer._local
-    fused = bool(plan is not None and getattr(plan, 'fuse_rows', 0) > 0 and all(plan.fused_ok))
+    fused = bool(plan is not None and getattr(plan, 'fuse_rows', 0) > 0 and plan.fused_ok[0])
+    fused_bwd = bool(fused and plan.fused_ok[1])
     traffic = {}
     try:       # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (1 GPU)
-        key = args.workload + ('_fused' if fused else '')
+        key = args.workload + ('_fused2' if fused_bwd else '_fused' if fused else '')
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(key, {}) if world == 1 else {}
     except OSError:
         pass
-    fwd_kernel = ('forward edge gather: rgcn_forward = ONE fused row-block kernel (gather + per-relation MMA + '
-                  'shared-memory row sums), k_fused_rows') if fused else \
+    fwd_kernel = ('forward edge gather: rgcn_forward = ONE fused row-block kernel, k_rowblock (TMA gather4 of the source '
+                  'rows, per-relation MMA, degree normalisation and row sums in shared memory; no per-edge message '
+                  'leaves the SM)') if fused else \
         'forward edge gather: rgcn_forward = gather+transform kernel + row-sum kernel'
     bwd_kernel = ('rgcn_backward = bf16 cast + bias grad, weight-gradient MMA pass, fused row-block kernel for the '
-                  'feature gradient') if fused else \
+                  'feature gradient') if fused_bwd else \
         'rgcn_backward = bf16 cast + bias grad, fused feature/weight gradient kernel, row-sum'
     line = {
         'metric': 'rgcn_layer_edges_per_sec_fwd_bwd', 'value': nnz / (ms_step * 1e-3), 'unit': 'edges/s',
@@ -349,7 +387,9 @@ def run_ours(args):
                                     f'grad_features rows (bwd)') if args.shard == 'rows' else
                                    f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)')
                    if world > 1 else 'single GPU',
-                   'kernels': 'fused row-block (RGCN_FUSED=1)' if fused else 'two-phase (messages through HBM)',
+                   'kernels': ('fused row-block TMA kernel for the forward' + (' and the feature gradient' if fused_bwd else
+                                                                                  '; two-phase tensor-core kernels for the backward')
+                               + f" (RGCN_FUSED={os.environ.get('RGCN_FUSED', '1')})") if fused else 'two-phase (messages through HBM)',
                    'graph_plan': 'built once at first call (outside timed region)' if wl['kind'] == 'nc'
                    else 'rebuilt every step (inside timed region)'},
         'ms_fwd': ms_fwd, 'ms_bwd': ms_bwd, 'first_call_s_incl_plan_build': t_build,
@@ -358,16 +398,33 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'roofline': {'kernel': fwd_kernel,
                      'bound': 'hbm', 'achieved': ach_f, 'peak': peak, 'unit': 'GB/s', 'frac': ach_f / peak,
-                     'traffic': traffic.get('fwd_dram_bytes'), 'peak_source': peak_src,
+                     'traffic': traffic.get('fwd_dram_bytes'), 'traffic_source': traffic.get('source'),
+                     'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': bf_rank, 'bytes_per_edge': per_edge},
         'roofline_bwd': {'kernel': bwd_kernel,
                          'bound': 'hbm', 'achieved': ach_b, 'peak': peak, 'unit': 'GB/s', 'frac': ach_b / peak,
-                         'traffic': traffic.get('bwd_dram_bytes'), 'algorithmic_bytes_per_step': bb_rank},
+                         'traffic': traffic.get('bwd_dram_bytes'), 'algorithmic_bytes_per_step': bb_rank,
+                         'byte_model': 'SURVEY 8(d) B_b (fp32 grad_out gather + second X gather)',
+                         'tight_model': {'bytes': bb_tight, 'achieved': ach_b_tight, 'frac': ach_b_tight / peak,
+                                         'definition': 'one X[o] + one grad_out[s] row per edge in the feature dtype, '
+                                                       '16 B/edge of indices and edge weight, cast pass over grad_out, '
+                                                       'feature gradient written once in the feature dtype'}},
         'roofline_step': {'definition': 'SURVEY 8(d): (B_f + B_b) / (t_fwd + t_bwd)', 'achieved': ach_s, 'peak': peak,
                           'unit': 'GB/s', 'frac': ach_s / peak},
         'clocks': clocks,
     }
     if rank == 0:
+        if world == 1 and args.workload == 'am64' and not args.skew and not args.no_subrecords:
+            # the two targets the north star quotes next to the headline: the fp32 (1e-4 parity) configuration of the
+            # same graph, and the reference's own algorithm on this GPU at the largest scale that fits
+            del layer, X, G, flush, dX, dG
+            torch.cuda.empty_cache()
+            sub = {'am16_fp32': engine_layer_record('am16', 10, 3)}
+            ref_gpu = reference_gpu_record('am16', 0.25, 3, 1)
+            sub['reference_gpu'] = ref_gpu
+            if 'value' in ref_gpu:
+                sub['am16_fp32_vs_reference_gpu_per_edge'] = sub['am16_fp32']['value'] / ref_gpu['value']
+            line['sub_records'] = sub
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
@@ -379,43 +436,68 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: CPU port of the reference's torch.sparse algorithm on a bounded sample
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
+def reference_runner(wl, t, N, Rp, device, ref_layers):
+    """(forward callable, parameter list, kind) for one layer call of the reference implementation on `device`:
+    the unmodified reference layer class when baseline/_ref is installed, else the op-for-op port."""
+    I, O = wl['in_f'], wl['out_f']
+    torch.manual_seed(2)
+    if ref_layers is not None:
+        import warnings
+        warnings.filterwarnings('ignore')
+        if wl['kind'] == 'nc':
+            if wl.get('raw'):
+                tp = t
+            else:
+                from torch_rgcn.utils import add_inverse_and_self as ref_add
+                tp = ref_add(t.cpu(), N, (Rp - 1) // 2, device)
+            layer = ref_layers.RelationalGraphConvolutionNC(
+                triples=tp.to(device), num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
+                decomposition=wl['decomp'], vertical_stacking=wl['vertical']).to(device)
+            return (lambda x: layer(x)), list(layer.parameters()), 'reference'
+        layer = ref_layers.RelationalGraphConvolutionLP(
+            num_nodes=N, num_relations=Rp, in_features=I, out_features=O, decomposition=wl['decomp'],
+            vertical_stacking=wl['vertical'], w_init='glorot-normal', b_init='zeros').to(device).eval()
+        tt = t.to(device)
+        return (lambda x: layer(tt, x)), list(layer.parameters()), 'reference'
     from oracle import torch_sparse_port as port
     from oracle import rgcn_oracle as orc
+    d = wl['decomp'] or {}
+    params = {}
+    if d.get('type') == 'block':
+        nb = d['num_blocks']
+        params['blocks'] = torch.randn(Rp - (1 if wl['kind'] == 'lp' else 0), nb, I // nb, O // nb, device=device)
+        if wl['kind'] == 'lp':
+            params['blocks_self'] = torch.randn(I, O, device=device)
+    elif d.get('type') == 'basis':
+        params['bases'] = torch.randn(d['num_bases'], I, O, device=device)
+        params['comps'] = torch.randn(Rp, d['num_bases'], device=device)
+    else:
+        params['weights'] = torch.randn(Rp, I, O, device=device)
+    params['bias'] = torch.zeros(O, device=device)
+    for p in params.values():
+        p.requires_grad_(True)
+    if wl['kind'] == 'nc':
+        tp = t if wl.get('raw') else torch.as_tensor(orc.add_inverse_and_self(t.cpu().numpy(), N, (Rp - 1) // 2))
+        tp = tp.to(device)
+        return (lambda x: port.nc_forward(tp, N, Rp, params, x, wl['vertical'])), list(params.values()), 'port'
+    tt = t.to(device)
+    return (lambda x: port.lp_forward(tt, N, Rp, params, x, wl['vertical'])), list(params.values()), 'port'
+
+
+def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
     wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    from torch_rgcn_b200.synthetic import SHAPES
-    N0, R0, E0 = SHAPES[wl['shape']]
+    N0, R0, E0 = _synthetic().SHAPES[wl['shape']]
     Rp = 2 * R0 if wl.get('raw') else 2 * R0 + 1
     # the reference materialises dense (R', N, d) fp32 temporaries; bound the largest to ~1 GB
     cap = 1e9 / (Rp * max(wl['in_f'], wl['out_f']) * 4)
     scale = min(1.0, cap / N0)
     t, N, Rp, nnz = build_triples(wl, 'cpu', scale=scale)
     I, O = wl['in_f'], wl['out_f']
-    torch.manual_seed(2)
-    d = wl['decomp'] or {}
-    params = {}
-    if d.get('type') == 'block':
-        nb = d['num_blocks']
-        params['blocks'] = torch.randn(Rp - (1 if wl['kind'] == 'lp' else 0), nb, I // nb, O // nb)
-        if wl['kind'] == 'lp':
-            params['blocks_self'] = torch.randn(I, O)
-    elif d.get('type') == 'basis':
-        params['bases'] = torch.randn(d['num_bases'], I, O)
-        params['comps'] = torch.randn(Rp, d['num_bases'])
-    else:
-        params['weights'] = torch.randn(Rp, I, O)
-    params['bias'] = torch.zeros(O)
-    for p in params.values():
-        p.requires_grad_(True)
+    fwd, params, kind = reference_runner(wl, t, N, Rp, 'cpu', load_reference())
     X = torch.randn(N, I)
     G = torch.randn(N, O)
-    if wl['kind'] == 'nc':
-        tp = t if wl.get('raw') else torch.as_tensor(orc.add_inverse_and_self(t.numpy(), N, (Rp - 1) // 2))
-        fwd = lambda x: port.nc_forward(tp, N, Rp, params, x, wl['vertical'])        # noqa: E731
-    else:
-        fwd = lambda x: port.lp_forward(t, N, Rp, params, x, wl['vertical'])         # noqa: E731
 
     def one():
         x = X.clone().requires_grad_(True)
@@ -424,7 +506,7 @@ def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
         b = time.perf_counter()
         out.backward(G)
         c = time.perf_counter()
-        for p in params.values():
+        for p in params:
             p.grad = None
         return b - a, c - b
 
@@ -439,11 +521,14 @@ def cpu_reference(args, budget_s=20.0, steps=None, warmup=1):
             break
     tf = sum(a for a, _ in times) / len(times)
     tb = sum(b for _, b in times) / len(times)
+    what = ('the UNMODIFIED reference layer (baseline/_ref/torch_rgcn, pip-installed from /root/reference)'
+            if kind == 'reference' else
+            'oracle/torch_sparse_port.py (op-for-op CPU port of the reference torch.sparse path; baseline/_ref absent)')
     return {'value': nnz / (tf + tb), 'unit': 'edges/s', 'cores': cores, 'torch_threads': torch.get_num_threads(),
-            'kind': 'port', 's_fwd': tf, 's_bwd': tb, 'steps': len(times),
-            'sample': f'oracle/torch_sparse_port.py (op-for-op CPU port of the reference torch.sparse path) on a '
-                      f'uniformly scaled graph: scale={scale:.4f}, N={N}, R\'={Rp}, nnz={nnz}, {I}->{O}, fp32; '
-                      f'per-edge rate is scale-invariant because the reference cost is O(R\'*N*d) with N/nnz fixed'}
+            'kind': kind, 's_fwd': tf, 's_bwd': tb, 'steps': len(times),
+            'sample': f'{what} on a uniformly scaled graph: scale={scale:.4f}, N={N}, R\'={Rp}, nnz={nnz}, {I}->{O}, '
+                      f'fp32, all {cores} host cores; per-edge rate is scale-invariant because the reference cost is '
+                      f'O(R\'*N*d) with N/nnz fixed'}
 
 
 def run_model(args):
@@ -847,64 +932,110 @@ def run_sampling(args):
     print(json.dumps(line), flush=True)
 
 
-def run_reference_gpu(args):
-    """Informational: the reference's torch.sparse algorithm (the port) on CUDA tensors at full workload size —
-    the north-star's '>= 1.0x the reference GPU path' comparison.  Falls back to a scaled graph on OOM."""
-    from oracle import torch_sparse_port as port
-    wl = WORKLOADS[args.workload]
+def reference_gpu_record(workload, scale, steps, warmup):
+    """The reference implementation on CUDA tensors of THIS box (the north star's '>= 1.0x the reference GPU
+    torch.sparse path' comparison): the unmodified reference layer `.cuda()` when baseline/_ref is installed and its
+    legacy sparse constructors still work on this torch, else the op-for-op port.  Halves the graph on OOM."""
+    wl = WORKLOADS[workload]
     dev = torch.device('cuda', 0)
-    scale = args.ref_scale
+    ref_layers = load_reference()
+    note = ''
     while True:
         try:
             t, N, Rp, nnz = build_triples(wl, dev, scale=scale)
             I, O = wl['in_f'], wl['out_f']
-            d = wl['decomp'] or {}
-            torch.manual_seed(2)
-            params = {}
-            if d.get('type') == 'block':
-                params['blocks'] = torch.randn(Rp, d['num_blocks'], I // d['num_blocks'], O // d['num_blocks'], device=dev)
-            elif d.get('type') == 'basis':
-                params['bases'] = torch.randn(d['num_bases'], I, O, device=dev)
-                params['comps'] = torch.randn(Rp, d['num_bases'], device=dev)
-            else:
-                params['weights'] = torch.randn(Rp, I, O, device=dev)
-            params['bias'] = torch.zeros(O, device=dev)
-            for p in params.values():
-                p.requires_grad_(True)
-            from torch_rgcn_b200.utils import add_inverse_and_self
-            tp = add_inverse_and_self(t, N, (Rp - 1) // 2, device=dev)
-            X = torch.randn(N, I, device=dev)
+            try:
+                fwd, params, kind = reference_runner(wl, t, N, Rp, dev, ref_layers)
+                X = torch.randn(N, I, device=dev)
+                fwd(X)                                   # the reference's legacy torch.cuda.sparse ctor (layers.py:277)
+            except (torch.OutOfMemoryError, torch.AcceleratorError):
+                raise
+            except Exception as exc:  # noqa: BLE001
+                if ref_layers is None:
+                    raise
+                note = f'unmodified reference failed on CUDA ({type(exc).__name__}: {str(exc)[:120]}); port used'
+                ref_layers = None
+                continue
             G = torch.randn(N, O, device=dev)
             times = []
-            for k in range(args.warmup + args.steps):
+            for k in range(warmup + steps):
                 x = X.clone().requires_grad_(True)
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 e[0].record()
-                out = port.nc_forward(tp, N, Rp, params, x, wl['vertical'])
+                out = fwd(x)
                 e[1].record()
                 out.backward(G)
                 e[2].record()
                 torch.cuda.synchronize()
-                for p in params.values():
+                for p in params:
                     p.grad = None
-                if k >= args.warmup:
+                if k >= warmup:
                     times.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
                 del out, x
             break
-        except torch.OutOfMemoryError:
+        except (torch.OutOfMemoryError, torch.AcceleratorError) as exc:
+            if isinstance(exc, torch.AcceleratorError):          # sticky error: the context is gone, report and stop
+                return {'impl': 'reference-gpu', 'unavailable': f'{str(exc)[:160]} at scale {scale}'}
             torch.cuda.empty_cache()
-            scale /= 2
+            scale *= 0.5
             if scale < 1e-3:
-                raise
+                return {'impl': 'reference-gpu', 'unavailable': 'out of memory at every scale tried'}
     tf = sum(a for a, _ in times) / len(times)
     tb = sum(b for _, b in times) / len(times)
-    print(json.dumps({'impl': 'reference-gpu', 'metric': 'rgcn_layer_edges_per_sec_fwd_bwd',
-                      'value': nnz / ((tf + tb) * 1e-3), 'unit': 'edges/s', 'ms_fwd': tf, 'ms_bwd': tb,
-                      'steps': len(times), 'config': {'workload': wl['label'], 'name': args.workload, 'scale': scale,
-                                                      'num_nodes': N, 'nnz': nnz},
-                      'note': 'reference torch.sparse algorithm (oracle/torch_sparse_port.py) on CUDA tensors, fp32, '
-                              'graph resident on the GPU (the unmodified reference also re-uploads the triples every '
-                              'forward)', 'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+    rec = {'impl': 'reference-gpu', 'kind': kind, 'metric': 'rgcn_layer_edges_per_sec_fwd_bwd',
+           'value': nnz / ((tf + tb) * 1e-3), 'unit': 'edges/s', 'ms_fwd': tf, 'ms_bwd': tb, 'steps': len(times),
+           'config': {'workload': wl['label'], 'name': workload, 'scale': scale, 'num_nodes': N, 'nnz': nnz},
+           'note': ('the unmodified reference layer (baseline/_ref) moved to CUDA' if kind == 'reference' else
+                    'reference torch.sparse algorithm (oracle/torch_sparse_port.py) on CUDA tensors') +
+                   ', fp32, CUDA-event timed, same box' + (('; ' + note) if note else ''),
+           'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_reference_gpu(args):
+    print(json.dumps(reference_gpu_record(args.workload, args.ref_scale, args.steps, args.warmup)), flush=True)
+
+
+def engine_layer_record(workload, steps, warmup):
+    """Device-resident fwd / bwd times of this engine on one NC workload (sub-records of the headline line)."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    from torch_rgcn_b200.utils import add_inverse_and_self
+    wl = WORKLOADS[workload]
+    dev = torch.device('cuda', 0)
+    t, N, Rp, nnz = build_triples(wl, dev)
+    xdt = torch.bfloat16 if wl['dtype'] == 'bf16' else torch.float32
+    torch.manual_seed(2)
+    tp = t if wl.get('raw') else add_inverse_and_self(t, N, (Rp - 1) // 2, device=dev)
+    layer = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=Rp, in_features=wl['in_f'],
+                                         out_features=wl['out_f'], decomposition=wl['decomp'],
+                                         vertical_stacking=wl['vertical']).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn(N, wl['in_f'], device=dev, generator=gen).to(xdt)
+    G = torch.randn(N, wl['out_f'], device=dev, generator=gen)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    tf = tb = 0.0
+    for k in range(warmup + steps):
+        flush.zero_()
+        x = X.detach().requires_grad_(True)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = layer(x)
+        e[1].record()
+        out.backward(G)
+        e[2].record()
+        torch.cuda.synchronize()
+        if k >= warmup:
+            tf += e[0].elapsed_time(e[1]) / steps
+            tb += e[1].elapsed_time(e[2]) / steps
+    b_f, b_b, _ = algorithmic_bytes(wl, N, Rp, nnz)
+    del layer, X, G, flush
+    torch.cuda.empty_cache()
+    return {'workload': wl['label'], 'name': workload, 'dtype': wl['dtype'], 'nnz': nnz, 'ms_fwd': tf, 'ms_bwd': tb,
+            'value': nnz / ((tf + tb) * 1e-3), 'unit': 'edges/s',
+            'gather_model_gbs_fwd': b_f / (tf * 1e-3) / 1e9,
+            'note': 'parity bar 1e-4 vs the reference (tests/test_gpu_parity.py); X fits L2, so the gather model is '
+                    'not an HBM fraction (SURVEY 8d)' if workload == 'am16' else ''}
 
 
 def run_reference(args):
@@ -931,6 +1062,7 @@ def main():
     ap.add_argument('--workload', default='am64', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-subrecords', action='store_true', help='skip the am16_fp32 / reference_gpu sub-records')
     ap.add_argument('--ref-scale', type=float, default=1.0, help='graph scale for --impl reference-gpu')
     ap.add_argument('--skew', action='store_true', help='power-law node degrees + Zipf relation sizes (hub rows)')
     ap.add_argument('--cpu-budget', type=float, default=20.0)

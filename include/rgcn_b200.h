@@ -201,6 +201,8 @@ typedef struct rgcn_graph {
     int64_t fuse_rows;      /* 0: no fused row-block lists (ff / fb unused); else rows per block (multiple of 16) */
     int64_t fuse_cap;       /* entries allocated per list (multiple of 16) */
     int64_t fuse_item_tiles;/* largest work item in tiles, 1 .. RGCN_FUSE_MAX_ITEM_TILES */
+    int64_t fuse_dirs;      /* which lists to build: bit 0 = ff (forward), bit 1 = fb (feature gradient); the arrays of a
+                               list that is not built may be NULL */
     int64_t fuse_items[2];  /* host copies of ff / fb meta[0] filled by the caller after the build;
                                0 = list unusable (overflow or not read back): the kernels fall back */
     int64_t fuse_split[2];  /* host copies of ff / fb meta[3] */

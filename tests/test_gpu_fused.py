@@ -24,7 +24,8 @@ def test_fused_lists_match_definition(cuda_device, FR, item_tiles, skew):
     t = random_triples(N, R, E, seed=11, rel_dist='zipf' if skew else 'uniform', node_skew=skew)
     tp = orc.add_inverse_and_self(t.numpy(), N, R)
     Rp = 2 * R + 1
-    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles)
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW, fuse_rows=FR, fuse_item_tiles=item_tiles,
+                     fuse_dirs=3)
     val = plan.val[:plan.nnz].cpu().numpy()
     for d in (0, 1):
         exp = _expected_lists(tp, N, Rp, val, FR, item_tiles, backward=bool(d))
@@ -62,7 +63,7 @@ def _graph(kind, N, R, E):
 
 def _run(cuda_device, monkeypatch, fused, N, R, t, vertical, grads, fuse_rows='512', item_tiles='4096', seed=8, tma='gather4'):
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
-    monkeypatch.setenv('RGCN_FUSED', '1' if fused else '0')
+    monkeypatch.setenv('RGCN_FUSED', '2' if fused else '0')
     monkeypatch.setenv('RGCN_FUSE_ROWS', fuse_rows)
     monkeypatch.setenv('RGCN_FUSE_ITEM_TILES', item_tiles)
     monkeypatch.setenv('RGCN_TILE_MB', '0')
@@ -154,7 +155,7 @@ def test_fused_is_reproducible_and_agrees_with_two_phase(cuda_device, monkeypatc
 def test_fused_isolated_rows_get_bias(cuda_device, monkeypatch):
     """Rows without edges (whole empty row blocks included) still receive the bias; their gradient is zero."""
     from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
-    monkeypatch.setenv('RGCN_FUSED', '1')
+    monkeypatch.setenv('RGCN_FUSED', '2')
     monkeypatch.setenv('RGCN_FUSE_ROWS', '64')
     N, Rp = 1000, 3
     tp = torch.tensor([[5, 0, 7], [5, 1, 900], [900, 2, 5], [999, 0, 0]])

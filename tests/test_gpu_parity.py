@@ -428,3 +428,23 @@ def test_models_match_reference(cuda_device, name):
     np.testing.assert_allclose(out.detach().cpu().numpy(), d['out'], atol=ATOL, rtol=1e-4)
     for n, p in model.named_parameters():
         np.testing.assert_allclose(p.grad.cpu().numpy(), grads[n], atol=ATOL, rtol=1e-4, err_msg=n)
+
+
+def test_block_diag_is_differentiable(cuda_device):
+    """utils.block_diag sits on the reference's autograd path (layers.py:244, :521): gradients reach the blocks."""
+    from torch_rgcn_b200.utils import block_diag
+    m = torch.randn(3, 2, 4, 5, device=cuda_device, requires_grad=True)
+    out = block_diag(m)
+    ref = torch.stack([torch.block_diag(*m[i].detach().unbind(0)) for i in range(3)])
+    assert torch.equal(out.detach(), ref)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    expect = torch.stack([torch.stack([w[i, 4 * k:4 * k + 4, 5 * k:5 * k + 5] for k in range(2)]) for i in range(3)])
+    assert torch.equal(m.grad, expect)
+
+
+def test_negative_sampling_default_device(cuda_device):
+    from torch_rgcn_b200.decoder import negative_sampling
+    batch = torch.zeros(4, 3, 3, dtype=torch.long, device=cuda_device)
+    out = negative_sampling(batch, 10, 0.5)                    # reference default device='cpu' would not reach the kernel
+    assert out.shape == (12, 3) and out.is_cuda

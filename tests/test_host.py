@@ -174,3 +174,23 @@ def test_product_never_imports_the_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert 'oracle' not in src.replace('no CPU', ''), fn
+
+
+def test_layer_copies_and_pickles_without_its_plan_cache():
+    """copy.deepcopy(model) / pickling (the best-checkpoint pattern) work after a forward has cached a GraphPlan, whose
+    ctypes structs cannot be pickled: the copy drops the cache and rebuilds it lazily."""
+    import copy
+    import pickle
+    import torch
+    from torch_rgcn_b200 import _lib
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    t = torch.tensor([[0, 0, 1], [1, 1, 2]])
+    layer = RelationalGraphConvolutionNC(triples=t, num_nodes=3, num_relations=2, in_features=4, out_features=4)
+    layer._plan_cache = ('key', _lib.Graph())                 # what a forward leaves behind
+    with pytest.raises(Exception):
+        pickle.dumps(_lib.Graph())
+    clone = copy.deepcopy(layer)
+    assert clone._plan_cache is None and layer._plan_cache is not None
+    assert torch.equal(clone.weights, layer.weights) and clone.weights is not layer.weights
+    again = pickle.loads(pickle.dumps(layer))
+    assert again._plan_cache is None and torch.equal(again.weights, layer.weights)

@@ -1,6 +1,6 @@
 """Time the am64 layer (forward / backward, CUDA events, L2 flushed between steps) for a list of fused-kernel
 settings.  Usage: python tools/fused_sweep.py [0 640 512/s4 320/c2 640/bulk ...]
-  0 = two-phase kernels; ROWS[/sSTAGES][/cCTAS_PER_SM][/bulk] = fused row-block kernel."""
+  0 = two-phase kernels; ROWS[/sSTAGES][/bulk][/f] = fused row-block kernel (f: forward only, two-phase backward)."""
 import os
 import sys
 
@@ -28,13 +28,15 @@ def main():
     ref = None
     for s in settings:
         parts = s.split('/')
-        os.environ['RGCN_FUSED'] = '0' if parts[0] == '0' else '1'
+        os.environ['RGCN_FUSED'] = '0' if parts[0] == '0' else ('1' if 'f' in parts[1:] else '2')
         for k in ('RGCN_FUSED_STAGES', 'RGCN_FUSED_CTAS', 'RGCN_FUSED_TMA'):
             os.environ.pop(k, None)
         if parts[0] != '0':
             os.environ['RGCN_FUSE_ROWS'] = parts[0]
         for q in parts[1:]:
-            if q == 'bulk':
+            if q == 'f':
+                pass
+            elif q == 'bulk':
                 os.environ['RGCN_FUSED_TMA'] = 'bulk'
             elif q[0] == 's':
                 os.environ['RGCN_FUSED_STAGES'] = q[1:]
@@ -61,7 +63,7 @@ def main():
         plan = layer._plan_cache[1]
         info = ''
         if plan.fuse_rows:
-            metas = [a['meta'].tolist() for a in plan._fused]
+            metas = [a['meta'].tolist() for a in plan._fused if a is not None]
             info = f' fused_ok={plan.fused_ok} meta(items,tiles,overflow,split,flagged)={[m[:5] for m in metas]} fill={plan.nnz / (16.0 * metas[0][1]):.3f}'
         if ref is None:
             ref = (out.detach().clone(), x.grad.detach().float().clone())

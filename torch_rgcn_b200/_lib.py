@@ -39,7 +39,7 @@ class Graph(C.Structure):
                 ('val', _p), ('status', _p), ('d_long', _p), ('s_long', _p), ('num_long_dst', _i64), ('num_long_src', _i64),
                 ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ring_depth', _i64),
                 ('ft', Tiling), ('bt', Tiling),
-                ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64),
+                ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64), ('fuse_dirs', _i64),
                 ('fuse_items', _i64 * 2), ('fuse_split', _i64 * 2), ('fuse_tiles', _i64 * 2), ('ff', Fused), ('fb', Fused)]
 
 

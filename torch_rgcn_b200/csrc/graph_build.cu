@@ -647,6 +647,7 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
     g->num_nodes = N; g->num_rels = Rp; g->nnz = nnz;
     g->num_tiles = 0; g->tile_capacity = 0; g->num_long_dst = g->num_long_src = -1;
     g->fuse_items[0] = g->fuse_items[1] = 0; g->fuse_split[0] = g->fuse_split[1] = 0;
+    g->fuse_tiles[0] = g->fuse_tiles[1] = 0;
     RGCN_REQUIRE(g->tile_edges >= 0, RGCN_ERR_ARG, "rgcn_graph_build: negative tile_edges");
     RGCN_REQUIRE(g->d_long && g->s_long, RGCN_ERR_ARG, "rgcn_graph_build: NULL long-row list");
     RGCN_CHECK_CUDA(cudaMemsetAsync(g->status, 0, 8 * sizeof(int32_t), stream));
@@ -744,7 +745,9 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         const int fbits = bits_for(fkey);
         const int64_t bound = rgcn_fused_items_bound(N, FR, cap, item_tiles);
         const int64_t cap_tiles = cap / RGCN_FUSE_TILE;
+        RGCN_REQUIRE(g->fuse_dirs >= 1 && g->fuse_dirs <= 3, RGCN_ERR_ARG, "rgcn_graph_build: fuse_dirs must be 1, 2 or 3");
         for (int backward = 0; backward < 2; ++backward) {
+            if (!((g->fuse_dirs >> backward) & 1)) continue;
             rgcn_fused& fl = backward ? g->fb : g->ff;
             RGCN_REQUIRE(fl.col && fl.rec && fl.blk_tile && fl.items && fl.meta, RGCN_ERR_ARG,
                          "rgcn_graph_build: NULL fused list array");

@@ -314,8 +314,13 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
     if (fused_path(g, p, s, x_dtype == RGCN_BF16, true)) return bytes + fused_ws_bytes(s.Rp);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
+    // bf16 16x16-block tensor-core backward: bf16 feature-gradient messages, sized by the predicate rgcn_backward uses
+    // (rel_path() below would give up above kMaxMsgBytes of fp32 messages and under-report this path)
+    if (x_dtype == RGCN_BF16 && p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 &&
+        mma_shape_supported(s.nb, s.bi, s.bo))
+        return bytes + align_up((size_t)s.nnz * s.I * 2);
     RelShape rs; size_t msg = 0;
-    if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32 upper bound)
+    if (rel_path(p, s, false, true, &rs, &msg)) bytes += msg;     // feature-gradient messages (fp32)
     return bytes;
 }
 

@@ -482,7 +482,10 @@ __device__ __forceinline__ void wait_count(const int32_t* counter, int need, int
         unsigned spins = 0;
         while (ld_acquire(counter) < need) {
             __nanosleep(64);
-            if (++spins > (1u << 24)) { atomicExch(status + 3, 1); break; }   // ~1 s: report instead of hanging
+            // ~1 s without progress (a pre-empted or time-sliced device, a profiler replay): record it and abort the
+            // launch.  Running on with an incomplete message ring would return silently wrong sums; the trap turns
+            // it into a CUDA error the caller sees at its next synchronisation.
+            if (++spins > (1u << 24)) { atomicExch(status + 3, 1); __threadfence_system(); __trap(); }
         }
     }
     __syncthreads();
@@ -759,11 +762,8 @@ inline bool mma_shape_supported(int nb, int bi, int bo) {
 
 inline int launch_rel_mma_fwd(const RelArgs& A, const __nv_bfloat16* X, __nv_bfloat16* msg, int max_chunks,
                               cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
-        attr_set = true;
-    }
+    // per device / context, so set on every launch (cheap) rather than once per process
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
     RGCN_LAUNCH(k_rel_mma_fwd, max_chunks, 256, kFwdSmemBytes, st, A, X, msg);
     return RGCN_OK;
 }
@@ -772,11 +772,7 @@ inline int launch_rel_mma_fwd(const RelArgs& A, const __nv_bfloat16* X, __nv_bfl
 inline int launch_rel_mma_bwd(const RelArgs& A, const __nv_bfloat16* X, const __nv_bfloat16* Gb, __nv_bfloat16* msg,
                               float* gW, int max_chunks, cudaStream_t st) {
     constexpr size_t smem = BwdSmem<true>::kBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_rel_mma_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RGCN_LAUNCH(k_rel_mma_bwd<true>, max_chunks, 256, smem, st, A, X, static_cast<const void*>(Gb), msg, gW);
     return RGCN_OK;
 }
@@ -813,13 +809,12 @@ inline TiledArgs make_tiled_args(const rgcn_graph* g, bool backward, int nb, con
 
 inline int launch_tiled_span(const TiledArgs& A, const __nv_bfloat16* src, __nv_bfloat16* ring, float* out,
                              cudaStream_t st) {
-    static int grid = 0;
-    if (!grid) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmemBytes));
-        int per_sm = 0;
-        RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_span, 256, kSpanSmemBytes));
-        grid = kNumSMs * (per_sm > 0 ? per_sm : 1);
-    }
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmemBytes));
+    int per_sm = 0, dev = 0, sms = kNumSMs;
+    RGCN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiled_span, 256, kSpanSmemBytes));
+    RGCN_CHECK_CUDA(cudaGetDevice(&dev));
+    RGCN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * (per_sm > 0 ? per_sm : 1);
     RGCN_LAUNCH(k_tiled_span, grid, 256, kSpanSmemBytes, st, A, src, ring, out);
     return RGCN_OK;
 }

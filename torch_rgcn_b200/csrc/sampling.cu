@@ -416,11 +416,8 @@ extern "C" int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32
     if (!p.seen) a.g_seen = c.take<uint32_t>((size_t)((N + 31) / 32));
     if (!p.picked) a.g_picked = c.take<uint32_t>((size_t)((E + 31) / 32));
     if (!p.counts) a.g_counts = c.take<int32_t>((size_t)N);
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load(std::memory_order_acquire)) {
-        RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_sample_edge_neighborhood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        attr_set.store(true, std::memory_order_release);
-    }
+    // per device / context, so set on every launch (cheap) rather than once per process
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_sample_edge_neighborhood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     RGCN_LAUNCH(k_sample_edge_neighborhood, 1, 1024, p.smem, st, a);
     return RGCN_OK;
 }

@@ -166,12 +166,14 @@ class DistMult(Module):
         return distmult_score(triples, nodes, self.relations, self.sbias, self.pbias, self.obias, self.validate_triples)
 
 
-def negative_sampling(batch, num_nodes, head_corrupt_prob, device='cpu'):
+def negative_sampling(batch, num_nodes, head_corrupt_prob, device=None):
     """Corrupt the head or the tail of every triple of `batch` (bs, ns, 3) in place; returns (bs * ns, 3).
 
     Same signature and the same two random draws in the same order as reference utils/misc.py:174-189
     (`randint` for the new entities, then `bernoulli` for head-vs-tail); the masked assignment
     `batch[mask] = corruptions` runs in the CUDA library."""
+    if device is None or (torch.device(device).type == 'cpu' and batch.is_cuda):
+        device = batch.device                   # the reference's default 'cpu' cannot feed the CUDA kernel
     bs, ns, _ = batch.size()
     corruptions = torch.randint(size=(bs * ns,), low=0, high=num_nodes, dtype=torch.long, device=device)
     mask = torch.bernoulli(torch.empty(size=(bs, ns, 1), dtype=torch.float, device=device).fill_(head_corrupt_prob)).to(torch.bool)

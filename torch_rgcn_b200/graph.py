@@ -19,7 +19,7 @@ class GraphPlan:
     """
 
     def __init__(self, triples_plus, num_nodes, num_rels, norm, n_general=0, n_self=0, val=None, validate=True,
-                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=4096):
+                 tile_edges=0, ring_depth=8, fuse_rows=0, fuse_item_tiles=4096, fuse_dirs=1):
         _lib.require_cuda(triples_plus)
         assert triples_plus.dtype == torch.long, 'triples must be torch.long'   # reference utils.py:148
         t = triples_plus.contiguous()
@@ -75,7 +75,12 @@ class GraphPlan:
             g.fuse_cap, g.fuse_item_tiles = cap, max(1, min(int(fuse_item_tiles), 1 << 20))
             NB = (num_nodes + self.fuse_rows - 1) // self.fuse_rows
             n_items = _lib.lib.rgcn_fused_items_bound(num_nodes, self.fuse_rows, cap, g.fuse_item_tiles)
-            for fl in (g.ff, g.fb):
+            g.fuse_dirs = self.fuse_dirs = int(fuse_dirs)        # bit 0: forward lists, bit 1: feature-gradient lists
+            assert self.fuse_dirs in (1, 2, 3)
+            for d, fl in enumerate((g.ff, g.fb)):
+                if not (self.fuse_dirs >> d) & 1:
+                    self._fused.append(None)
+                    continue
                 arrs = dict(col=torch.empty(cap, **i32), rec=torch.empty(cap // 16, _lib.FUSE_REC_WORDS, **i32),
                             blk_tile=torch.empty(NB + 1, **i32), items=torch.empty(n_items, 4, **i32),
                             meta=torch.zeros(8, **i32))
@@ -97,6 +102,8 @@ class GraphPlan:
         self.fused_flagged = [0, 0]
         if self.fuse_rows > 0:                       # host copies of the list sizes; an overflowing list is not used
             for d, arrs in enumerate(self._fused):
+                if arrs is None:
+                    continue
                 items, tiles, overflow, split, flagged = arrs['meta'].tolist()[:5]
                 self.fused_ok[d] = overflow == 0 and items > 0
                 g.fuse_items[d] = items if self.fused_ok[d] else 0

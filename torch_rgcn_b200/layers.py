@@ -19,9 +19,15 @@ from .graph import GraphPlan
 from .utils import select_b_init, select_w_init, schlichtkrull_normal_
 from .decoder import DistMult                      # noqa: F401  (reference layers.py:9 defines it in this module)
 
-# RGCN_FUSED default: '1' routes bf16 64 -> 64 block layers to the fused row-block kernel (propagate_fused.cuh),
-# '0' keeps the two-phase tensor-core kernels (propagate_mma.cuh)
+# RGCN_FUSED: '1' (default) routes the forward of bf16 64 -> 64 block layers to the fused row-block kernel
+# (propagate_fused.cuh) and keeps the two-phase tensor-core kernels (propagate_mma.cuh) for the backward, '2' also
+# computes the feature gradient with the fused kernel, '0' uses the two-phase kernels throughout
 _FUSED_DEFAULT = '1'
+
+
+def _fuse_dirs():
+    """Lists the plan builds for the fused kernel: 1 = forward only, 3 = forward and feature gradient."""
+    return 3 if os.environ.get('RGCN_FUSED', _FUSED_DEFAULT) == '2' else 1
 
 
 def _unpack_decomposition(decomposition):
@@ -37,7 +43,27 @@ def _check_blocks(num_blocks, in_dim, out_dim):
         f'by number of blocks ({num_blocks})'
 
 
-class RelationalGraphConvolutionNC(Module):
+class _PlanCacheMixin:
+    """The cached GraphPlan holds ctypes structs with device pointers: it is dropped when a layer is copied or pickled
+    (copy.deepcopy(model), torch.save(model)) and rebuilt lazily at the next forward."""
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        if '_plan_cache' in state:
+            state['_plan_cache'] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_plan_cache' else copy.deepcopy(v, memo)
+        return new
+
+
+class RelationalGraphConvolutionNC(_PlanCacheMixin, Module):
     """Relational graph convolution for node classification (graph fixed at construction).
 
     Mirrors reference torch_rgcn/layers.py:101-308.  The graph plan (sorted CSR + per-edge weights) is
@@ -162,7 +188,8 @@ class RelationalGraphConvolutionNC(Module):
             plan = GraphPlan(t.to(device), self.num_nodes, self.num_relations, norm, n_general, self.num_nodes,
                              validate=self.validate_triples, tile_edges=tile_edges,
                              ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), fuse_rows=fuse_rows,
-                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
+                             fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')),
+                             fuse_dirs=_fuse_dirs())
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

@@ -19,6 +19,7 @@ import torch.distributed as dist
 from . import _lib
 from .functional import _Propagate
 from .graph import GraphPlan
+from .layers import _fuse_dirs
 
 
 def plan_relation_shards(rel_counts, world):
@@ -92,7 +93,7 @@ class RelationShardedNC(torch.nn.Module):
     def _local_plan(self, device, features=None):
         tile_edges = self.layer._tile_edges(features)
         fuse = dict(fuse_rows=self.layer._fuse_rows(features),
-                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
+                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')), fuse_dirs=_fuse_dirs())
         if (self._local is None or self._local.device != device or self._local.tile_edges != tile_edges or
                 self._local.fuse_rows != fuse['fuse_rows']):
             L = self.layer
@@ -232,7 +233,7 @@ class RowShardedNC(torch.nn.Module):
         L = self.layer
         tile_edges = L._tile_edges(features)
         kw = dict(tile_edges=tile_edges, ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')),
-                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')))
+                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')), fuse_dirs=_fuse_dirs())
         key = (str(device), tile_edges, kw['fuse_rows'])
         if self._plans is None or self._plans[0] != key:
             tp = L.triples.to(device)

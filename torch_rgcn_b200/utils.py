@@ -91,17 +91,36 @@ def sum_sparse(indices, values, size, row_normalisation=True, device='cpu'):
     return out.to(device).view(k)
 
 
+class _BlockDiag(torch.autograd.Function):
+    """rgcn_block_diag with the gradient the reference's differentiable block_diag has: the diagonal blocks of grad."""
+
+    @staticmethod
+    def forward(ctx, mm):
+        n, nb, bi, bo = mm.shape
+        ctx.dims = (nb, bi, bo)
+        out = torch.empty(n, nb * bi, nb * bo, dtype=torch.float32, device=mm.device)
+        with torch.cuda.device(mm.device):
+            _lib.check(_lib.lib.rgcn_block_diag(_lib.ptr(mm), n, nb, bi, bo, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        nb, bi, bo = ctx.dims
+        g = grad.reshape(-1, nb, bi, nb, bo)
+        idx = torch.arange(nb, device=grad.device)
+        return g[:, idx, :, idx, :].permute(1, 0, 2, 3).contiguous()     # (n, nb, bi, bo)
+
+
 def block_diag(m):
-    """(..., nb, bi, bo) -> (..., nb*bi, nb*bo) block-diagonal — reference utils.py:168-196."""
+    """(..., nb, bi, bo) -> (..., nb*bi, nb*bo) block-diagonal — reference utils.py:168-196 (differentiable, like
+    the reference's: it sits on the autograd path of layers.py:244 and :521)."""
     if type(m) is list:
         m = torch.cat([m1.unsqueeze(-3) for m1 in m], -3)
     lead = m.shape[:-3]
     nb, bi, bo = m.shape[-3:]
     src = m
-    mm = m.detach().to(device=m.device if m.is_cuda else _dev(), dtype=torch.float32).reshape(-1, nb, bi, bo).contiguous()
-    out = torch.empty(mm.size(0), nb * bi, nb * bo, dtype=torch.float32, device=mm.device)
-    with torch.cuda.device(mm.device):
-        _lib.check(_lib.lib.rgcn_block_diag(_lib.ptr(mm), mm.size(0), nb, bi, bo, _lib.ptr(out), _lib.stream_ptr()))
+    mm = m.to(device=m.device if m.is_cuda else _dev(), dtype=torch.float32).reshape(-1, nb, bi, bo).contiguous()
+    out = _BlockDiag.apply(mm)
     return out.reshape(lead + (nb * bi, nb * bo)).to(src.device)
 
 
