@@ -223,6 +223,12 @@ def run_ours(args):
     G = torch.randn(N, O, device=dev, generator=gen)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # 256 MB > 126 MB L2
 
+    def step_with(mod, x_in, g_in):
+        x = x_in.detach().requires_grad_(True)
+        out = mod(x)
+        out.backward(g_in)
+        return out.detach(), x.grad
+
     def step(x_in, g_in, ev=None):
         x = x_in.detach().requires_grad_(True)
         if ev:
@@ -235,6 +241,31 @@ def run_ours(args):
             ev[2].record()
         return out, x.grad
 
+    sharded_parity = None
+    if world > 1 and wl['kind'] == 'nc':
+        # the sharded layer against the single-GPU engine on the same full-size inputs, on every rank, before timing
+        torch.manual_seed(2)
+        single = RelationalGraphConvolutionNC(triples=tp, num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
+                                              decomposition=wl['decomp'], vertical_stacking=wl['vertical']).to(dev)
+        o_s, gx_s = step_with(single, X, G)
+        gp_s = [p.grad.clone() for p in single.parameters()]
+        inner = layer.layer
+        for p in inner.parameters():
+            p.grad = None
+        o_m, gx_m = step(X, G)
+        layer.sync_parameter_grads()
+        tol = 3e-2 if wl['dtype'] == 'bf16' else 2e-4
+
+        def rel_err(a, b):
+            return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+        errs = [rel_err(o_m, o_s), rel_err(gx_m, gx_s)] + [rel_err(p.grad, g) for p, g in zip(inner.parameters(), gp_s)]
+        bad = torch.tensor([float(max(errs) > tol)], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        sharded_parity = 'ok' if bad.item() == 0 else f'FAILED: max relative error {max(errs):.3g} on rank {rank} (tolerance {tol})'
+        for p in inner.parameters():
+            p.grad = None
+        del single, o_s, gx_s, gp_s, o_m, gx_m
+        torch.cuda.empty_cache()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     step(X, G)                                   # first call builds (and caches) the NC graph plan
@@ -270,18 +301,28 @@ def run_ours(args):
 
     # ---- end to end: host (pinned) buffers in and out, copies inside the timed region
     params = [p for p in layer.parameters()]
-    hX = X.cpu().pin_memory(); hG = G.cpu().pin_memory()
-    hOut = torch.empty(N, O, dtype=torch.float32).pin_memory()
-    hGX = torch.empty(N, I, dtype=xdt).pin_memory()
-    hGP = [torch.empty_like(p, device='cpu').pin_memory() for p in params]
+    # multi-GPU: a rank uploads / downloads only its 1/world slice of the rows over PCIe; the slices of X and G are
+    # all-gathered over NVLink before the step (the host buffers of the ranks together hold each tensor once)
+    rows_per = (N + world - 1) // world
+    r_lo, r_hi = min(rank * rows_per, N), min((rank + 1) * rows_per, N)
+    hX = X[r_lo:r_hi].cpu().pin_memory(); hG = G[r_lo:r_hi].cpu().pin_memory()
+    hOut = torch.empty(r_hi - r_lo, O, dtype=torch.float32).pin_memory()
+    hGX = torch.empty(r_hi - r_lo, I, dtype=xdt).pin_memory()
+    hGP = [torch.empty_like(p, device='cpu').pin_memory() for p in params] if rank == 0 else []
     h2d = hX.numel() * hX.element_size() + hG.numel() * hG.element_size()
     d2h = hOut.numel() * 4 + hGX.numel() * hGX.element_size() + sum(h.numel() * 4 for h in hGP)
+    io = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    h2d, d2h = int(io[0].item()), int(io[1].item())            # whole-job bytes per step
+    stageX = torch.zeros(rows_per, I, dtype=xdt, device=dev)
+    stageG = torch.zeros(rows_per, O, dtype=torch.float32, device=dev)
 
     # Steps are pipelined the way a training loop would: copies run on their own streams, so the upload of step k+1
     # and the download of step k overlap compute (PCIe is full duplex); every byte still moves inside the timed region.
     s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    dX = [torch.empty_like(X) for _ in range(2)]
-    dG = [torch.empty_like(G) for _ in range(2)]
+    dX = [torch.empty(world * rows_per, I, dtype=xdt, device=dev) for _ in range(2)]
+    dG = [torch.empty(world * rows_per, O, dtype=torch.float32, device=dev) for _ in range(2)]
     slot_free = [None, None]
 
     def e2e_step(k):
@@ -290,27 +331,37 @@ def run_ours(args):
         with torch.cuda.stream(s_h2d):
             if slot_free[slot] is not None:
                 s_h2d.wait_event(slot_free[slot])
-            dX[slot].copy_(hX, non_blocking=True)
-            dG[slot].copy_(hG, non_blocking=True)
+            if world == 1:
+                dX[slot].copy_(hX, non_blocking=True)
+                dG[slot].copy_(hG, non_blocking=True)
+            else:
+                stageX[: r_hi - r_lo].copy_(hX, non_blocking=True)
+                stageG[: r_hi - r_lo].copy_(hG, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(s_h2d)
         cur.wait_event(ready)
+        if world > 1:
+            dist.all_gather_into_tensor(dX[slot], stageX)
+            dist.all_gather_into_tensor(dG[slot], stageG)
+            staged = torch.cuda.Event()
+            staged.record(cur)
+            s_h2d.wait_event(staged)                           # the staging buffers may be refilled
         for p in params:
             p.grad = None
-        x = dX[slot].detach().requires_grad_(True)
+        x = dX[slot][:N].detach().requires_grad_(True)
         out = call(x)
         fwd_done = torch.cuda.Event()
         fwd_done.record(cur)
-        out.backward(dG[slot])
+        out.backward(dG[slot][:N])
         bwd_done = torch.cuda.Event()
         bwd_done.record(cur)
         slot_free[slot] = bwd_done
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(fwd_done)
-            hOut.copy_(out.detach(), non_blocking=True)
+            hOut.copy_(out.detach()[r_lo:r_hi], non_blocking=True)
             out.record_stream(s_d2h)
             s_d2h.wait_event(bwd_done)
-            hGX.copy_(x.grad, non_blocking=True)
+            hGX.copy_(x.grad[r_lo:r_hi], non_blocking=True)
             x.grad.record_stream(s_d2h)
             for h, p in zip(hGP, params):
                 if p.grad is not None:
@@ -361,6 +412,8 @@ def run_ours(args):
         plan = inner._plan_cache[1]
     if getattr(layer, '_local', None) is not None:
         plan = layer._local
+    if getattr(layer, '_plans', None) is not None:           # row-sharded: (key, forward plan, backward plan)
+        plan = layer._plans[1]
     fused = bool(plan is not None and getattr(plan, 'fuse_rows', 0) > 0 and plan.fused_ok[0])
     fused_bwd = bool(fused and plan.fused_ok[1])
     traffic = {}
@@ -383,8 +436,10 @@ def run_ours(args):
         'config': {'workload': wl['label'] + (' [skewed: cubic node skew, Zipf relations]' if args.skew else ''),
                    'name': args.workload, 'num_nodes': N, 'num_relations': Rp, 'nnz': nnz,
                    'l2': 'L2 flushed (256 MB write) between timed steps; flush outside the event pairs',
-                   'parallelism': ((f'row-sharded x{world} (experimental), one all-gather of out rows (fwd) and of '
-                                    f'grad_features rows (bwd)') if args.shard == 'rows' else
+                   'parallelism': ((f'row-sharded x{world}: every rank owns 1/{world} of the output rows; forward rows are '
+                                    f'stored to all ranks by the fused kernel itself over NVLink peer memory, '
+                                    f'feature-gradient rows pushed by the copy engines; parameter gradients all-reduced')
+                                   if args.shard == 'rows' else
                                    f'relation-sharded x{world}, one all-reduce of out (fwd) and of grad_features (bwd)')
                    if world > 1 else 'single GPU',
                    'kernels': ('fused row-block TMA kernel for the forward' + (' and the feature gradient' if fused_bwd else
@@ -396,6 +451,7 @@ def run_ours(args):
         'e2e': {'value': nnz / (ms_e2e * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches),
+        'sharded_parity': sharded_parity,
         'roofline': {'kernel': fwd_kernel,
                      'bound': 'hbm', 'achieved': ach_f, 'peak': peak, 'unit': 'GB/s', 'frac': ach_f / peak,
                      'traffic': traffic.get('fwd_dram_bytes'), 'traffic_source': traffic.get('source'),
@@ -449,7 +505,7 @@ def reference_runner(wl, t, N, Rp, device, ref_layers):
                 tp = t
             else:
                 from torch_rgcn.utils import add_inverse_and_self as ref_add
-                tp = ref_add(t.cpu(), N, (Rp - 1) // 2, device)
+                tp = ref_add(t.to(device), N, (Rp - 1) // 2, str(torch.device(device).type))
             layer = ref_layers.RelationalGraphConvolutionNC(
                 triples=tp.to(device), num_nodes=N, num_relations=Rp, in_features=I, out_features=O,
                 decomposition=wl['decomp'], vertical_stacking=wl['vertical']).to(device)
@@ -1066,9 +1122,10 @@ def main():
     ap.add_argument('--ref-scale', type=float, default=1.0, help='graph scale for --impl reference-gpu')
     ap.add_argument('--skew', action='store_true', help='power-law node degrees + Zipf relation sizes (hub rows)')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
-    ap.add_argument('--shard', default='relations', choices=['relations', 'rows'],
-                    help='multi-GPU partition of an NC layer: relations + all-reduce (default, the north-star design) or '
-                         'rows + all-gather (experimental, parallel.RowShardedNC)')
+    ap.add_argument('--shard', default='rows', choices=['relations', 'rows'],
+                    help='multi-GPU partition of an NC layer: rows (default: every rank owns output rows, which the fused '
+                         'kernel stores to all ranks over NVLink -- half the bytes of an all-reduce, see DESIGN.md 5) or '
+                         'relations + all-reduce (the first design of the north star, kept for comparison)')
     args = ap.parse_args()
     if args.impl == 'reference-gpu':
         run_reference_gpu(args)

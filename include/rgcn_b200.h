@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 12
+#define RGCN_ABI_VERSION 14
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
@@ -41,6 +41,7 @@ extern "C" {
 #define RGCN_FUSE_REC_WORDS 36        /* int32 words per tile record of rgcn_fused.rec (144 bytes) */
 #define RGCN_FUSE_AHEAD 8             /* a tile record names the relation of the tile this many places later */
 #define RGCN_FUSE_MAX_ITEM_TILES (1 << 20)  /* upper bound on rgcn_graph.fuse_item_tiles */
+#define RGCN_MAX_PEERS 8              /* ranks of one NVLink domain a row-sharded forward can store to */
 
 typedef void* rgcn_stream_t;
 
@@ -248,6 +249,19 @@ typedef struct rgcn_params {
     const float* bias;      /* (O) or NULL */
     const float* self_mask; /* (N, O) or NULL: dropout mask on the transformed features of relation R'-1
                                ('schlichtkrull-dropout', layers.py:545-546) */
+    int32_t out_dtype;      /* rgcn_forward only: enum rgcn_dtype of `out`.  RGCN_BF16 is accepted on the fused row-block
+                               path only (bf16 features, a usable ff list without split blocks): a row-sharded layer
+                               writes its rows straight into the bf16 all-gather buffer */
+    int32_t pad_;
+    int64_t row_lo;         /* rgcn_forward only, fused row-block path: write output rows [row_lo, row_hi) only */
+    int64_t row_hi;         /* (multiples of fuse_rows; 0, 0 = all rows).  The plan must hold no edge into other rows */
+    void* peer_out[8];      /* (RGCN_MAX_PEERS entries) rgcn_forward only, fused row-block path with a bf16 output: when num_peer_out > 0
+                               every output row is stored to the same offset of ALL these (N, 64) bf16 buffers instead
+                               of `out` -- the symmetric exchange buffers of the ranks of a row-sharded layer, mapped
+                               over NVLink (peer-to-peer stores issued by the kernel's flush: the all-gather of the
+                               output rows is part of the kernel).  The caller synchronises the ranks afterwards. */
+    int32_t num_peer_out;
+    int32_t pad2_;
 } rgcn_params;
 
 typedef struct rgcn_grads { /* NULL = gradient not wanted; buffers are overwritten, not accumulated */
@@ -345,6 +359,10 @@ int rgcn_sample_edge_neighborhood(const int32_t* adj_ptr, const int32_t* adj, in
  * sample or the tail of a dropout permutation -> the (n, 3) graph.  Out-of-range indices are counted in status. */
 int rgcn_take_triples(const int64_t* triples, int64_t num_rows, const void* index, int index_is_int64, int64_t n,
                       int64_t* out, int32_t* status, rgcn_stream_t stream);
+
+/* out[i] = (float) in[i] for i < n: widens the bf16 exchange buffer of a row-sharded layer to the fp32 output the layer
+ * returns (streaming 16-byte loads / stores).  n must be a multiple of 8, pointers 16-byte aligned. */
+int rgcn_widen_rows(const void* in_bf16, int64_t n, float* out, rgcn_stream_t stream);
 
 /* number of kernels the engine has launched on this process since load (bench.py's gpu_launches) */
 int64_t rgcn_launch_count(void);

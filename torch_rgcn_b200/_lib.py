@@ -48,7 +48,9 @@ class Params(C.Structure):
                 ('in_dim', _i64), ('out_dim', _i64), ('num_bases', _i64), ('num_blocks', _i64),
                 ('num_block_rels', _i64),
                 ('weights', _p), ('bases', _p), ('comps', _p), ('blocks', _p), ('blocks_self', _p),
-                ('bias', _p), ('self_mask', _p)]
+                ('bias', _p), ('self_mask', _p), ('out_dtype', C.c_int32), ('pad_', C.c_int32),
+                ('row_lo', _i64), ('row_hi', _i64), ('peer_out', _p * 8), ('num_peer_out', C.c_int32),
+                ('pad2_', C.c_int32)]
 
 
 class Grads(C.Structure):
@@ -95,6 +97,7 @@ def _load():
         'rgcn_backward': (C.c_int, [C.POINTER(Graph), C.POINTER(Params), _p, C.c_int, _p, C.POINTER(Grads), _p,
                                     C.c_size_t, _p]),
         'rgcn_shard_plan': (C.c_int, [_p, _i64, C.c_int32, _p]),
+        'rgcn_widen_rows': (C.c_int, [_p, _i64, _p, _p]),
         'rgcn_distmult_forward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
         'rgcn_distmult_backward': (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
         'rgcn_distmult_penalty_workspace_bytes': (C.c_size_t, [_i64, _i64]),
@@ -123,7 +126,7 @@ lib = _load()
 EXPORTS = ['rgcn_last_error', 'rgcn_abi_version', 'rgcn_launch_count', 'rgcn_add_inverse_and_self',
            'rgcn_generate_inverses', 'rgcn_lp_triples_plus', 'rgcn_stack_matrices', 'rgcn_sum_sparse',
            'rgcn_block_diag', 'rgcn_graph_workspace_bytes', 'rgcn_tile_items_bound', 'rgcn_tile_steps_len', 'rgcn_fused_items_bound', 'rgcn_graph_build', 'rgcn_forward_workspace_bytes',
-           'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan',
+           'rgcn_forward', 'rgcn_backward_workspace_bytes', 'rgcn_backward', 'rgcn_shard_plan', 'rgcn_widen_rows',
            'rgcn_distmult_forward', 'rgcn_distmult_backward', 'rgcn_distmult_penalty_workspace_bytes',
            'rgcn_distmult_penalty', 'rgcn_distmult_penalty_backward', 'rgcn_corrupt_triples',
            'rgcn_rank_filter_workspace_bytes', 'rgcn_rank_build_filter', 'rgcn_rank_workspace_bytes', 'rgcn_rank_triples',

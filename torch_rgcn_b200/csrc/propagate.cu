@@ -214,6 +214,31 @@ int max_chunks(const Shape& s) { return (int)(s.nnz / RGCN_CHUNK_EDGES + s.Rp); 
 
 }  // namespace
 
+namespace {
+__global__ void k_widen_bf16(const uint4* __restrict__ in, int64_t n8, float4* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 v;
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + i));
+        const float4 a = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                                     __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+        const float4 b = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u),
+                                     __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
+        __stcs(out + 2 * i, a);
+        __stcs(out + 2 * i + 1, b);
+    }
+}
+}  // namespace
+
+extern "C" int rgcn_widen_rows(const void* in, int64_t n, float* out, rgcn_stream_t stream) {
+    RGCN_REQUIRE(n >= 0 && n % 8 == 0 && (n == 0 || (in && out)), RGCN_ERR_ARG, "rgcn_widen_rows: n must be a multiple of 8");
+    RGCN_REQUIRE(((uintptr_t)in | (uintptr_t)out) % 16 == 0, RGCN_ERR_ARG, "rgcn_widen_rows: pointers must be 16-byte aligned");
+    if (n == 0) return RGCN_OK;
+    const int64_t n8 = n / 8;
+    const int grid = (int)(n8 / 256 + 1 < (int64_t)kNumSMs * 16 ? n8 / 256 + 1 : (int64_t)kNumSMs * 16);
+    RGCN_LAUNCH(k_widen_bf16, grid, 256, 0, (cudaStream_t)stream, static_cast<const uint4*>(in), n8, reinterpret_cast<float4*>(out));
+    return RGCN_OK;
+}
+
 extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p, int x_dtype) {
     Shape s;
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
@@ -254,10 +279,26 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         A.form = RGCN_W_DENSE; A.W = weff;
     }
     const bool bf16 = x_dtype == RGCN_BF16 && !p->featureless;
+    RGCN_REQUIRE(p->out_dtype == RGCN_F32 || p->out_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_forward: unknown out_dtype %d",
+                 p->out_dtype);
+    const bool ranged = p->row_lo != 0 || p->row_hi != 0;
     if (fused_path(g, p, s, bf16, false)) {
         void* fws = carve.take<char>(fused_ws_bytes(s.Rp));
-        return launch_fused_rows<float>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X), out, fws, st);
+        if (ranged)
+            RGCN_REQUIRE(p->row_lo >= 0 && p->row_lo < p->row_hi && p->row_lo % g->fuse_rows == 0 &&
+                             (p->row_hi % g->fuse_rows == 0 || p->row_hi >= s.N), RGCN_ERR_ARG,
+                         "rgcn_forward: row range [%lld, %lld) must be cut at multiples of fuse_rows %lld",
+                         (long long)p->row_lo, (long long)p->row_hi, (long long)g->fuse_rows);
+        const int64_t lo = ranged ? p->row_lo : 0, hi = ranged ? p->row_hi : s.N;
+        RGCN_REQUIRE(p->num_peer_out == 0 || p->out_dtype == RGCN_BF16, RGCN_ERR_ARG, "rgcn_forward: peer_out needs a bf16 output");
+        if (p->out_dtype == RGCN_BF16)
+            return launch_fused_rows<__nv_bfloat16>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X),
+                                                    reinterpret_cast<__nv_bfloat16*>(out), fws, st, lo, hi, p->peer_out,
+                                                    p->num_peer_out);
+        return launch_fused_rows<float>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X), out, fws, st, lo, hi);
     }
+    RGCN_REQUIRE(p->out_dtype == RGCN_F32 && !ranged && p->num_peer_out == 0, RGCN_ERR_UNSUPPORTED,
+                 "rgcn_forward: a bf16 output / an output row range / peer stores need the fused row-block path");
     if (tiled_path(g, p, s, bf16)) {
         int32_t* counters = reinterpret_cast<int32_t*>(carve.take<char>(tiled_counter_bytes(g->num_tiles)));
         __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(tiled_ring_bytes(g, s.O)));

@@ -80,6 +80,9 @@ struct RbArgs {
     const uint4* wfrag;        // [(p * 4 + b) * 32 + lane]: B fragments of the two n8 halves of block b
     const float* bias;         // initial value of the accumulators of unshared items, or NULL
     const unsigned char* src;  // the gathered bf16 matrix (N, 64), used by the cp.async.bulk fallback
+    int item_lo, item_hi;      // work items [item_lo, item_hi) are processed (a row range of a sharded layer)
+    void* peers[RGCN_MAX_PEERS];   // bf16 output: the exchange buffers of all ranks (peer-to-peer stores), see rgcn_params
+    int n_peers;
 };
 
 __host__ __device__ inline size_t rb_smem_bytes(int fuse_rows, int nstage, bool gather4) {
@@ -204,19 +207,24 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     const uint32_t empty0 = full0 + (uint32_t)NS * 8u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- this CTA's share: a contiguous range of work items holding ~1/gridDim of the tiles
+    // ---- this CTA's share: a contiguous range of work items holding ~1/gridDim of the work
     const int4* items = reinterpret_cast<const int4*>(A.items);
-    auto first_item_at = [&](long long tile) {                          // first item whose first tile is >= tile
-        int lo = 0, hi = A.n_items;
+    // Cut by weight = tiles + items: item i starts at weight (first tile of i) + i, so both long items and runs of
+    // empty items (row blocks without edges still have to write their bias rows) spread over the CTAs.
+    const int IL = A.item_lo, IH = A.item_hi;
+    auto first_item_at = [&](long long w) {                             // first item of [IL, IH) with start weight >= w
+        int lo = IL, hi = IH;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if ((long long)__ldg(&items[mid].y) < tile) lo = mid + 1; else hi = mid;
+            if ((long long)__ldg(&items[mid].y) + mid < w) lo = mid + 1; else hi = mid;
         }
         return lo;
     };
+    const long long w_lo = (long long)(IL < A.n_items ? __ldg(&items[IL].y) : A.total_tiles) + IL;
+    const long long w_hi = (long long)(IH < A.n_items ? __ldg(&items[IH].y) : A.total_tiles) + IH;
     const int G = gridDim.x, c = blockIdx.x;
-    const int i0 = first_item_at((long long)A.total_tiles * c / G);
-    const int i1 = (c == G - 1) ? A.n_items : first_item_at((long long)A.total_tiles * (c + 1) / G);
+    const int i0 = c == 0 ? IL : first_item_at(w_lo + (w_hi - w_lo) * c / G);
+    const int i1 = c == G - 1 ? IH : first_item_at(w_lo + (w_hi - w_lo) * (c + 1) / G);
     const int tile_begin = i0 < A.n_items ? __ldg(&items[i0].y) : A.total_tiles;
     const int tile_end = i1 < A.n_items ? __ldg(&items[i1].y) : A.total_tiles;
     const int n_stages = (tile_end - tile_begin + kRbStageTiles - 1) / kRbStageTiles;
@@ -300,13 +308,15 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     const uint4* wmine = A.wfrag + (size_t)b * 32 + lane;
     const int FR = A.fuse_rows;
 
-    // accumulator (re)initialisation and flush: 16 consecutive threads handle one 256-byte row
+    // accumulator (re)initialisation and flush: 16 consecutive threads handle one 256-byte row (fp32 output) or 8
+    // threads one 128-byte row (bf16 output, 16-byte stores)
     const int fc4 = ctid & 15;                                          // float4 column of this thread in a row
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias) + fc4);
-    auto acc_addr = [&](int r) {                                        // un-swizzled float4 fc4 of local row r
-        return acc0 + (uint32_t)r * 256u + (uint32_t)((((fc4 >> 2) ^ (r & 1)) << 6) | ((fc4 & 3) << 4));
+    auto acc_addr_c = [&](int r, int c4) {                              // un-swizzled float4 c4 of local row r
+        return acc0 + (uint32_t)r * 256u + (uint32_t)((((c4 >> 2) ^ (r & 1)) << 6) | ((c4 & 3) << 4));
     };
+    auto acc_addr = [&](int r) { return acc_addr_c(r, fc4); };
     int cur = i0;
     int4 it = cur < i1 ? __ldg(&items[cur]) : make_int4(0, 0x7fffffff, 0x7fffffff, 0);
     if (turn == 0)
@@ -320,23 +330,39 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
         const long long row0 = (long long)item.x * FR;
         const int nrows = (int)min((long long)FR, A.N - row0);
         const float4 init = nxt_shared ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4;
-        for (int r = ctid >> 4; r < FR; r += 8) {
-            const uint32_t a = acc_addr(r);
-            if (r < nrows) {
-                const float4 v = lds128(a);
-                const size_t o = (size_t)(row0 + r) * kRbWidth + 4 * fc4;
-                if (!item.w) {
-                    if constexpr (sizeof(OT) == 2) {
-                        *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        if constexpr (sizeof(OT) == 2) {
+            // bf16 rows: 8 threads per row, two float4 columns each -> one 16-byte store per thread and destination;
+            // with peer buffers the row goes to every rank's exchange buffer (NVLink peer-to-peer stores)
+            const int c8 = ctid & 7;
+            for (int r = ctid >> 3; r < FR; r += 16) {
+                const uint32_t a0 = acc_addr_c(r, 2 * c8), a1 = acc_addr_c(r, 2 * c8 + 1);
+                if (r < nrows && !item.w) {
+                    const float4 v = lds128(a0), w = lds128(a1);
+                    const uint4 pk = make_uint4(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w), pack_bf16x2(w.x, w.y),
+                                                pack_bf16x2(w.z, w.w));
+                    const size_t o = (size_t)(row0 + r) * kRbWidth + 8 * c8;
+                    if (A.n_peers == 0) {
+                        *reinterpret_cast<uint4*>(out + o) = pk;
                     } else {
-                        *reinterpret_cast<float4*>(out + o) = v;
+#pragma unroll 1
+                        for (int q = 0; q < A.n_peers; ++q)
+                            *reinterpret_cast<uint4*>(static_cast<OT*>(A.peers[q]) + o) = pk;
                     }
-                } else {
-                    if constexpr (sizeof(OT) == 4)                      // split blocks are never routed to a bf16 output
-                        atomicAdd(reinterpret_cast<float4*>(out + o), v);
                 }
             }
-            sts128(a, init);
+            named_sync(1 + turn, kRbBlocks * 32);                       // all rows read before they are re-initialised
+            for (int r = ctid >> 4; r < FR; r += 8) sts128(acc_addr(r), init);
+        } else {
+            for (int r = ctid >> 4; r < FR; r += 8) {
+                const uint32_t a = acc_addr(r);
+                if (r < nrows) {
+                    const float4 v = lds128(a);
+                    const size_t o = (size_t)(row0 + r) * kRbWidth + 4 * fc4;
+                    if (!item.w) *reinterpret_cast<float4*>(out + o) = v;
+                    else atomicAdd(reinterpret_cast<float4*>(out + o), v);
+                }
+                sts128(a, init);
+            }
         }
         named_sync(1 + turn, kRbBlocks * 32);
     };
@@ -546,7 +572,8 @@ inline RbTuning rb_tuning() {
 // W: (R', 4, 16, 16) blocks.  out: (N, 64) fp32 or bf16 (bf16 only when the list has no split blocks).
 template <typename OT>
 inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W, const float* bias,
-                             const __nv_bfloat16* src, OT* out, void* ws, cudaStream_t st) {
+                             const __nv_bfloat16* src, OT* out, void* ws, cudaStream_t st, int64_t row_lo = 0,
+                             int64_t row_hi = -1, void* const* peers = nullptr, int n_peers = 0) {
     const rgcn_fused& fl = backward ? g->fb : g->ff;
     const int n_items = (int)g->fuse_items[backward ? 1 : 0];
     const int n_split = (int)g->fuse_split[backward ? 1 : 0];
@@ -595,8 +622,23 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
     A.col = fl.col; A.rec = fl.rec; A.items = fl.items; A.n_items = n_items; A.total_tiles = total_tiles;
     A.fuse_rows = FR; A.nstage = nstage; A.N = (long long)g->num_nodes;
     A.wfrag = frag; A.bias = bias; A.src = reinterpret_cast<const unsigned char*>(src);
+    // output rows [row_lo, row_hi): the work items of those row blocks.  Items are listed block by block; a range cut at
+    // block boundaries is a contiguous item range only if no block is split, which is what a row-sharded caller has.
+    const int64_t NB = (g->num_nodes + FR - 1) / FR;
+    if (row_hi < 0 || row_hi > g->num_nodes) row_hi = g->num_nodes;
+    A.item_lo = 0; A.item_hi = n_items;
+    RGCN_REQUIRE(n_peers >= 0 && n_peers <= RGCN_MAX_PEERS && (n_peers == 0 || (sizeof(OT) == 2 && n_split == 0)), RGCN_ERR_ARG,
+                 "fused rows: peer stores need a bf16 output, unsplit blocks and at most %d peers", RGCN_MAX_PEERS);
+    A.n_peers = n_peers;
+    for (int q = 0; q < n_peers; ++q) A.peers[q] = peers[q];
+    if (row_lo > 0 || row_hi < g->num_nodes) {
+        RGCN_REQUIRE(n_split == 0 && n_items == NB, RGCN_ERR_UNSUPPORTED, "fused rows: a row range needs unsplit row blocks");
+        A.item_lo = (int)(row_lo / FR);
+        A.item_hi = (int)((row_hi + FR - 1) / FR);
+    }
     int grid = kNumSMs * ctas;
-    if (grid > n_items) grid = n_items;
+    if (grid > A.item_hi - A.item_lo) grid = A.item_hi - A.item_lo;
+    if (grid < 1) return RGCN_OK;
     auto go = [&](auto kernel) -> int {
         RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RGCN_LAUNCH(kernel, grid, kRbThreads, smem, st, tm, A, out);

@@ -208,13 +208,156 @@ class _RowShardedApply(torch.autograd.Function):
         return (None, g_feat, *g_params)
 
 
+class _Exchange:
+    """Symmetric (rows, 64) bf16 buffers of a row-sharded layer: allocated with torch's symmetric-memory allocator and
+    mapped on every rank of the NVLink domain, so a rank can store (kernel) or copy (copy engine) its rows straight
+    into every peer's buffer.  Two buffers per direction, used alternately: a rank that is one step ahead writes the
+    other buffer, and the barrier that ends every exchange keeps it from getting two steps ahead, so no barrier is
+    needed before the writes.  slot(direction) -> (local buffer, handle, peer views, peer pointers)."""
+
+    def __init__(self, rows, device, group):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.rows = rows
+        self.slots = [[], []]                    # [direction][parity]
+        self.step = [0, 0]
+        for direction in range(2):
+            for _ in range(2):
+                t = symm.empty(rows, 64, dtype=torch.bfloat16, device=device)
+                h = symm.rendezvous(t, pg)
+                peers = [h.get_buffer(q, (rows, 64), torch.bfloat16) for q in range(h.world_size)]
+                self.slots[direction].append((t, h, peers, [int(x) for x in h.buffer_ptrs]))
+
+    def slot(self, direction):
+        k = self.step[direction]
+        self.step[direction] = k + 1
+        return self.slots[direction][k & 1]
+
+    @staticmethod
+    def create(rows, device, group):
+        """None when symmetric memory cannot be set up (no peer access, a CPU group): callers use NCCL instead."""
+        if os.environ.get('RGCN_SHARD_COMM', 'symm') != 'symm' or dist.get_world_size(group) > 8:
+            return None
+        try:
+            return _Exchange(rows, device, group)
+        except Exception as exc:  # noqa: BLE001
+            if dist.get_rank(group) == 0:
+                print(f'torch_rgcn_b200: symmetric memory unavailable ({type(exc).__name__}: {str(exc)[:200]}); '
+                      f'row-sharded layers fall back to NCCL all-gathers', flush=True)
+            return None
+
+
+class _RowShardedFused(torch.autograd.Function):
+    """Row-sharded layer on the fused row-block path (bf16 features, 64 -> 64, four blocks).
+
+    Rows are owned in `chunks` interleaved pieces per rank (piece k of rank r = row blocks [(k W + r) cb, (k W + r + 1) cb)),
+    so that piece k of all ranks is one contiguous slab of the bf16 exchange buffer.  forward: for every piece the fused
+    kernel writes this rank's rows straight into the slab (bf16 output, row range) and an asynchronous in-place
+    all-gather of the slab starts at once: the NVLink transfer of piece k overlaps the gather kernel of piece k + 1.
+    backward: the two-phase kernels over the edges whose SOURCE row this rank owns give complete feature-gradient rows
+    (bf16) and partial parameter gradients; the rows are all-gathered slab by slab, the parameter gradients all-reduced.
+    """
+
+    @staticmethod
+    def forward(ctx, shard, features, blocks, bias):
+        import ctypes as C
+        from .functional import _params_struct, _f32c
+        N, W, r, cb, H, nch = shard.num_nodes, shard.world, shard.rank, shard.chunk_blocks, shard.block_rows, shard.chunks
+        dev = features.device
+        slab = W * cb * H
+        buf = torch.empty(nch * slab, 64, dtype=torch.bfloat16, device=dev)
+        feats = features.contiguous()
+        wb, bs = _f32c(blocks), _f32c(bias)
+        plan = shard._plan_f
+        p = _params_struct('block', False, 64, 64, None, None, None, wb, None, bs, None)
+        p.out_dtype = _lib.BF16
+        ws_bytes = _lib.lib.rgcn_forward_workspace_bytes(C.byref(plan.c), C.byref(p), _lib.BF16)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        ex = shard._exchange
+        if ex is not None:
+            # ONE kernel: the flush stores every output row of this rank to all ranks' exchange buffers over NVLink
+            # (peer-to-peer stores, rgcn_params.peer_out); the barriers order it against the peers' reads and writes
+            buf, h, _peers, ptrs = ex.slot(0)
+            lo = r * cb * H
+            out = torch.empty(N, 64, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                if lo < N:
+                    p.row_lo, p.row_hi = lo, min(lo + cb * H, N)
+                    p.num_peer_out = W
+                    for q in range(W):
+                        p.peer_out[q] = ptrs[q]
+                    _lib.check(_lib.lib.rgcn_forward(C.byref(plan.c), C.byref(p), _lib.ptr(feats), _lib.BF16,
+                                                     _lib.ptr(buf), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+                h.barrier(channel=0)                     # every rank's rows have arrived
+                _lib.check(_lib.lib.rgcn_widen_rows(_lib.ptr(buf), N * 64, _lib.ptr(out), _lib.stream_ptr()))
+            ctx.shard = shard
+            ctx.save_for_backward(feats, blocks, bias)
+            return out
+        works = []
+        with torch.cuda.device(dev):
+            for k in range(nch):
+                lo = (k * W + r) * cb * H
+                if lo < N:
+                    p.row_lo, p.row_hi = lo, min(lo + cb * H, N)
+                    _lib.check(_lib.lib.rgcn_forward(C.byref(plan.c), C.byref(p), _lib.ptr(feats), _lib.BF16, _lib.ptr(buf),
+                                                     _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+                works.append(dist.all_gather_into_tensor(buf[k * slab:(k + 1) * slab], buf[lo:lo + cb * H],
+                                                         group=shard.group, async_op=True))
+        for w in works:
+            w.wait()
+        ctx.shard = shard
+        ctx.save_for_backward(feats, blocks, bias)
+        return buf[:N].float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        shard = ctx.shard
+        feats, blocks, bias = ctx.saved_tensors
+        N, W, r, cb, H, nch = shard.num_nodes, shard.world, shard.rank, shard.chunk_blocks, shard.block_rows, shard.chunks
+        need = ctx.needs_input_grad                      # (shard, features, blocks, bias)
+        shard.param_names = ['blocks', 'bias']
+        g_feat, (g_blocks, g_bias) = shard.backward_local(feats, [blocks, bias], grad_out.contiguous(), need[1],
+                                                          [need[2], need[3]])
+        works = []
+        if g_blocks is not None:
+            works.append(dist.all_reduce(g_blocks, op=dist.ReduceOp.SUM, group=shard.group, async_op=True))
+        gx = None
+        ex = shard._exchange
+        if g_feat is not None and ex is not None:
+            # copy engines push this rank's feature-gradient rows into every rank's exchange buffer (no SMs involved)
+            buf, h, peers, _ptrs = ex.slot(1)
+            lo, hi = r * cb * H, min((r + 1) * cb * H, N)
+            with torch.cuda.device(g_feat.device):
+                if lo < N:
+                    for q in range(W):
+                        peers[(r + q) % W][lo:hi].copy_(g_feat[lo:hi], non_blocking=True)
+                h.barrier(channel=0)
+            gx = buf[:N].clone()
+        elif g_feat is not None:
+            slab = W * cb * H
+            buf = torch.empty(nch * slab, 64, dtype=g_feat.dtype, device=g_feat.device)
+            for k in range(nch):
+                lo = (k * W + r) * cb * H
+                hi = min(lo + cb * H, N)
+                if lo < N:
+                    buf[lo:hi].copy_(g_feat[lo:hi])
+                works.append(dist.all_gather_into_tensor(buf[k * slab:(k + 1) * slab], buf[lo:lo + cb * H],
+                                                         group=shard.group, async_op=True))
+            gx = buf[:N]
+        for w in works:
+            w.wait()
+        return None, gx, g_blocks, g_bias
+
+
 class RowShardedNC(torch.nn.Module):
     """Runs a RelationalGraphConvolutionNC with the OUTPUT ROWS sharded over the ranks (see the block comment above).
 
     Same contract as RelationShardedNC: every rank constructs the same layer and passes the same features; the output
-    and, after backward, all gradients are identical on all ranks (no sync_parameter_grads needed)."""
+    and, after backward, all gradients are identical on all ranks (no sync_parameter_grads needed).  Layers the
+    fused row-block kernel serves (bf16 features, 64 -> 64, four blocks) take the overlapped path of
+    _RowShardedFused; every other layer the generic path (_RowShardedApply)."""
 
-    def __init__(self, layer, group=None):
+    def __init__(self, layer, group=None, chunks=None):
         super().__init__()
         self.layer = layer
         self.group = group
@@ -224,25 +367,50 @@ class RowShardedNC(torch.nn.Module):
         self.rows_per, ranges = plan_row_shards(layer.num_nodes, self.world)
         self.lo, self.hi = ranges[self.rank]
         self.out_comm_dtype = self.grad_comm_dtype = None
+        self.chunks = int(chunks if chunks is not None else os.environ.get('RGCN_SHARD_CHUNKS', '2'))
         self._plans = None
+        self._exchange = None
 
     def sync_parameter_grads(self):
         """Nothing to do (kept for interface parity with RelationShardedNC)."""
 
+    def _fused_rows(self, features):
+        """Block height of the fused row-block kernel if this layer takes the overlapped path, else 0."""
+        return self.layer._fuse_rows(features)
+
+    def row_owner_mask(self, rows, block_rows, chunk_blocks):
+        """Rows owned by this rank under the interleaved-piece ownership of _RowShardedFused."""
+        return ((rows // block_rows) // chunk_blocks) % self.world == self.rank
+
     def _local_plans(self, device, features):
         L = self.layer
         tile_edges = L._tile_edges(features)
-        kw = dict(tile_edges=tile_edges, ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')),
-                  fuse_rows=L._fuse_rows(features), fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')), fuse_dirs=_fuse_dirs())
-        key = (str(device), tile_edges, kw['fuse_rows'])
+        H = self._fused_rows(features)
+        kw = dict(tile_edges=tile_edges, ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')))
+        key = (str(device), tile_edges, H, self.chunks)
         if self._plans is None or self._plans[0] != key:
             tp = L.triples.to(device)
             full = L._plan(device)                               # per-edge weights of the FULL graph, caller order
             val = full.val[:full.nnz]
-            fwd_mask = partition_edges_by_rows(tp, 0, self.lo, self.hi)
-            bwd_mask = partition_edges_by_rows(tp, 2, self.lo, self.hi)
+            if H > 0:
+                nblocks = (L.num_nodes + H - 1) // H
+                self.block_rows = H
+                # symmetric memory: one contiguous piece per rank, exchanged by the kernel itself / the copy engines;
+                # otherwise `chunks` interleaved pieces whose NCCL all-gathers overlap the next piece's kernel
+                cb1 = (nblocks + self.world - 1) // self.world
+                self._exchange = _Exchange.create(self.world * cb1 * H, device, self.group)
+                if self._exchange is not None:
+                    self.chunks = 1
+                self.chunk_blocks = (nblocks + self.world * self.chunks - 1) // (self.world * self.chunks)
+                fwd_mask = self.row_owner_mask(tp[:, 0], H, self.chunk_blocks)
+                bwd_mask = self.row_owner_mask(tp[:, 2], H, self.chunk_blocks)
+                fkw = dict(fuse_rows=H, fuse_item_tiles=1 << 20, fuse_dirs=1)      # unsplit blocks: row ranges = item ranges
+            else:
+                fwd_mask = partition_edges_by_rows(tp, 0, self.lo, self.hi)
+                bwd_mask = partition_edges_by_rows(tp, 2, self.lo, self.hi)
+                fkw = {}
             plan_f = GraphPlan(tp[fwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[fwd_mask],
-                               validate=False, **kw)
+                               validate=False, **kw, **fkw)
             plan_b = GraphPlan(tp[bwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[bwd_mask],
                                validate=False, **kw)
             L._plan_cache = None
@@ -303,6 +471,8 @@ class RowShardedNC(torch.nn.Module):
             names = names + ['bias']
         self.param_names = names
         bf16 = features is not None and features.dtype == torch.bfloat16
+        if self._fused_rows(features) > 0 and self._plan_f.fused_ok[0]:
+            return _RowShardedFused.apply(self, features, L.blocks, L.bias)
         self.out_comm_dtype = torch.bfloat16 if bf16 else None       # like RelationShardedNC: bf16 layers send bf16
         self.grad_comm_dtype = None                                  # the feature gradient already has the feature dtype
         return _RowShardedApply.apply(self, features, *[getattr(L, n) for n in names])
