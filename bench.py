@@ -469,18 +469,26 @@ def run_ours(args):
                           'unit': 'GB/s', 'frac': ach_s / peak},
         'clocks': clocks,
     }
+    syn = None
+    if args.workload == 'am64' and not args.skew and not args.no_subrecords and os.environ.get('RGCN_BENCH_SYN', '1') != '0':
+        # config 5 of BASELINE.json next to the headline, at every GPU count (all ranks take part)
+        del layer, X, G, flush, dX, dG, stageX, stageG
+        torch.cuda.empty_cache()
+        syn = syn_record(rank, world, dev, args.shard)
+        layer = X = G = flush = dX = dG = None
     if rank == 0:
+        if syn is not None:
+            line.setdefault('sub_records', {})['syn'] = syn
         if world == 1 and args.workload == 'am64' and not args.skew and not args.no_subrecords:
             # the two targets the north star quotes next to the headline: the fp32 (1e-4 parity) configuration of the
             # same graph, and the reference's own algorithm on this GPU at the largest scale that fits
-            del layer, X, G, flush, dX, dG
             torch.cuda.empty_cache()
-            sub = {'am16_fp32': engine_layer_record('am16', 10, 3)}
+            sub = line.setdefault('sub_records', {})
+            sub['am16_fp32'] = engine_layer_record('am16', 10, 3)
             ref_gpu = reference_gpu_record('am16', 0.25, 3, 1)
             sub['reference_gpu'] = ref_gpu
             if 'value' in ref_gpu:
                 sub['am16_fp32_vs_reference_gpu_per_edge'] = sub['am16_fp32']['value'] / ref_gpu['value']
-            line['sub_records'] = sub
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
@@ -1051,6 +1059,64 @@ def reference_gpu_record(workload, scale, steps, warmup):
 
 def run_reference_gpu(args):
     print(json.dumps(reference_gpu_record(args.workload, args.ref_scale, args.steps, args.warmup)), flush=True)
+
+
+def syn_record(rank, world, dev, shard_mode, steps=3, warmup=1):
+    """BASELINE configs[4] (synthetic 5M-node / 256-rel / 200M-edge layer, 512 -> 512, nb=32, bf16) as a sub-record of
+    every --gpus N line: device-resident fwd / bwd of the (row- or relation-) sharded layer, max over ranks."""
+    import torch.distributed as dist
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionNC
+    from torch_rgcn_b200.parallel import RelationShardedNC, RowShardedNC
+    wl = WORKLOADS['syn']
+    ok = torch.ones(1, device=dev)
+    rec = {'workload': wl['label'], 'name': 'syn', 'n_gpus': world, 'steps': steps, 'warmup': warmup}
+    try:
+        t, N, Rp, nnz = build_triples(wl, dev)
+        torch.manual_seed(2)
+        layer = RelationalGraphConvolutionNC(triples=t, num_nodes=N, num_relations=Rp, in_features=wl['in_f'],
+                                             out_features=wl['out_f'], decomposition=wl['decomp'],
+                                             vertical_stacking=wl['vertical']).to(dev)
+        if world > 1:
+            layer = RowShardedNC(layer) if shard_mode == 'rows' else RelationShardedNC(layer)
+        gen = torch.Generator(device=dev).manual_seed(1)
+        X = torch.randn(N, wl['in_f'], device=dev, generator=gen).to(torch.bfloat16)
+        G = torch.randn(N, wl['out_f'], device=dev, generator=gen)
+    except Exception as exc:  # noqa: BLE001  (out of memory while building: report, keep the headline line)
+        ok.zero_()
+        rec['error'] = f'{type(exc).__name__}: {str(exc)[:200]}'
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        rec.setdefault('error', 'another rank failed while building the workload')
+        return rec
+    tf = tb = 0.0
+    for k in range(warmup + steps):
+        x = X.detach().requires_grad_(True)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e[0].record()
+        out = layer(x)
+        e[1].record()
+        out.backward(G)
+        e[2].record()
+        torch.cuda.synchronize()
+        if k >= warmup:
+            tf += e[0].elapsed_time(e[1]) / steps
+            tb += e[1].elapsed_time(e[2]) / steps
+        del out, x
+    tt = torch.tensor([tf + tb, tf, tb], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, tf, tb = tt.tolist()
+    b_f, b_b, _ = algorithmic_bytes(wl, N, Rp, nnz)
+    rec.update({'nnz': nnz, 'ms_fwd': tf, 'ms_bwd': tb, 'value': nnz / (ms * 1e-3), 'unit': 'edges/s', 'scaling': 'strong',
+                'gather_model_gbs_step_per_gpu': (b_f + b_b) / world / (ms * 1e-3) / 1e9,
+                'note': 'X (5.1 GB) is far larger than L2; inputs larger than L2, no flush between steps'})
+    del layer, X, G
+    torch.cuda.empty_cache()
+    return rec
 
 
 def engine_layer_record(workload, steps, warmup):

@@ -253,8 +253,10 @@ typedef struct rgcn_params {
                                path only (bf16 features, a usable ff list without split blocks): a row-sharded layer
                                writes its rows straight into the bf16 all-gather buffer */
     int32_t pad_;
-    int64_t row_lo;         /* rgcn_forward only, fused row-block path: write output rows [row_lo, row_hi) only */
-    int64_t row_hi;         /* (multiples of fuse_rows; 0, 0 = all rows).  The plan must hold no edge into other rows */
+    int64_t row_lo;         /* rgcn_forward, fused row-block path: write output rows [row_lo, row_hi) only (multiples of */
+    int64_t row_hi;         /* fuse_rows; 0, 0 = all rows; the plan must hold no edge into other rows).  rgcn_backward,
+                               bf16 tensor-core path with a bf16 feature gradient: only the feature-gradient rows
+                               [row_lo, row_hi) are written (the plan must hold no edge out of other rows) */
     void* peer_out[8];      /* (RGCN_MAX_PEERS entries) rgcn_forward only, fused row-block path with a bf16 output: when num_peer_out > 0
                                every output row is stored to the same offset of ALL these (N, 64) bf16 buffers instead
                                of `out` -- the symmetric exchange buffers of the ranks of a row-sharded layer, mapped

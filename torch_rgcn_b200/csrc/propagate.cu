@@ -444,9 +444,14 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         if (gr->features) msg = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.nnz * s.I * 2)));
         rc = launch_rel_mma_bwd(R, static_cast<const __nv_bfloat16*>(X), gb16, msg, gr->blocks, max_chunks(s), st);
         if (rc) return rc;
-        if (gr->features && gx_bf16)
-            return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr,
-                                  static_cast<__nv_bfloat16*>(gr->features), g->s_long, g->status + 5, g->num_long_src, s.nnz, st);
+        if (gr->features && gx_bf16) {
+            // a row-sharded caller's plan holds only the edges out of rows [row_lo, row_hi): sum (and write) those rows only
+            const bool ranged = p->row_hi > p->row_lo && p->row_lo >= 0 && p->row_hi <= s.N;
+            const int64_t lo = ranged ? p->row_lo : 0, n = ranged ? p->row_hi - p->row_lo : s.N;
+            return launch_row_sum(g->s_rowptr + lo, n, s.I, msg, (const float*)nullptr,
+                                  static_cast<__nv_bfloat16*>(gr->features) + lo * s.I, g->s_long, g->status + 5,
+                                  g->num_long_src, s.nnz, st);
+        }
         if (gr->features)
             return launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, static_cast<float*>(gr->features),
                                   g->s_long, g->status + 5, g->num_long_src, s.nnz, st);

@@ -78,6 +78,9 @@ class _Propagate(torch.autograd.Function):
         need = ctx.needs_input_grad
         p = _params_struct(form, features is None, in_dim, out_dim, weights, bases, comps, blocks, blocks_self, bias,
                            self_mask)
+        rows = getattr(ctx, 'rows', None)        # a row-sharded caller needs (and its plan covers) only these rows
+        if rows is not None:
+            p.row_lo, p.row_hi = rows
 
         def alloc(flag, like, dtype=torch.float32):
             return torch.empty(like.shape, dtype=dtype, device=dev) if (flag and like is not None) else None

@@ -316,8 +316,9 @@ class _RowShardedFused(torch.autograd.Function):
         N, W, r, cb, H, nch = shard.num_nodes, shard.world, shard.rank, shard.chunk_blocks, shard.block_rows, shard.chunks
         need = ctx.needs_input_grad                      # (shard, features, blocks, bias)
         shard.param_names = ['blocks', 'bias']
+        own = (r * cb * H, min((r + 1) * cb * H, N)) if (shard._exchange is not None and r * cb * H < N) else None
         g_feat, (g_blocks, g_bias) = shard.backward_local(feats, [blocks, bias], grad_out.contiguous(), need[1],
-                                                          [need[2], need[3]])
+                                                          [need[2], need[3]], rows=own)
         works = []
         if g_blocks is not None:
             works.append(dist.all_reduce(g_blocks, op=dist.ReduceOp.SUM, group=shard.group, async_op=True))
@@ -429,7 +430,7 @@ class RowShardedNC(torch.nn.Module):
             return _Propagate.apply(self._plan_f, self._form, self._in_dim, self.layer.out_features, features,
                                     p['weights'], p['bases'], p['comps'], p['blocks'], None, p['bias'], None, True)
 
-    def backward_local(self, features, params, grad_out, need_features, need_params):
+    def backward_local(self, features, params, grad_out, need_features, need_params, rows=None):
         """The engine's backward over the source-row shard, through _Propagate.backward with a stand-in context (the
         engine keeps no forward state: it needs the plan, the inputs and the upstream gradient only)."""
         from types import SimpleNamespace
@@ -449,6 +450,7 @@ class RowShardedNC(torch.nn.Module):
             needs_input_grad=(False, False, False, False, bool(need_features and features is not None),
                               needs.get('weights', False), needs.get('bases', False), needs.get('comps', False),
                               needs.get('blocks', False), False, needs.get('bias', False), False, False))
+        ctx.rows = rows                                          # (lo, hi): only these feature-gradient rows are needed
         grads = _Propagate.backward(ctx, grad_out)
         by_name = dict(weights=grads[5], bases=grads[6], comps=grads[7], blocks=grads[8], bias=grads[10])
         return grads[4], [by_name[n] for n in self.param_names]
