@@ -139,7 +139,7 @@ typedef struct rgcn_tile_item {
     int32_t pad;
 } rgcn_tile_item;
 
-/* Optional fused row-block lists (bf16 features, four 16x16 blocks): rows are cut into blocks of `fuse_rows`
+/* Optional fused row-block lists (bf16 features, 16x16 blocks in groups of four): rows are cut into blocks of `fuse_rows`
  * consecutive rows whose fp32 output tile lives in shared memory; the edges of a block are sorted by
  * (relation, row parity, row) and every (block, relation) run is dealt over whole 16-entry tiles, so that one MMA
  * tile never mixes relations.  Tiles are numbered block by block; a block with more than fuse_item_tiles tiles is

@@ -202,8 +202,8 @@ bool tiled_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool 
 // list for this direction was built and fits (fuse_items > 0).
 bool fused_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool bf16, bool backward) {
     return bf16 && g->fuse_rows > 0 && g->fuse_items[backward ? 1 : 0] > 0 && !p->featureless &&
-           p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 && s.nb == 4 && s.bi == 16 &&
-           s.bo == 16;
+           p->form == RGCN_W_BLOCK && !p->blocks_self && !p->self_mask && s.nnz > 0 && s.nb >= 4 && s.nb % 4 == 0 &&
+           s.bi == 16 && s.bo == 16;
 }
 
 size_t tiled_ring_bytes(const rgcn_graph* g, int width) {
@@ -244,7 +244,7 @@ extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_p
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
     size_t bytes = 0;
     if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
-    if (fused_path(g, p, s, x_dtype == RGCN_BF16, false)) return bytes + fused_ws_bytes(s.Rp);
+    if (fused_path(g, p, s, x_dtype == RGCN_BF16, false)) return bytes + fused_ws_bytes(s.Rp, s.nb);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O) + wfrag_bytes(s.Rp, s.nb);
     RelShape rs; size_t msg = 0;
@@ -283,7 +283,7 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
                  p->out_dtype);
     const bool ranged = p->row_lo != 0 || p->row_hi != 0;
     if (fused_path(g, p, s, bf16, false)) {
-        void* fws = carve.take<char>(fused_ws_bytes(s.Rp));
+        void* fws = carve.take<char>(fused_ws_bytes(s.Rp, s.nb));
         if (ranged)
             RGCN_REQUIRE(p->row_lo >= 0 && p->row_lo < p->row_hi && p->row_lo % g->fuse_rows == 0 &&
                              (p->row_hi % g->fuse_rows == 0 || p->row_hi >= s.N), RGCN_ERR_ARG,
@@ -294,8 +294,9 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         if (p->out_dtype == RGCN_BF16)
             return launch_fused_rows<__nv_bfloat16>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X),
                                                     reinterpret_cast<__nv_bfloat16*>(out), fws, st, lo, hi, p->peer_out,
-                                                    p->num_peer_out);
-        return launch_fused_rows<float>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X), out, fws, st, lo, hi);
+                                                    p->num_peer_out, s.nb);
+        return launch_fused_rows<float>(g, false, p->blocks, p->bias, static_cast<const __nv_bfloat16*>(X), out, fws, st, lo, hi,
+                                        nullptr, 0, s.nb);
     }
     RGCN_REQUIRE(p->out_dtype == RGCN_F32 && !ranged && p->num_peer_out == 0, RGCN_ERR_UNSUPPORTED,
                  "rgcn_forward: a bf16 output / an output row range / peer stores need the fused row-block path");
@@ -352,7 +353,7 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
     }
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.I * 4);   // fp32 staging of a bf16 feature gradient
-    if (fused_path(g, p, s, x_dtype == RGCN_BF16, true)) return bytes + fused_ws_bytes(s.Rp);
+    if (fused_path(g, p, s, x_dtype == RGCN_BF16, true)) return bytes + fused_ws_bytes(s.Rp, s.nb);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
     // bf16 16x16-block tensor-core backward: bf16 feature-gradient messages, sized by the predicate rgcn_backward uses
@@ -412,11 +413,11 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
                 rc = launch_rel_mma_bwd(Rw, static_cast<const __nv_bfloat16*>(X), gb16, nullptr, gr->blocks, max_chunks(s), st);
                 if (rc) return rc;
             }
-            void* fws = carve.take<char>(fused_ws_bytes(s.Rp));
+            void* fws = carve.take<char>(fused_ws_bytes(s.Rp, s.nb));
             if (gx_bf16 && g->fuse_split[1] == 0)
                 return launch_fused_rows<__nv_bfloat16>(g, true, p->blocks, nullptr, gb16,
-                                                        static_cast<__nv_bfloat16*>(gr->features), fws, st);
-            rc = launch_fused_rows<float>(g, true, p->blocks, nullptr, gb16, gx_f32, fws, st);
+                                                        static_cast<__nv_bfloat16*>(gr->features), fws, st, 0, -1, nullptr, 0, s.nb);
+            rc = launch_fused_rows<float>(g, true, p->blocks, nullptr, gb16, gx_f32, fws, st, 0, -1, nullptr, 0, s.nb);
             if (rc) return rc;
             return finish_gx();
         }

@@ -58,7 +58,7 @@ constexpr int kRbTurns = 2;                             // consumer warps per co
 constexpr int kRbConsumers = kRbBlocks * kRbTurns;      // warps 0-7: warp = turn * 4 + block
 constexpr int kRbProducers = 4;                         // warps 8-11
 constexpr int kRbThreads = (kRbConsumers + kRbProducers) * 32;
-constexpr int kRbWidth = 64;                            // I == O == 4 blocks of 16
+constexpr int kRbWidth = 64;                            // columns one launch computes: 4 blocks of 16
 static_assert(kRbStageTiles * kRbTurns == RGCN_FUSE_AHEAD, "a tile record names the relation of the warp's next stage");
 
 // gathered rows in shared memory: 128-byte rows with the TMA 128-byte swizzle, or 144-byte rows (linear copies)
@@ -83,6 +83,9 @@ struct RbArgs {
     int item_lo, item_hi;      // work items [item_lo, item_hi) are processed (a row range of a sharded layer)
     void* peers[RGCN_MAX_PEERS];   // bf16 output: the exchange buffers of all ranks (peer-to-peer stores), see rgcn_params
     int n_peers;
+    int ld;                    // row pitch of the gathered matrix and of `out` in elements (the layer width, 64 * groups)
+    int col0;                  // first column of the 64-column group this launch computes
+    int rel_stride;            // uint4 entries between consecutive relations in wfrag (blocks per relation * 32)
 };
 
 __host__ __device__ inline size_t rb_smem_bytes(int fuse_rows, int nstage, bool gather4) {
@@ -154,17 +157,16 @@ __device__ __forceinline__ void mma_bf16_16816_z(float (&c)[4], const uint32_t (
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 
-// wfrag[(p * 4 + b) * 32 + lane] = {b0, b1 of half 0, b0, b1 of half 1} for lane (g = lane / 4, t = lane % 4):
+// wfrag[(p * nb + b) * 32 + lane] = {b0, b1 of half 0, b0, b1 of half 1} for lane (g = lane / 4, t = lane % 4):
 // half h multiplies by the 16 x 8 matrix whose column n is column 4 (n / 2) + 2 h + (n % 2) of block b, so that after
 // the two MMAs a lane holds columns 4 t .. 4 t + 3 of rows g and g + 8.  transpose = 0: B[k][c] = W[k][c] (forward);
-// 1: B[k][c] = W[c][k] (feature gradient).
-__global__ void k_pack_wfrag4(const float* __restrict__ W, int Rp, int transpose, uint4* __restrict__ frag) {
+// 1: B[k][c] = W[c][k] (feature gradient).  A launch of k_rowblock uses the four blocks of one 64-column group.
+__global__ void k_pack_wfrag4(const float* __restrict__ W, long long n_blocks, int transpose, uint4* __restrict__ frag) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)Rp * 128) return;
-    const int lane = (int)(i & 31), b = (int)((i >> 5) & 3);
-    const long long p = i >> 7;
+    if (i >= n_blocks * 32) return;
+    const int lane = (int)(i & 31);
     const int g = lane >> 2, t = lane & 3;
-    const float* wb = W + ((size_t)p * 4 + b) * 256;
+    const float* wb = W + (size_t)(i >> 5) * 256;
     auto at = [&](int k, int c) { return transpose ? wb[c * 16 + k] : wb[k * 16 + c]; };
     uint32_t r[4];
 #pragma unroll
@@ -178,7 +180,7 @@ __global__ void k_pack_wfrag4(const float* __restrict__ W, int Rp, int transpose
 
 // rows of split blocks start from the bias (or zero): their items add partial sums with atomics
 __global__ void k_fused_init_shared(const int32_t* __restrict__ items, int n_items, const int32_t* __restrict__ blk_tile,
-                                    int fuse_rows, long long N, const float* __restrict__ bias,
+                                    int fuse_rows, long long N, int width, const float* __restrict__ bias,
                                     float* __restrict__ out) {
     const int q = blockIdx.x;
     if (q >= n_items) return;
@@ -186,10 +188,10 @@ __global__ void k_fused_init_shared(const int32_t* __restrict__ items, int n_ite
     if (!it.w || it.y != __ldg(blk_tile + it.x)) return;        // only the first item of a split block
     const long long row0 = (long long)it.x * fuse_rows;
     const int nrows = (int)min((long long)fuse_rows, N - row0);
-    for (int i = threadIdx.x; i < nrows * (kRbWidth / 4); i += blockDim.x) {
-        const int c4 = i % (kRbWidth / 4);
+    for (int i = threadIdx.x; i < nrows * (width / 4); i += blockDim.x) {
+        const int c4 = i % (width / 4);
         const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(out + (size_t)row0 * kRbWidth)[i] = b;
+        reinterpret_cast<float4*>(out + (size_t)row0 * width)[i] = b;
     }
 }
 
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                              (uint32_t)nt * kRbRecBytes, fb);
                 }
                 __syncwarp();
-                if (go) tma_gather4(xdst + (uint32_t)(q & 3) * 512u, &tmap, fb, 0, cur.x, cur.y, cur.z, cur.w);
+                if (go) tma_gather4(xdst + (uint32_t)(q & 3) * 512u, &tmap, fb, A.col0, cur.x, cur.y, cur.z, cur.w);
             } else {
                 const int rows[4] = {cur.x, cur.y, cur.z, cur.w};
                 int n = 0;
@@ -289,7 +291,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (rows[k] >= 0)
-                            bulk_g2s(xdst + (uint32_t)((q & 3) * 4 + k) * XL::row_bytes, A.src + (size_t)rows[k] * 128, 128u, fb);
+                            bulk_g2s(xdst + (uint32_t)((q & 3) * 4 + k) * XL::row_bytes,
+                                     A.src + ((size_t)rows[k] * A.ld + A.col0) * 2, 128u, fb);
                 }
             }
             slot += NP;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     // threads one 128-byte row (bf16 output, 16-byte stores)
     const int fc4 = ctid & 15;                                          // float4 column of this thread in a row
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias) + fc4);
+    if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias + A.col0) + fc4);
     auto acc_addr_c = [&](int r, int c4) {                              // un-swizzled float4 c4 of local row r
         return acc0 + (uint32_t)r * 256u + (uint32_t)((((c4 >> 2) ^ (r & 1)) << 6) | ((c4 & 3) << 4));
     };
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                     const float4 v = lds128(a0), w = lds128(a1);
                     const uint4 pk = make_uint4(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w), pack_bf16x2(w.x, w.y),
                                                 pack_bf16x2(w.z, w.w));
-                    const size_t o = (size_t)(row0 + r) * kRbWidth + 8 * c8;
+                    const size_t o = (size_t)(row0 + r) * A.ld + A.col0 + 8 * c8;
                     if (A.n_peers == 0) {
                         *reinterpret_cast<uint4*>(out + o) = pk;
                     } else {
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                 const uint32_t a = acc_addr(r);
                 if (r < nrows) {
                     const float4 v = lds128(a);
-                    const size_t o = (size_t)(row0 + r) * kRbWidth + 4 * fc4;
+                    const size_t o = (size_t)(row0 + r) * A.ld + A.col0 + 4 * fc4;
                     if (!item.w) *reinterpret_cast<float4*>(out + o) = v;
                     else atomicAdd(reinterpret_cast<float4*>(out + o), v);
                 }
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     for (int j = 0; j < kRbStageTiles; ++j) {
         const long long tile = (long long)tile_begin + turn * kRbStageTiles + j;
         const int rel = tile < tile_end ? __ldg(A.rec + tile * RGCN_FUSE_REC_WORDS + 33) : 0;
-        wr[j] = __ldg(wmine + (size_t)rel * 128);
+        wr[j] = __ldg(wmine + (size_t)rel * A.rel_stride);
     }
 
     uint4 rv[kRbStageTiles];            // per tile {offset of row g | rank, val, offset of row g + 8 | rank, val}
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     int fslot = turn;                   // pipeline slot and phase parity of this warp's next front stage (NS >= 2)
     uint32_t fpar = 0;
     const unsigned char* wbytes = reinterpret_cast<const unsigned char*>(wmine);
+    const uint32_t wrel_bytes = (uint32_t)A.rel_stride * 16u;
     auto front_tile = [&](uint32_t xs, uint32_t rs, int j) {
         rv[j] = lds128u(rs + j * kRbRecBytes + g * 16);
         hd[j] = lds32(rs + j * kRbRecBytes + 128);
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
         mma_bf16_16816_z(d1, a, wr[j].z, wr[j].w);
         d[j][0] = d0[0]; d[j][1] = d0[1]; d[j][2] = d1[0]; d[j][3] = d1[1];
         d[j][4] = d0[2]; d[j][5] = d0[3]; d[j][6] = d1[2]; d[j][7] = d1[3];
-        wr[j] = __ldg(reinterpret_cast<const uint4*>(wbytes + (size_t)((uint32_t)(hd[j] & 0xffffff) * 2048u)));
+        wr[j] = __ldg(reinterpret_cast<const uint4*>(wbytes + (size_t)(uint32_t)(hd[j] & 0xffffff) * wrel_bytes));
     };
     auto front = [&](int s) {
         const int slot = fslot;
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-inline size_t fused_ws_bytes(int64_t Rp) { return align_up((size_t)Rp * 128 * sizeof(uint4)); }
+inline size_t fused_ws_bytes(int64_t Rp, int nb = 4) { return align_up((size_t)Rp * nb * 32 * sizeof(uint4)); }
 
 typedef CUresult (*rb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -569,11 +573,13 @@ inline RbTuning rb_tuning() {
     return r;
 }
 
-// W: (R', 4, 16, 16) blocks.  out: (N, 64) fp32 or bf16 (bf16 only when the list has no split blocks).
+// W: (R', nb, 16, 16) blocks, nb a multiple of 4; src (N, 16 nb) bf16; out: (N, 16 nb) fp32 or bf16 (bf16 only when the
+// list has no split blocks).  The layer is nb / 4 independent 64-column layers over the same graph (block-diagonal
+// weights): one launch of k_rowblock per 64-column group, all on the same lists.
 template <typename OT>
 inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W, const float* bias,
                              const __nv_bfloat16* src, OT* out, void* ws, cudaStream_t st, int64_t row_lo = 0,
-                             int64_t row_hi = -1, void* const* peers = nullptr, int n_peers = 0) {
+                             int64_t row_hi = -1, void* const* peers = nullptr, int n_peers = 0, int nb = 4) {
     const rgcn_fused& fl = backward ? g->fb : g->ff;
     const int n_items = (int)g->fuse_items[backward ? 1 : 0];
     const int n_split = (int)g->fuse_split[backward ? 1 : 0];
@@ -597,20 +603,23 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
     RGCN_REQUIRE(smem <= per_sm - reserve, RGCN_ERR_UNSUPPORTED,
                  "fused rows: %d stages with fuse_rows %d need %zu bytes of shared memory", nstage, FR, smem);
     Carver carve(ws);
-    uint4* frag = carve.take<uint4>((size_t)g->num_rels * 128);
-    RGCN_LAUNCH(k_pack_wfrag4, grid_for(g->num_rels * 128, 256), 256, 0, st, W, (int)g->num_rels, backward ? 1 : 0, frag);
+    RGCN_REQUIRE(nb >= 4 && nb % 4 == 0, RGCN_ERR_ARG, "fused rows: the number of 16x16 blocks must be a multiple of 4");
+    const int width = 16 * nb;
+    uint4* frag = carve.take<uint4>((size_t)g->num_rels * nb * 32);
+    RGCN_LAUNCH(k_pack_wfrag4, grid_for(g->num_rels * nb * 32, 256), 256, 0, st, W, (long long)g->num_rels * nb,
+                backward ? 1 : 0, frag);
     if (n_split > 0) {
         if constexpr (sizeof(OT) == 4)
             RGCN_LAUNCH(k_fused_init_shared, n_items, 256, 0, st, fl.items, n_items, fl.blk_tile, FR, (long long)g->num_nodes,
-                        bias, reinterpret_cast<float*>(out));
+                        width, bias, reinterpret_cast<float*>(out));
     }
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     if (tune.gather4) {
         rb_encode_fn enc = rb_encoder();
         RGCN_REQUIRE(enc, RGCN_ERR_CUDA, "fused rows: cuTensorMapEncodeTiled is not available from this driver");
-        const cuuint64_t gdim[2] = {(cuuint64_t)kRbWidth, (cuuint64_t)g->num_nodes};
-        const cuuint64_t gstr[1] = {(cuuint64_t)kRbWidth * 2};
+        const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)g->num_nodes};
+        const cuuint64_t gstr[1] = {(cuuint64_t)width * 2};
         const cuuint32_t box[2] = {(cuuint32_t)kRbWidth, 1};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(src), gdim, gstr, box, estr,
@@ -622,6 +631,7 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
     A.col = fl.col; A.rec = fl.rec; A.items = fl.items; A.n_items = n_items; A.total_tiles = total_tiles;
     A.fuse_rows = FR; A.nstage = nstage; A.N = (long long)g->num_nodes;
     A.wfrag = frag; A.bias = bias; A.src = reinterpret_cast<const unsigned char*>(src);
+    A.ld = width; A.rel_stride = nb * 32;
     // output rows [row_lo, row_hi): the work items of those row blocks.  Items are listed block by block; a range cut at
     // block boundaries is a contiguous item range only if no block is split, which is what a row-sharded caller has.
     const int64_t NB = (g->num_nodes + FR - 1) / FR;
@@ -641,7 +651,11 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
     if (grid < 1) return RGCN_OK;
     auto go = [&](auto kernel) -> int {
         RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RGCN_LAUNCH(kernel, grid, kRbThreads, smem, st, tm, A, out);
+        for (int cg = 0; cg < nb / 4; ++cg) {                           // one 64-column group per launch
+            A.col0 = 64 * cg;
+            A.wfrag = frag + (size_t)cg * 4 * 32;                       // blocks 4 cg .. 4 cg + 3 of every relation
+            RGCN_LAUNCH(kernel, grid, kRbThreads, smem, st, tm, A, out);
+        }
         return RGCN_OK;
     };
     return tune.gather4 ? go(k_rowblock<OT, true>) : go(k_rowblock<OT, false>);

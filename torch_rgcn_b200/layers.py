@@ -19,15 +19,20 @@ from .graph import GraphPlan
 from .utils import select_b_init, select_w_init, schlichtkrull_normal_
 from .decoder import DistMult                      # noqa: F401  (reference layers.py:9 defines it in this module)
 
-# RGCN_FUSED: '1' (default) routes the forward of bf16 64 -> 64 block layers to the fused row-block kernel
-# (propagate_fused.cuh) and keeps the two-phase tensor-core kernels (propagate_mma.cuh) for the backward, '2' also
-# computes the feature gradient with the fused kernel, '0' uses the two-phase kernels throughout
+# RGCN_FUSED: '1' (default) routes the forward of bf16 block layers with 16x16 blocks (width 64 .. 512) to the fused
+# row-block kernel (propagate_fused.cuh); the backward of a 64-wide layer keeps the two-phase tensor-core kernels
+# (propagate_mma.cuh), wider layers also compute the feature gradient with the fused kernel.  '2': fused feature
+# gradient for every width.  '0': two-phase / tiled kernels throughout.
 _FUSED_DEFAULT = '1'
 
 
-def _fuse_dirs():
-    """Lists the plan builds for the fused kernel: 1 = forward only, 3 = forward and feature gradient."""
-    return 3 if os.environ.get('RGCN_FUSED', _FUSED_DEFAULT) == '2' else 1
+def _fuse_dirs(width=64):
+    """Lists the plan builds for the fused kernel: 1 = forward only, 3 = forward and feature gradient.  By default the
+    feature gradient of a 64-wide layer stays with the fused two-phase backward (one gather serves both gradients,
+    1.54 vs 1.65 ms at am64); wider layers, whose messages would not fit and go through the tiled ring kernels instead,
+    take the fused kernel for the feature gradient too (synthetic 512-wide layer: 141 vs 230 ms)."""
+    mode = os.environ.get('RGCN_FUSED', _FUSED_DEFAULT)
+    return 3 if (mode == '2' or (mode == '1' and width > 64)) else 1
 
 
 def _unpack_decomposition(decomposition):
@@ -165,12 +170,14 @@ class RelationalGraphConvolutionNC(_PlanCacheMixin, Module):
         return max(tile_bytes // row_bytes, 4096) if tile_bytes > 0 else 0
 
     def _fuse_rows(self, features):
-        """Rows per block of the fused row-block kernel (bf16 features, four 16x16 blocks, i.e. 64 -> 64), 0 = off.
+        """Rows per block of the fused row-block kernel, 0 = off.  It serves bf16 features with 16x16 weight blocks in
+        groups of four (width 64, 128, ... 512: the layer is width / 64 independent 64-column layers over the same graph).
 
         RGCN_FUSED=0 disables it, RGCN_FUSE_ROWS overrides the block height (a multiple of 16; 640 rows x 64 fp32
         columns = 160 KB of the CTA's shared memory)."""
         if (features is None or features.dtype != torch.bfloat16 or self.weight_decomp != 'block' or
-                self.in_features != 64 or self.out_features != 64 or self.num_blocks != 4):
+                self.in_features != self.out_features or self.num_blocks % 4 != 0 or
+                self.in_features != 16 * self.num_blocks):
             return 0
         if os.environ.get('RGCN_FUSED', _FUSED_DEFAULT) == '0':
             return 0
@@ -189,7 +196,7 @@ class RelationalGraphConvolutionNC(_PlanCacheMixin, Module):
                              validate=self.validate_triples, tile_edges=tile_edges,
                              ring_depth=int(os.environ.get('RGCN_RING_DEPTH', '8')), fuse_rows=fuse_rows,
                              fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')),
-                             fuse_dirs=_fuse_dirs())
+                             fuse_dirs=_fuse_dirs(self.out_features or 64))
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

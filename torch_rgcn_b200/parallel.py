@@ -93,7 +93,7 @@ class RelationShardedNC(torch.nn.Module):
     def _local_plan(self, device, features=None):
         tile_edges = self.layer._tile_edges(features)
         fuse = dict(fuse_rows=self.layer._fuse_rows(features),
-                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')), fuse_dirs=_fuse_dirs())
+                    fuse_item_tiles=int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096')), fuse_dirs=_fuse_dirs(self.layer.out_features or 64))
         if (self._local is None or self._local.device != device or self._local.tile_edges != tile_edges or
                 self._local.fuse_rows != fuse['fuse_rows']):
             L = self.layer
@@ -376,8 +376,8 @@ class RowShardedNC(torch.nn.Module):
         """Nothing to do (kept for interface parity with RelationShardedNC)."""
 
     def _fused_rows(self, features):
-        """Block height of the fused row-block kernel if this layer takes the overlapped path, else 0."""
-        return self.layer._fuse_rows(features)
+        """Block height of the fused row-block kernel if this layer takes the overlapped 64-wide path, else 0."""
+        return self.layer._fuse_rows(features) if self.layer.out_features == 64 else 0
 
     def row_owner_mask(self, rows, block_rows, chunk_blocks):
         """Rows owned by this rank under the interleaved-piece ownership of _RowShardedFused."""
@@ -406,14 +406,21 @@ class RowShardedNC(torch.nn.Module):
                 fwd_mask = self.row_owner_mask(tp[:, 0], H, self.chunk_blocks)
                 bwd_mask = self.row_owner_mask(tp[:, 2], H, self.chunk_blocks)
                 fkw = dict(fuse_rows=H, fuse_item_tiles=1 << 20, fuse_dirs=1)      # unsplit blocks: row ranges = item ranges
+                bkw = {}
             else:
                 fwd_mask = partition_edges_by_rows(tp, 0, self.lo, self.hi)
                 bwd_mask = partition_edges_by_rows(tp, 2, self.lo, self.hi)
-                fkw = {}
+                fkw = bkw = {}
+                Hw = L._fuse_rows(features)                      # wider layers: fused kernels inside the generic path
+                if Hw > 0:
+                    item_tiles = int(os.environ.get('RGCN_FUSE_ITEM_TILES', '4096'))
+                    fkw = dict(fuse_rows=Hw, fuse_item_tiles=item_tiles, fuse_dirs=1)
+                    if _fuse_dirs(L.out_features) == 3:
+                        bkw = dict(fuse_rows=Hw, fuse_item_tiles=item_tiles, fuse_dirs=2)
             plan_f = GraphPlan(tp[fwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[fwd_mask],
                                validate=False, **kw, **fkw)
             plan_b = GraphPlan(tp[bwd_mask], L.num_nodes, L.num_relations, _lib.NORM_EXPLICIT, val=val[bwd_mask],
-                               validate=False, **kw)
+                               validate=False, **kw, **bkw)
             L._plan_cache = None
             self._plans = (key, plan_f, plan_b)
         return self._plans[1], self._plans[2]
