@@ -359,3 +359,21 @@ class RelationalGraphConvolutionLP(Module):
                 self_mask = self._test_self_mask.to(device)
         return rgcn_propagate(plan, 'block', self.in_features, self.out_features, features, blocks=self.blocks,
                               blocks_self=self.blocks_self, bias=self.bias, self_mask=self_mask)
+
+
+def graph_lp_layer(layer, triples, features):
+    """CUDA-graph the link-prediction layer for a fixed problem shape (reference layers.py:450-565 rebuilds its graph
+    every forward; here that is ~30 small kernels — augmentation, three radix sorts, decode, normalisation, the
+    propagation kernels — whose launch gaps, not their work, dominate a WN18-sized step).
+
+    Returns a callable `f(triples, features) -> out` that replays ONE captured graph for the forward and one for the
+    backward (`torch.cuda.make_graphed_callables`): same numerics and autograd behaviour as `layer(triples, features)`,
+    for inputs of the SAME shapes and dtypes as the samples (a training loop with a fixed sampled-graph size, or the
+    evaluation graph).  The layer must not need host decisions inside the forward: eval mode or no self-loop
+    dropout by node removal, and `validate_triples = False` (index validation is a host read-back)."""
+    assert isinstance(layer, RelationalGraphConvolutionLP)
+    assert not (layer.training and layer.edge_dropout is not None and layer.edge_dropout.get("self_loop", 0) and
+                layer.edge_dropout.get("self_loop_type") != 'schlichtkrull-dropout'), \
+        'self-loop dropout by node removal changes the edge count per step: it cannot be captured in a CUDA graph'
+    layer.validate_triples = False
+    return torch.cuda.make_graphed_callables(layer, (triples, features))
