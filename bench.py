@@ -64,6 +64,14 @@ WORKLOADS = {
     'wn18_sampling': dict(shape='wn18', kind='sampling', in_f=0, out_f=0, decomp=None, dtype='i32', vertical=False,
                           label='WN18-shaped per-step graph construction (141,442 training triples, 40,943 nodes): '
                                 '30,000 edge-neighbourhood picks + 300,000 negatives + edge dropout 0.5'),
+    # the whole link-prediction training step of the shipped WN18 rgcn config (reference experiments/predict_links.py:119-195):
+    # per-step sampling + negatives + edge dropout, encoder, DistMult decoder, BCE + L2 penalty, backward, optimiser
+    'wn18_lp_step': dict(shape='wn18', kind='lp_step', in_f=200, out_f=200, decomp={'type': 'basis', 'num_bases': 2},
+                         dtype='f32', vertical=False,
+                         label='WN18-shaped rgcn training step (configs/rgcn/lp-WN18.yaml: 40,943 nodes, 18 relations, '
+                               '141,442 training triples; 30,000 edge-neighbourhood positives + 10 negatives each, edge '
+                               'dropout 0.5, 1 layer 200 -> 200 with basis B=2, DistMult, Adam): sampler + encoder + decoder '
+                               '+ loss + backward + optimiser step'),
     'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
                 vertical=True, raw=True,
                 label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
@@ -954,6 +962,83 @@ def run_ranking(args):
     print(json.dumps(line), flush=True)
 
 
+def run_lp_step(args):
+    """One epoch of experiments/predict_links.py:119-195 as ONE workload.  `value`: scored triples per second with the
+    epoch inputs prefetched (StepInputPrefetcher, `depth` samplers in flight); `inline` sub-record: the same step with the
+    sampler inside the step (depth 0, the reference's order of operations)."""
+    import torch.nn.functional as F
+    from torch_rgcn_b200 import _lib, models
+    from torch_rgcn_b200.sampling import EdgeNeighborhoodSampler, StepInputPrefetcher, training_step_inputs
+    syn = _synthetic()
+    wl = WORKLOADS[args.workload]
+    dev = torch.device('cuda', 0)
+    N, R, E = syn.SHAPES[wl['shape']]
+    S, rate, depth = 30000, 10, int(os.environ.get('RGCN_PREFETCH_DEPTH', '16'))
+    train = syn.random_triples(N, R, E, seed=0, device=dev)
+    torch.manual_seed(2)
+    enc = {'node_embedding': 200, 'hidden1_size': 200, 'num_layers': 1, 'decomposition': dict(wl['decomp']),
+           'edge_dropout': {'general': 0.5, 'self_loop': 0.2, 'self_loop_type': 'schlichtkrull-dropout'},
+           # the shipped 'schlichtkrull-normal' raises inside the reference's (and the drop-in's) initialise_weights for
+           # decomposed layers (layers.py:405-447 calls it without `shape`); glorot-normal has the same tensor shapes
+           'weight_init': 'glorot-normal', 'include_gain': False, 'bias_init': 'zeros'}
+    dec = {'l2_penalty_type': 'schlichtkrull-l2', 'l2_penalty': 0.01, 'weight_init': 'standard-normal', 'include_gain': False,
+           'bias_init': 'zeros'}
+    model = models.LinkPredictor(nnodes=N, nrel=R, encoder_config=enc, decoder_config=dec).to(dev).train()
+    for m in model.modules():
+        if hasattr(m, 'validate_triples'):
+            m.validate_triples = False
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    sm = EdgeNeighborhoodSampler(train, N)
+    kw = dict(graph_batch_size=S, neg_sample_rate=rate, edge_dropout_rate=0.5)
+
+    def train_on(graph, batch, lbl):
+        opt.zero_grad(set_to_none=True)
+        scores, penalty = model(graph, batch)
+        loss = F.binary_cross_entropy_with_logits(scores, lbl) + dec['l2_penalty'] * penalty
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(fetch, steps, warmup):
+        for _ in range(warmup):
+            train_on(*fetch())
+        torch.cuda.synchronize()
+        l0 = _lib.lib.rgcn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = train_on(*fetch())
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, _lib.lib.rgcn_launch_count() - l0, float(loss.item())
+
+    W = max(args.warmup, 3)
+    ms_inline, _, _ = timed(lambda: training_step_inputs(sm, N, **kw), min(args.steps, 10), W)
+    pre = StepInputPrefetcher(sm, N, depth=depth, **kw)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms, launches, loss = timed(pre.next, args.steps, W + depth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        train_on(*pre.next()).item()                   # e2e: the loss is read back every epoch, like upstream's logging
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+    sm.check()
+    scored = S * (1 + rate)
+    print(json.dumps({
+        'metric': 'lp_training_step_scored_triples_per_sec', 'value': scored / (ms * 1e-3), 'unit': 'triples/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': W + depth, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['label'], 'name': args.workload, 'num_nodes': N, 'positives': S, 'negatives': S * rate,
+                   'prefetch_depth': depth,
+                   'l2': 'working set of the step fits L2 (latency-bound shape); not flushed'},
+        'inline_sampler': {'ms_per_step': ms_inline, 'note': 'sampler inside the step (reference order, no prefetch)'},
+        'e2e': {'value': scored / (ms_e2e * 1e-3), 'unit': 'triples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches), 'final_loss': loss, 'clocks': clocks}), flush=True)
+
+
 def run_sampling(args):
     """Per-step graph construction (reference predict_links.py:123-148 with utils/misc.py:125-172).  `value`: picks per
     second of training_step_inputs with the training set resident; e2e: the same plus the D2H read of the sampled
@@ -1244,6 +1329,8 @@ def main():
         run_ranking(args)
     elif WORKLOADS[args.workload]['kind'] == 'sampling':
         run_sampling(args)
+    elif WORKLOADS[args.workload]['kind'] == 'lp_step':
+        run_lp_step(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

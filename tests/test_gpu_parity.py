@@ -35,7 +35,10 @@ def _compare(out, grads_ref, layer, feats, out_ref, atol=ATOL, rtol=1e-4):
         else:
             got = dict(layer.named_parameters())[name].grad
         assert got is not None, name
-        np.testing.assert_allclose(got.float().cpu().numpy(), g, atol=atol, rtol=rtol, err_msg=name)
+        # parameter gradients are fp32 sums over up to ~1e4 edges whose order differs between kernels: elements that
+        # cancel to ~0 carry rounding noise of ~eps * sqrt(n) * (largest term), i.e. a few 1e-6 of the tensor's scale
+        extra = 5e-6 * float(np.abs(g).max()) if name != 'features' else 0.0
+        np.testing.assert_allclose(got.float().cpu().numpy(), g, atol=atol + extra, rtol=rtol, err_msg=name)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -80,8 +80,84 @@ int launch_wgrad_generic(WGradArgs A, const XT* X, const float* G, int64_t nnz, 
     return RGCN_OK;
 }
 
+// Dense weight gradient of mid / wide layers (the 200 x 200 basis layer of configs/rgcn/lp-WN18.yaml, 500-wide layers):
+// gW[p] += (val X[src])^T G[dst] over the edges of relation p is a GEMM with gathered rows.  One CTA owns a 64 x 64 tile
+// of gW[p] and a slice of the relation's edges: 16-edge slabs of the two gathered row tiles go through shared memory,
+// each thread keeps a 4 x 4 register tile, slices are combined with one atomicAdd per element (split-K).
+template <typename XT>
+__global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT* __restrict__ X, const float* __restrict__ G) {
+    constexpr int TE = 16, T = 64;
+    __shared__ __align__(16) float Xs[TE][T];
+    __shared__ __align__(16) float Gs[TE][T];
+    const int I = A.I, O = A.O;
+    const int tiles_j = (O + T - 1) / T;
+    const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j, p = blockIdx.y;
+    const int e0 = A.relptr[p], e1 = A.relptr[p + 1];
+    const int n = e1 - e0;
+    if (n <= 0) return;
+    const int per = ((n + gridDim.z - 1) / gridDim.z + TE - 1) / TE * TE;
+    const int b0 = e0 + blockIdx.z * per, b1 = min(e1, b0 + per);
+    if (b0 >= b1) return;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int le = tid >> 4, lc = (tid & 15) * 4;            // loader role: edge le of the slab, columns lc .. lc + 3
+    float acc[4][4] = {};
+    for (int s0 = b0; s0 < b1; s0 += TE) {
+        const int e = s0 + le;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+        if (e < b1) {
+            const float v = A.val[e];
+            const XT* xr = X + (size_t)A.src[e] * I + ti * T + lc;
+            const float* gr = G + (size_t)A.dst[e] * O + tj * T + lc;
+            const int ci = ti * T + lc, cj = tj * T + lc;
+            if (ci + 0 < I) xv.x = v * to_f32(xr[0]);
+            if (ci + 1 < I) xv.y = v * to_f32(xr[1]);
+            if (ci + 2 < I) xv.z = v * to_f32(xr[2]);
+            if (ci + 3 < I) xv.w = v * to_f32(xr[3]);
+            if (cj + 0 < O) gv.x = gr[0];
+            if (cj + 1 < O) gv.y = gr[1];
+            if (cj + 2 < O) gv.z = gr[2];
+            if (cj + 3 < O) gv.w = gr[3];
+        }
+        __syncthreads();                                     // the previous slab has been consumed
+        *reinterpret_cast<float4*>(&Xs[le][lc]) = xv;
+        *reinterpret_cast<float4*>(&Gs[le][lc]) = gv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TE; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float* gw = A.gW + (size_t)p * I * O;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = ti * T + ty * 4 + i;
+        if (r >= I) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = tj * T + tx * 4 + j;
+            if (c < O && acc[i][j] != 0.f) atomicAdd(gw + (size_t)r * O + c, acc[i][j]);
+        }
+    }
+}
+
 template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
+    if (A.form == RGCN_W_DENSE && !A.mask && (int64_t)A.I * A.O >= 1024) {
+        const int tiles = ((A.I + 63) / 64) * ((A.O + 63) / 64);
+        // slices of ~1024 edges on average, at most 64 per relation (the self-loop relation is the long one)
+        int64_t z = nnz / ((int64_t)Rp * 1024) + 1;
+        if (z > 64) z = 64;
+        while (z > 1 && (int64_t)tiles * Rp * z > 65535LL * 4) --z;
+        dim3 grid((unsigned)tiles, (unsigned)Rp, (unsigned)z);
+        RGCN_LAUNCH((k_wgrad_dense_tiled<XT>), grid, 256, 0, st, A, X, G);
+        return RGCN_OK;
+    }
     return launch_wgrad_generic(A, X, G, nnz, Rp, st);
 }
 
