@@ -36,7 +36,7 @@ def test_algorithmic_bytes_follow_the_survey_formulas():
 def test_workload_table_is_well_formed():
     b = _bench()
     from torch_rgcn_b200.synthetic import SHAPES
-    kinds = {'nc', 'lp', 'nc_model', 'decoder', 'ranking', 'sampling'}
+    kinds = {'nc', 'lp', 'lp_step', 'nc_model', 'decoder', 'ranking', 'sampling'}
     for name, wl in b.WORKLOADS.items():
         assert wl['kind'] in kinds and wl['shape'] in SHAPES and wl['label'], name
         assert wl['dtype'] in ('bf16', 'f32', 'i32'), name

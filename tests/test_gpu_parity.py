@@ -218,6 +218,8 @@ CASES = [
     ('featureless_block', 2400, 7, 30000, None, 16, {'type': 'block', 'num_blocks': 4}, False, True, False),
     ('diag32', 3000, 11, 40000, 32, 32, None, False, False, True),
     ('dense128', 1500, 5, 20000, 128, 96, None, False, False, False),
+    ('dense_wide_odd', 1500, 5, 20000, 50, 37, None, True, False, False),       # tiled dense kernels, scalar tails
+    ('dense500', 700, 3, 6000, 500, 500, None, False, False, False),            # lp-FB-toy width
     ('dense16x4', 3000, 11, 40000, 16, 4, None, True, False, False),
     ('block32x8', 3000, 11, 40000, 32, 8, {'type': 'block', 'num_blocks': 2}, False, False, False),
     ('block512', 600, 3, 5000, 512, 512, {'type': 'block', 'num_blocks': 32}, True, False, False),
@@ -370,6 +372,38 @@ def test_gradient_dtypes_follow_inputs(cuda_device):
     x = torch.randn(N, 16, device=cuda_device, requires_grad=True)
     layer(x).sum().backward()
     assert layer.weights.grad.dtype == torch.bfloat16 and layer.bias.grad.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize('I,O,bf16', [(48, 40, False), (50, 37, False), (200, 200, False), (64, 96, True)])
+def test_dense_tiled_with_self_mask(cuda_device, I, O, bf16):
+    """The tiled dense propagation kernels (forward and feature gradient) with the 'schlichtkrull-dropout' mask on the
+    self-loop relation (reference layers.py:545-546), through the functional entry point, against the oracle."""
+    from torch_rgcn_b200 import GraphPlan, rgcn_propagate, _lib
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = 1800, 7, 16000
+    t = random_triples(N, R, E, seed=4, rel_dist='zipf', node_skew=True)
+    tp = orc.add_inverse_and_self(t.numpy(), N, R)
+    Rp = 2 * R + 1
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_COL_SWAPPED, n_general=E, n_self=N)
+    gen = torch.Generator(device=cuda_device).manual_seed(11)
+    W = torch.randn(Rp, I, O, device=cuda_device, generator=gen).requires_grad_(True)
+    bias = torch.randn(O, device=cuda_device, generator=gen)
+    x = torch.randn(N, I, device=cuda_device, generator=gen)
+    if bf16:
+        x = x.to(torch.bfloat16)
+    x.requires_grad_(True)
+    mask = (torch.rand(N, O, device=cuda_device, generator=gen) > 0.3).float() * 2.0
+    out = rgcn_propagate(plan, 'dense', I, O, x, weights=W, bias=bias, self_mask=mask)
+    G = torch.randn(N, O, device=cuda_device, generator=gen)
+    out.backward(G)
+    val = plan.val[:tp.shape[0]].cpu().numpy()
+    Xn = x.detach().float().cpu().numpy()
+    ref = orc.propagate(tp, val, W.detach().cpu().numpy(), Xn, bias.cpu().numpy(), N, mask.cpu().numpy(), Rp - 1)
+    gX, gW = orc.propagate_backward(tp, val, W.detach().cpu().numpy(), G.cpu().numpy(), Xn, mask.cpu().numpy(), Rp - 1)
+    tol = 1e-2 if bf16 else 1e-4
+    for got, want, name in ((out, ref, 'out'), (x.grad.float(), gX, 'gX'), (W.grad, gW, 'gW')):
+        scale = float(np.abs(want).max())
+        np.testing.assert_allclose(got.detach().cpu().numpy(), want, atol=tol * max(1.0, scale), rtol=tol, err_msg=name)
 
 
 # ---------------------------------------------------------------------------------------------------

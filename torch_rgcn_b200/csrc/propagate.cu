@@ -146,6 +146,137 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
     }
 }
 
+// Dense propagation of mid / wide layers (200 -> 200 basis layer of configs/rgcn/lp-WN18.yaml, 500-wide dense self-loop
+// weights): out[scatter_e] += val_e * X[gather_e] W_p is, per relation, a GEMM whose A rows are gathered.  One CTA owns a
+// chunk of <= RGCN_CHUNK_EDGES edges of one relation and a 64-column tile of the output; 64-edge sub-tiles go through
+// the inner dimension in 16-wide slabs (gathered rows and the weight slab staged in shared memory, 4 x 4 register tile
+// per thread), and each finished sub-tile is added to its destination rows with vector reductions.  Serves the forward
+// (gather sources, W) and the feature gradient (gather destinations, W^T) — reference layers.py:293-301 / :534-548
+// without the (R'N, I) temporary.  `out` holds the bias / zeros before the launch.
+struct GemmArgs {
+    const int32_t* relptr; const int32_t* chunkptr; int num_rels;
+    const int32_t* gather; const int32_t* scatter; const float* val;
+    const float* W;               // (R', I, O)
+    int I, O;
+    const float* out_mask;        // (N, O): multiplies the messages of relation mask_rel
+    const float* in_mask;         // (N, I): multiplies the gathered rows of relation mask_rel
+    int mask_rel;
+    float* out;
+};
+
+template <typename XT>
+__global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* __restrict__ X) {
+    constexpr int TK = 16, T = 64;
+    __shared__ __align__(16) float Xs[TK][T + 4];
+    __shared__ __align__(16) float Ws[TK][T];
+    const int c = blockIdx.y;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int I = A.I, O = A.O, tj = blockIdx.x;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int le = tid >> 2, lk = (tid & 3) * 4;             // X loader: edge le of the sub-tile, inner offsets lk .. lk + 3
+    const int wk = tid >> 4, wc = (tid & 15) * 4;            // W loader: inner row wk of the slab, columns wc .. wc + 3
+    const float* Wp = A.W + (size_t)p * I * O;
+    const float* imask = (A.in_mask && p == A.mask_rel) ? A.in_mask : nullptr;
+    const float* omask = (A.out_mask && p == A.mask_rel) ? A.out_mask : nullptr;
+    const bool vec_w = (O & 3) == 0, vec_x = (I & 3) == 0 && sizeof(XT) == 4;
+    for (int sub = e0; sub < e1; sub += T) {
+        const int e = sub + le;
+        const int64_t grow = e < e1 ? A.gather[e] : -1;
+        float acc[4][4] = {};
+        for (int k0 = 0; k0 < I; k0 += TK) {
+            float xv[4] = {0.f, 0.f, 0.f, 0.f};
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow >= 0) {
+                const int k = k0 + lk;
+                const XT* xr = X + (size_t)grow * I + k;
+                if (vec_x && k + 3 < I) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(xr));
+                    xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (k + i < I) xv[i] = to_f32(xr[i]);
+                }
+                if (imask) {
+                    const float* mr = imask + (size_t)grow * I + k;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (k + i < I) xv[i] *= mr[i];
+                }
+            }
+            if (k0 + wk < I) {
+                const int col = tj * T + wc;
+                const float* wr = Wp + (size_t)(k0 + wk) * O + col;
+                if (vec_w && col + 3 < O) wv = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    if (col + 0 < O) wv.x = wr[0];
+                    if (col + 1 < O) wv.y = wr[1];
+                    if (col + 2 < O) wv.z = wr[2];
+                    if (col + 3 < O) wv.w = wr[3];
+                }
+            }
+            __syncthreads();                                 // the previous slab has been consumed
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Xs[lk + i][le] = xv[i];
+            *reinterpret_cast<float4*>(&Ws[wk][wc]) = wv;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < TK; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+        const int col = tj * T + tx * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ee = sub + ty * 4 + i;
+            if (ee >= e1 || col >= O) continue;
+            const float v = A.val[ee];
+            const size_t base = (size_t)A.scatter[ee] * O + col;
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = v * acc[i][j] * ((omask && col + j < O) ? omask[base + j] : 1.f);
+            if (vec_w) {
+                atomicAdd(reinterpret_cast<float4*>(A.out + base), make_float4(r[0], r[1], r[2], r[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (col + j < O) atomicAdd(A.out + base + j, r[j]);
+            }
+        }
+    }
+}
+
+// out[row, :] = bias (or 0): the starting value of the reductions above
+__global__ void k_init_rows(float* __restrict__ out, int64_t n, int O, const float* __restrict__ bias) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bias ? bias[i % O] : 0.f;
+}
+
+bool dense_tiled_shape(int form, int featureless, int I, int O, int64_t nnz) {
+    return form == RGCN_W_DENSE && !featureless && (int64_t)I * O >= 1024 && nnz > 0;
+}
+
+template <typename XT>
+int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bias, int chunks, cudaStream_t st) {
+    const int64_t n = N * (int64_t)A.O;
+    RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, A.out, n, A.O, bias);
+    RGCN_REQUIRE(chunks <= 65535, RGCN_ERR_UNSUPPORTED, "dense tiled propagation: %d chunks exceed the grid", chunks);
+    dim3 grid((unsigned)((A.O + 63) / 64), (unsigned)chunks);
+    RGCN_LAUNCH((k_prop_dense_tiled<XT>), grid, 256, 0, st, A, X);
+    return RGCN_OK;
+}
+
 template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
     if (A.form == RGCN_W_DENSE && !A.mask && (int64_t)A.I * A.O >= 1024) {
@@ -408,6 +539,12 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const float*>(msg), p->bias, out, g->d_long, g->status + 4,
                               g->num_long_dst, s.nnz, st);
     }
+    if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz) && max_chunks(s) <= 65535) {
+        GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, A.W, s.I, s.O,
+                    p->self_mask, nullptr, (int)s.Rp - 1, out};
+        if (bf16) return launch_prop_dense_tiled(Gm, static_cast<const __nv_bfloat16*>(X), s.N, p->bias, max_chunks(s), st);
+        return launch_prop_dense_tiled(Gm, static_cast<const float*>(X), s.N, p->bias, max_chunks(s), st);
+    }
     if (bf16) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
     return launch_prop(A, static_cast<const float*>(X), st);
 }
@@ -607,6 +744,10 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             if (rc) return rc;
             rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gx_f32, g->s_long, g->status + 5,
                                 g->num_long_src, s.nnz, st);
+        } else if (dense_tiled_shape(A.form, 0, s.O, s.I, s.nnz) && max_chunks(s) <= 65535) {
+            GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.W, s.O, s.I,
+                        nullptr, p->self_mask, (int)s.Rp - 1, gx_f32};
+            rc = launch_prop_dense_tiled(Gm, G, s.N, (const float*)nullptr, max_chunks(s), st);
         } else {
             rc = launch_prop(A, G, st);
         }
