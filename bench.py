@@ -75,6 +75,11 @@ WORKLOADS = {
     'syn': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp={'type': 'block', 'num_blocks': 32}, dtype='bf16',
                 vertical=True, raw=True,
                 label='synthetic 5M-node / 256-rel / 200M-edge layer, block-diagonal nb=32, 512->512, bf16'),
+    # the same graph with full (undecomposed) 512 x 512 weights per relation: 105 TFLOP per direction, a true GEMM with
+    # gathered rows -> tcgen05 tensor-core kernel (propagate_umma.cuh)
+    'syn_none': dict(shape='syn', kind='nc', in_f=512, out_f=512, decomp=None, dtype='bf16', vertical=True, raw=True,
+                     label='synthetic 5M-node / 256-rel / 200M-edge layer, no decomposition (256 dense 512x512 weights), '
+                           '512->512, bf16'),
 }
 
 
@@ -496,6 +501,17 @@ def run_ours(args):
                           'unit': 'GB/s', 'frac': ach_s / peak},
         'clocks': clocks,
     }
+    if not wl['decomp'] and wl['dtype'] == 'bf16' and I % 64 == 0 and O % 64 == 0:
+        # dense weights over bf16 features: per relation a GEMM with gathered rows (tcgen05 kernel k_gemm_umma); the
+        # forward is bounded by the tensor cores, not by HBM
+        tpeak = peaks.get('bf16_tflops_sustained', 1400.0)
+        flops = 2.0 * nnz * I * O / world
+        line['config']['kernels'] = ('tcgen05 gathered GEMM (k_gemm_umma: TMA gather4 -> UMMA 128 x 256 x 16, TMEM accumulators) '
+                                     'for the forward and the feature gradient; fp32 register-tiled weight gradient')
+        line['roofline_tensor'] = {'kernel': 'k_gemm_umma (forward)', 'bound': 'tensor', 'achieved': flops / (ms_fwd * 1e-3) / 1e12,
+                                   'peak': tpeak, 'unit': 'TFLOP/s', 'frac': flops / (ms_fwd * 1e-3) / 1e12 / tpeak,
+                                   'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS 8192^3)',
+                                   'flops_per_launch': flops}
     syn = None
     if args.workload == 'am64' and not args.skew and not args.no_subrecords and os.environ.get('RGCN_BENCH_SYN', '1') != '0':
         # config 5 of BASELINE.json next to the headline, at every GPU count (all ranks take part)

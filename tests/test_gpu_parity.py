@@ -406,6 +406,55 @@ def test_dense_tiled_with_self_mask(cuda_device, I, O, bf16):
         np.testing.assert_allclose(got.detach().cpu().numpy(), want, atol=tol * max(1.0, scale), rtol=tol, err_msg=name)
 
 
+@pytest.mark.parametrize('I,O,form', [(64, 64, 'dense'), (128, 256, 'dense'), (512, 512, 'dense'), (192, 320, 'dense'), (72, 80, 'dense'),
+                                      (256, 192, 'basis')])
+def test_dense_bf16_tensor_core_gemm(cuda_device, I, O, form):
+    """bf16 features with dense / basis weights of 64 x 64 and up run the tcgen05 gathered GEMM (propagate_umma.cuh):
+    forward and feature gradient against the fp64 oracle on the bf16-rounded operands' scale (stated bf16 bar: 1e-2 of
+    the tensor's scale); relation sizes from 0 edges to several M tiles; widths that are not multiples of 64 take the fp32 tiled kernels."""
+    from torch_rgcn_b200 import GraphPlan, rgcn_propagate, _lib
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = 3000, 6, 30000
+    t = random_triples(N, R, E, seed=9, rel_dist='zipf', node_skew=True).numpy()
+    t = t[t[:, 1] != 3]                                   # relation 3 (and its inverse) have no edges at all
+    tp = orc.add_inverse_and_self(t, N, R)
+    Rp = 2 * R + 1
+    plan = GraphPlan(torch.as_tensor(tp).to(cuda_device), N, Rp, _lib.NORM_ROW)
+    gen = torch.Generator(device=cuda_device).manual_seed(13)
+    kw = {}
+    if form == 'dense':
+        W = torch.randn(Rp, I, O, device=cuda_device, generator=gen).requires_grad_(True)
+        kw['weights'] = W
+        leaves = {'weights': W}
+    else:
+        bases = torch.randn(3, I, O, device=cuda_device, generator=gen).requires_grad_(True)
+        comps = torch.randn(Rp, 3, device=cuda_device, generator=gen).requires_grad_(True)
+        kw.update(bases=bases, comps=comps)
+        leaves = {'bases': bases, 'comps': comps}
+    bias = torch.randn(O, device=cuda_device, generator=gen)
+    x = torch.randn(N, I, device=cuda_device, generator=gen).to(torch.bfloat16).requires_grad_(True)
+    launches0 = _lib.lib.rgcn_launch_count()
+    out = rgcn_propagate(plan, form, I, O, x, bias=bias, **kw)
+    G = torch.randn(N, O, device=cuda_device, generator=gen)
+    out.backward(G)
+    torch.cuda.synchronize()
+    assert _lib.lib.rgcn_launch_count() > launches0
+    val = plan.val[:tp.shape[0]].cpu().numpy()
+    Xn = x.detach().float().cpu().numpy()
+    Wn = (kw['weights'] if form == 'dense' else torch.einsum('rb,bio->rio', comps, bases)).detach().cpu().numpy()
+    ref = orc.propagate(tp, val, Wn, Xn, bias.cpu().numpy(), N)
+    gX, gW = orc.propagate_backward(tp, val, Wn, G.cpu().numpy(), Xn)
+    for got, want, name in ((out, ref, 'out'), (x.grad.float(), gX, 'gX')):
+        scale = float(np.abs(want).max())
+        err = np.abs(got.detach().cpu().numpy() - want)
+        assert err.max() <= 1e-2 * scale, f'{name}: max err {err.max():.4g} vs scale {scale:.4g}'
+        # and not merely small: the mean relative error of a bf16-operand product is ~1e-3
+        assert err.mean() <= 2e-3 * scale, name
+    if form == 'dense':
+        scale = float(np.abs(gW).max())
+        assert np.abs(W.grad.cpu().numpy() - gW).max() <= 1e-3 * scale
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at a large shape
 # ---------------------------------------------------------------------------------------------------

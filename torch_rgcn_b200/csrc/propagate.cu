@@ -10,6 +10,7 @@
 #include "propagate_fast.cuh"
 #include "propagate_mma.cuh"
 #include "propagate_fused.cuh"
+#include "propagate_umma.cuh"
 
 using namespace rgcn;
 
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
     const int e0 = A.relptr[p], e1 = A.relptr[p + 1];
     const int n = e1 - e0;
     if (n <= 0) return;
-    const int per = ((n + gridDim.z - 1) / gridDim.z + TE - 1) / TE * TE;
+    // slices of at least 256 edges: short relations flush their tile once, the long (self-loop) one is spread wide
+    const int per = max(256, ((n + (int)gridDim.z - 1) / (int)gridDim.z + TE - 1) / TE * TE);
     const int b0 = e0 + blockIdx.z * per, b1 = min(e1, b0 + per);
     if (b0 >= b1) return;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -281,8 +283,9 @@ template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
     if (A.form == RGCN_W_DENSE && !A.mask && (int64_t)A.I * A.O >= 1024) {
         const int tiles = ((A.I + 63) / 64) * ((A.O + 63) / 64);
-        // slices of ~1024 edges on average, at most 64 per relation (the self-loop relation is the long one)
-        int64_t z = nnz / ((int64_t)Rp * 1024) + 1;
+        // up to 64 slices per relation, sized for the longest one a graph of nnz edges can hold (the self-loop
+        // relation of an LP step has more edges than all others together); CTAs of slices past a relation's end exit
+        int64_t z = nnz / 512 + 1;
         if (z > 64) z = 64;
         while (z > 1 && (int64_t)tiles * Rp * z > 65535LL * 4) --z;
         dim3 grid((unsigned)tiles, (unsigned)Rp, (unsigned)z);
@@ -413,6 +416,12 @@ bool fused_path(const rgcn_graph* g, const rgcn_params* p, const Shape& s, bool 
            s.bi == 16 && s.bo == 16;
 }
 
+// Tensor-core gathered GEMM (propagate_umma.cuh): bf16 features, dense or basis weights of at least 64 x 64, no mask.
+bool umma_path(const rgcn_params* p, const Shape& s, bool bf16) {
+    return bf16 && !p->featureless && !p->self_mask && (p->form == RGCN_W_DENSE || p->form == RGCN_W_BASIS) && s.nnz > 0 &&
+           umma_shape_supported(s.I, s.O) && umma_shape_supported(s.O, s.I);
+}
+
 size_t tiled_ring_bytes(const rgcn_graph* g, int width) {
     return align_up((size_t)g->ring_depth * (size_t)g->tile_capacity * width * 2);
 }
@@ -451,6 +460,7 @@ extern "C" size_t rgcn_forward_workspace_bytes(const rgcn_graph* g, const rgcn_p
     if (check_common(g, p, &s, "rgcn_forward_workspace_bytes")) return 0;
     size_t bytes = 0;
     if (p->form == RGCN_W_BASIS && !p->featureless) bytes += align_up(s.w_elems * sizeof(float));
+    if (umma_path(p, s, x_dtype == RGCN_BF16)) return bytes + umma_wt_bytes(s.Rp, s.I, s.O);
     if (fused_path(g, p, s, x_dtype == RGCN_BF16, false)) return bytes + fused_ws_bytes(s.Rp, s.nb);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.O) + wfrag_bytes(s.Rp, s.nb);
@@ -539,6 +549,15 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         return launch_row_sum(g->d_rowptr, s.N, s.O, static_cast<const float*>(msg), p->bias, out, g->d_long, g->status + 4,
                               g->num_long_dst, s.nnz, st);
     }
+    if (umma_path(p, s, bf16)) {
+        __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(umma_wt_bytes(s.Rp, s.I, s.O)));
+        const int64_t cnt = (int64_t)s.Rp * s.I * s.O;
+        RGCN_LAUNCH(k_pack_wt_bf16, grid_for(cnt, 256), 256, 0, st, A.W, cnt, s.I, s.O, 1, wt);
+        const int64_t n = s.N * (int64_t)s.O;
+        RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, out, n, s.O, p->bias);
+        UmmaArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, s.I, s.O, 0, out};
+        return launch_gemm_umma(U, static_cast<const __nv_bfloat16*>(X), s.N, wt, max_chunks(s), st);
+    }
     if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz) && max_chunks(s) <= 65535) {
         GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, A.W, s.I, s.O,
                     p->self_mask, nullptr, (int)s.Rp - 1, out};
@@ -566,6 +585,7 @@ extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_
     }
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.O * 2);   // bf16 copy of grad_out (tensor-core path)
     if (x_dtype == RGCN_BF16) bytes += align_up((size_t)s.N * s.I * 4);   // fp32 staging of a bf16 feature gradient
+    if (umma_path(p, s, x_dtype == RGCN_BF16)) bytes += umma_wt_bytes(s.Rp, s.I, s.O);   // bf16 weights of the tensor-core GEMM
     if (fused_path(g, p, s, x_dtype == RGCN_BF16, true)) return bytes + fused_ws_bytes(s.Rp, s.nb);
     if (tiled_path(g, p, s, x_dtype == RGCN_BF16))
         return bytes + tiled_counter_bytes(g->num_tiles) + tiled_ring_bytes(g, s.I) + wfrag_bytes(s.Rp, s.nb);
@@ -744,6 +764,19 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             if (rc) return rc;
             rc = launch_row_sum(g->s_rowptr, s.N, s.I, msg, (const float*)nullptr, gx_f32, g->s_long, g->status + 5,
                                 g->num_long_src, s.nnz, st);
+        } else if (umma_path(p, s, x_dtype == RGCN_BF16)) {
+            // gX[o_e] += val_e * bf16(G)[s_e] W_p^T: the inner dimension is the layer's output, so W_p is K-major as stored
+            __nv_bfloat16* gb16 = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
+            rc = launch_cast_colsum(G, s.N, s.O, gb16, nullptr, st);
+            if (rc) return rc;
+            __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(umma_wt_bytes(s.Rp, s.I, s.O)));
+            const int64_t cnt = (int64_t)s.Rp * IO;
+            RGCN_LAUNCH(k_pack_wt_bf16, grid_for(cnt, 256), 256, 0, st, p->form == RGCN_W_BASIS ? weff : p->weights, cnt,
+                        s.I, s.O, 0, wb);
+            const int64_t n = s.N * (int64_t)s.I;
+            RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, gx_f32, n, s.I, (const float*)nullptr);
+            UmmaArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, s.O, s.I, 0, gx_f32};
+            rc = launch_gemm_umma(U, gb16, s.N, wb, max_chunks(s), st);
         } else if (dense_tiled_shape(A.form, 0, s.O, s.I, s.nnz) && max_chunks(s) <= 65535) {
             GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.W, s.O, s.I,
                         nullptr, p->self_mask, (int)s.Rp - 1, gx_f32};

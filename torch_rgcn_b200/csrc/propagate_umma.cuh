@@ -1,0 +1,264 @@
+// Gathered GEMM on the 5th-generation tensor cores for dense (and basis) weights over bf16 features:
+//
+//     out[scatter_e, :] += val_e * X[gather_e, :] W_p          for the edges e of relation p
+//
+// is, per relation, a real GEMM (edges_p x I x O — 105 TFLOP for the 200 M-edge 512 x 512 layer of SURVEY §8) whose A
+// rows are gathered.  Reference: the dense / basis branch of torch_rgcn/layers.py:286-301 (NC) and :518-551 (LP), there an
+// (R'N, I) sparse product followed by an einsum.
+//
+//   CTA        = one chunk of <= RGCN_CHUNK_EDGES edges of one relation (the plan's relation-major lists) x one tile of
+//                NT <= 256 output columns; 128-edge M tiles, the inner dimension in 64-wide blocks.
+//   producer   = warp 0.  Per k block: the 128 gathered rows come in through 32 TMA tile::gather4 copies (one per
+//                lane, four rows each, 128-byte swizzle) — exactly the canonical K-major SWIZZLE_128B operand layout of
+//                tcgen05.mma, so no thread touches the data; the NT x 64 weight tile (bf16, packed K-major by
+//                k_pack_wt_bf16) through one 3-D TMA tile copy.  Both complete on the stage's "full" mbarrier.
+//   MMA        = one elected lane of warp 1: four tcgen05.mma.cta_group::1.kind::f16 (M 128, N NT, K 16) per stage on
+//                shared-memory descriptors, fp32 accumulators in tensor memory (NT columns x 128 lanes);
+//                tcgen05.commit hands the stage back to the producer and, after the last k block, the accumulator
+//                to the epilogue.
+//   epilogue   = warps 2-5 (one TMEM lane quarter each): tcgen05.ld 32 columns at a time, scale by the edge's
+//                normalisation weight, 16-byte fp32 reductions into the destination row (rows of different M tiles,
+//                chunks and relations meet in `out`, which holds the bias beforehand).
+//   occupancy  = 2 CTAs per SM (2 x 96 KB of stages, 2 x 256 TMEM columns): the epilogue of one overlaps the MMAs of
+//                the other.
+//
+// The same kernel serves the forward (gather sources, W_p) and the feature gradient (gather the bf16 copy of
+// grad_out by destination, W_p^T).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "propagate_fused.cuh"
+
+namespace rgcn {
+
+constexpr int kUmM = 128;            // edges per M tile = TMEM lanes
+constexpr int kUmK = 64;             // inner elements per stage = one 128-byte swizzle atom of bf16
+constexpr int kUmStages = 2;
+constexpr int kUmThreads = 192;      // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+constexpr int kUmABytes = kUmM * kUmK * 2;
+
+struct UmmaArgs {
+    const int32_t* relptr; const int32_t* chunkptr; int num_rels;
+    const int32_t* gather; const int32_t* scatter; const float* val;
+    int I, O, NT;
+    float* out;
+};
+
+inline size_t umma_smem_bytes(int NT) { return 1024 + (size_t)kUmStages * (kUmABytes + (size_t)NT * kUmK * 2); }
+inline size_t umma_wt_bytes(int64_t Rp, int I, int O) { return align_up((size_t)Rp * I * O * 2); }
+
+// bf16 weights, K-major: wt[p][n][k] = W[p][k][n] (forward, transpose = 1) or W[p][n][k] (feature gradient: the inner
+// dimension is the layer's output, transpose = 0; `rows` x `cols` is the shape of one W[p])
+__global__ void k_pack_wt_bf16(const float* __restrict__ W, int64_t count, int rows, int cols, int transpose,
+                               __nv_bfloat16* __restrict__ wt) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (!transpose) { wt[i] = __float2bfloat16(W[i]); return; }
+    const int64_t per = (int64_t)rows * cols, p = i / per, rem = i - p * per;
+    const int n = (int)(rem / rows), k = (int)(rem - (int64_t)n * rows);       // wt viewed as [p][cols][rows]
+    wt[i] = __float2bfloat16(W[p * per + (int64_t)k * cols + n]);
+}
+
+__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile with the 128-byte swizzle: 128-byte rows, 8-row groups 1024 bytes apart (cute UMMA::SmemDescriptor:
+// start address and offsets in 16-byte units, version 1, layout type 2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kUmThreads, 2)
+k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs A, int tmem_cols) {
+    extern __shared__ unsigned char um_smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * kUmStages + 2];
+    __shared__ uint32_t tmem_slot;
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int NT = A.NT, n0 = blockIdx.y * NT;
+    const int mtiles = (e1 - e0 + kUmM - 1) / kUmM, kblocks = (A.I + kUmK - 1) / kUmK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = ((uint32_t)__cvta_generic_to_shared(um_smem) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = kUmABytes + (uint32_t)NT * kUmK * 2;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (kUmStages + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * kUmStages), tempty = tfull + 8u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kUmStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ---- producer
+        int it = 0;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            int r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e0 + mt * kUmM + 4 * lane + j;
+                r[j] = A.gather[e < e1 ? e : e0];                 // rows past the chunk's end: any valid row, never stored
+            }
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % kUmStages;
+                mbar_wait(empty(s), ((it / kUmStages) & 1) ^ 1);
+                if (lane == 0) mbar_expect_tx(full(s), stage_bytes);
+                __syncwarp();
+                const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                tma_gather4(sa + (uint32_t)lane * 512u, &tmA, full(s), kb * kUmK, r[0], r[1], r[2], r[3]);
+                if (lane == 0) tma_tile_3d(sa + kUmABytes, &tmB, full(s), kb * kUmK, n0, p);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        // instruction descriptor (cute UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both operands K-major
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kUmM >> 4) << 24);
+        int it = 0;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            mbar_wait(tempty, (mt & 1) ^ 1);                      // the epilogue has drained the previous M tile
+            tc_fence_after();
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % kUmStages;
+                mbar_wait(full(s), (it / kUmStages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kUmABytes);
+#pragma unroll
+                    for (int k = 0; k < kUmK / 16; ++k)           // 16 bf16 = 32 bytes = 2 descriptor units per step
+                        tc_mma_bf16(tmem, ad + 2u * k, bd + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+                    tc_commit(empty(s));
+                    if (kb == kblocks - 1) tc_commit(tfull);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- epilogue: warp w reads the TMEM lane quarter w % 4
+        const int q = warp & 3;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            mbar_wait(tfull, mt & 1);
+            tc_fence_after();
+            const int e = e0 + mt * kUmM + q * 32 + lane;
+            const bool valid = e < e1;
+            const float v = valid ? A.val[e] : 0.f;
+            float* orow = A.out + (size_t)(valid ? A.scatter[e] : 0) * A.O + n0;
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c0 + 4 * j < NT)
+                            atomicAdd(reinterpret_cast<float4*>(orow + c0 + 4 * j),
+                                      make_float4(v * __uint_as_float(r[4 * j]), v * __uint_as_float(r[4 * j + 1]),
+                                                  v * __uint_as_float(r[4 * j + 2]), v * __uint_as_float(r[4 * j + 3])));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// column tile: the largest multiple of 16 that divides O and fits one MMA (N <= 256)
+inline int umma_col_tile(int O) {
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (O % nt == 0) return nt;
+    return 0;
+}
+
+inline bool umma_shape_supported(int I, int O) {
+    const char* e = getenv("RGCN_UMMA");
+    if (e && e[0] == '0') return false;
+    return I >= 64 && O >= 64 && I % 64 == 0 && O % 64 == 0;   // whole 64-element k blocks in both directions
+}
+
+// `wt` = bf16 K-major weights from k_pack_wt_bf16: (R', O, I); X = gathered bf16 matrix (N, I); out (N, O) pre-set.
+inline int launch_gemm_umma(UmmaArgs A, const __nv_bfloat16* X, int64_t N, const __nv_bfloat16* wt, int chunks, cudaStream_t st) {
+    rb_encode_fn enc = rb_encoder();
+    RGCN_REQUIRE(enc, RGCN_ERR_CUDA, "tensor-core GEMM: cuTensorMapEncodeTiled is not available from this driver");
+    const int NT = umma_col_tile(A.O);
+    A.NT = NT;
+    CUtensorMap ta, tb;
+    memset(&ta, 0, sizeof(ta));
+    memset(&tb, 0, sizeof(tb));
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)A.I, (cuuint64_t)N};
+        const cuuint64_t gstr[1] = {(cuuint64_t)A.I * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)kUmK, 1};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(X), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RGCN_REQUIRE(r == CUDA_SUCCESS, RGCN_ERR_CUDA, "tensor-core GEMM: feature tensor map failed with %d", (int)r);
+    }
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)A.I, (cuuint64_t)A.O, (cuuint64_t)A.num_rels};
+        const cuuint64_t gstr[2] = {(cuuint64_t)A.I * 2, (cuuint64_t)A.I * A.O * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)kUmK, (cuuint32_t)NT, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(wt), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RGCN_REQUIRE(r == CUDA_SUCCESS, RGCN_ERR_CUDA, "tensor-core GEMM: weight tensor map failed with %d", (int)r);
+    }
+    int cols = 32;
+    while (cols < NT) cols <<= 1;
+    const size_t smem = umma_smem_bytes(NT);
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)chunks, (unsigned)(A.O / NT));
+    RGCN_LAUNCH(k_gemm_umma, grid, kUmThreads, smem, st, ta, tb, A, cols);
+    return RGCN_OK;
+}
+
+}  // namespace rgcn
