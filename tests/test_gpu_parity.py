@@ -451,8 +451,16 @@ def test_dense_bf16_tensor_core_gemm(cuda_device, I, O, form):
         # and not merely small: the mean relative error of a bf16-operand product is ~1e-3
         assert err.mean() <= 2e-3 * scale, name
     if form == 'dense':
+        # I % 128 == 0: tensor-core weight gradient (bf16 operands, X rows scaled by the edge weight in bf16)
         scale = float(np.abs(gW).max())
-        assert np.abs(W.grad.cpu().numpy() - gW).max() <= 1e-3 * scale
+        err = np.abs(W.grad.cpu().numpy() - gW)
+        assert err.max() <= 1e-2 * scale and err.mean() <= 2e-3 * scale, (err.max(), err.mean(), scale)
+    else:
+        gb = np.einsum('rb,rio->bio', comps.detach().cpu().numpy().astype(np.float64), gW)
+        gc = np.einsum('rio,bio->rb', gW, bases.detach().cpu().numpy().astype(np.float64))
+        for got, want, name in ((bases.grad, gb, 'bases'), (comps.grad, gc, 'comps')):
+            scale = float(np.abs(want).max())
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-2 * scale, name
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -723,6 +723,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
     }
 
     // ---- effective / transposed weights for the feature gradient
+    __nv_bfloat16* gb16_dense = nullptr;     // bf16 copy of grad_out shared by the tensor-core GEMMs of dense layers
     float* weff = nullptr;
     if (p->form == RGCN_W_BASIS) {
         weff = carve.take<float>((size_t)s.Rp * IO);
@@ -769,6 +770,7 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             __nv_bfloat16* gb16 = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
             rc = launch_cast_colsum(G, s.N, s.O, gb16, nullptr, st);
             if (rc) return rc;
+            gb16_dense = gb16;
             __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(umma_wt_bytes(s.Rp, s.I, s.O)));
             const int64_t cnt = (int64_t)s.Rp * IO;
             RGCN_LAUNCH(k_pack_wt_bf16, grid_for(cnt, 256), 256, 0, st, p->form == RGCN_W_BASIS ? weff : p->weights, cnt,
@@ -834,6 +836,15 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
                                   max_chunks(s), st);
         else
             rc = launch_rel_wgrad(R, ws_shape.bi, ws_shape.bo, static_cast<const float*>(X), G, target, max_chunks(s), st);
+    }
+    if (rc > 0 && umma_path(p, s, x_dtype == RGCN_BF16) && umma_wgrad_shape_supported(s.I, s.O)) {
+        if (!gb16_dense) {
+            gb16_dense = reinterpret_cast<__nv_bfloat16*>(carve.take<char>(align_up((size_t)s.N * s.O * 2)));
+            rc = launch_cast_colsum(G, s.N, s.O, gb16_dense, nullptr, st);
+            if (rc) return rc;
+        }
+        UmmaWgradArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, s.I, s.O, 0, Wg.gW};
+        rc = launch_wgrad_umma(U, static_cast<const __nv_bfloat16*>(X), gb16_dense, s.N, max_chunks(s), st);
     }
     if (rc > 0) {
         if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);

@@ -33,7 +33,7 @@ namespace rgcn {
 
 constexpr int kUmM = 128;            // edges per M tile = TMEM lanes
 constexpr int kUmK = 64;             // inner elements per stage = one 128-byte swizzle atom of bf16
-constexpr int kUmStages = 2;
+constexpr int kUmMaxStages = 4;      // 2 stages: two CTAs per SM (default); 3-4: one CTA per SM with a deeper pipeline
 constexpr int kUmThreads = 192;      // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 epilogue
 constexpr int kUmABytes = kUmM * kUmK * 2;
 
@@ -44,7 +44,12 @@ struct UmmaArgs {
     float* out;
 };
 
-inline size_t umma_smem_bytes(int NT) { return 1024 + (size_t)kUmStages * (kUmABytes + (size_t)NT * kUmK * 2); }
+constexpr int kUmStgStride = 20;     // floats per staged row: 16 columns + 4 of padding (conflict-free 16-byte stores)
+constexpr int kUmStgBytes = 32 * kUmStgStride * 4;
+
+inline size_t umma_smem_bytes(int NT, int stages) {
+    return 1024 + (size_t)stages * (kUmABytes + (size_t)NT * kUmK * 2) + 4 * kUmStgBytes;
+}
 inline size_t umma_wt_bytes(int64_t Rp, int I, int O) { return align_up((size_t)Rp * I * O * 2); }
 
 // bf16 weights, K-major: wt[p][n][k] = W[p][k][n] (forward, transpose = 1) or W[p][n][k] (feature gradient: the inner
@@ -91,10 +96,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kUmThreads, 2)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int kUmStages>
+__global__ void __launch_bounds__(kUmThreads, kUmStages == 2 ? 2 : 1)
 k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs A, int tmem_cols) {
     extern __shared__ unsigned char um_smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * kUmStages + 2];
+    __shared__ __align__(8) unsigned long long bars[2 * kUmMaxStages + 2];
     __shared__ uint32_t tmem_slot;
     const int c = blockIdx.x;
     if (c >= A.chunkptr[A.num_rels]) return;
@@ -177,31 +193,200 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ---- epilogue: warp w reads the TMEM lane quarter w % 4
+        // ---- epilogue: warp w reads the TMEM lane quarter w % 4 (lane = edge), scales by the edge weight, and turns the
+        //      16-column slices through a padded staging tile so that a warp instruction adds 64 contiguous bytes to each of
+        //      8 destination rows instead of 16 bytes to each of 32
         const int q = warp & 3;
+        const uint32_t stg = base + (uint32_t)kUmStages * stage_bytes + (uint32_t)(warp - 2) * kUmStgBytes;
         for (int mt = 0; mt < mtiles; ++mt) {
             mbar_wait(tfull, mt & 1);
             tc_fence_after();
             const int e = e0 + mt * kUmM + q * 32 + lane;
             const bool valid = e < e1;
             const float v = valid ? A.val[e] : 0.f;
-            float* orow = A.out + (size_t)(valid ? A.scatter[e] : 0) * A.O + n0;
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                uint32_t r[32];
-                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                if (valid) {
+            const int drow = valid ? A.scatter[e] : -1;
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                uint32_t r[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (c0 + 4 * j < NT)
-                            atomicAdd(reinterpret_cast<float4*>(orow + c0 + 4 * j),
-                                      make_float4(v * __uint_as_float(r[4 * j]), v * __uint_as_float(r[4 * j + 1]),
-                                                  v * __uint_as_float(r[4 * j + 2]), v * __uint_as_float(r[4 * j + 3])));
-                    }
+                for (int j = 0; j < 4; ++j)
+                    sts128(stg + (uint32_t)(lane * kUmStgStride + 4 * j) * 4u,
+                           make_float4(v * __uint_as_float(r[4 * j]), v * __uint_as_float(r[4 * j + 1]),
+                                       v * __uint_as_float(r[4 * j + 2]), v * __uint_as_float(r[4 * j + 3])));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = i * 8 + (lane >> 2), ch = lane & 3;
+                    const int d = __shfl_sync(0xffffffffu, drow, row);
+                    const float4 t = lds128(stg + (uint32_t)(row * kUmStgStride + 4 * ch) * 4u);
+                    if (d >= 0) atomicAdd(reinterpret_cast<float4*>(A.out + (size_t)d * A.O + n0 + c0 + 4 * ch), t);
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  gW_p[i, o] += sum_{e in p} (val_e X[src_e, i]) G[dst_e, o]
+//
+// Per relation a GEMM whose INNER dimension is the gathered one: the rows TMA brings in (one edge each, 128 bytes = 64
+// consecutive inputs / outputs) are the k rows of MN-major operands — the canonical MN-major SWIZZLE_128B layout is
+// exactly "8 k-rows of 128 contiguous MN bytes" per 1 KB group, 64-element MN atoms `LBO` apart.  A CTA owns a chunk of
+// <= RGCN_CHUNK_EDGES edges of relation p, 128 rows (inputs) and NT <= 256 columns (outputs) of gW_p; stages of 64
+// edges; warps 2-5 scale the X rows of a landed stage by the edge weights in place (generic-proxy writes, then
+// fence.proxy.async) before the elected lane issues the stage's four MMAs; the 128 x NT accumulator leaves TMEM once per
+// chunk and is added to gW_p with 64-byte row pieces.
+// ---------------------------------------------------------------------------------------------------------------
+struct UmmaWgradArgs {
+    const int32_t* relptr; const int32_t* chunkptr; int num_rels;
+    const int32_t* src; const int32_t* dst; const float* val;
+    int I, O, NT;
+    float* gW;                 // (R', I, O)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t atom_stride_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((atom_stride_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kUmThreads, 2)
+k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, UmmaWgradArgs A, int tmem_cols) {
+    constexpr int kStages = 2, kE = 64;                   // edges per stage
+    extern __shared__ unsigned char um_smem[];
+    __shared__ __align__(8) unsigned long long bars[3 * kStages + 1];
+    __shared__ uint32_t tmem_slot;
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int NT = A.NT, mtiles = A.I / kUmM;
+    const int m0 = ((int)blockIdx.y % mtiles) * kUmM, n0 = ((int)blockIdx.y / mtiles) * NT;
+    const int nstages = (e1 - e0 + kE - 1) / kE, natoms_b = NT / 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = ((uint32_t)__cvta_generic_to_shared(um_smem) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = kUmABytes + (uint32_t)NT * 128u;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto scaled = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+    const uint32_t tfull = bar0 + 8u * (3 * kStages);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(scaled(s), 128); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ---- producer: lane = (atom parity, quad of four edges)
+        const int quad = lane & 15, half = lane >> 4;
+        for (int ks = 0; ks < nstages; ++ks) {
+            const int s = ks % kStages;
+            int rs[4], rd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e0 + ks * kE + 4 * quad + j, ee = e < e1 ? e : e0;   // past the end: a valid row, weight 0
+                rs[j] = A.src[ee]; rd[j] = A.dst[ee];
+            }
+            mbar_wait(empty(s), ((ks / kStages) & 1) ^ 1);
+            if (lane == 0) mbar_expect_tx(full(s), stage_bytes);
+            __syncwarp();
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+            tma_gather4(sa + (uint32_t)half * 8192u + (uint32_t)quad * 512u, &tmX, full(s), m0 + half * 64, rs[0], rs[1], rs[2], rs[3]);
+            for (int a = half; a < natoms_b; a += 2)
+                tma_gather4(sa + kUmABytes + (uint32_t)a * 8192u + (uint32_t)quad * 512u, &tmG, full(s), n0 + a * 64, rd[0], rd[1],
+                            rd[2], rd[3]);
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: both operands MN-major (bits 15 / 16 of the instruction descriptor)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
+                               ((uint32_t)(kUmM >> 4) << 24);
+        for (int ks = 0; ks < nstages; ++ks) {
+            const int s = ks % kStages;
+            mbar_wait(scaled(s), (ks / kStages) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = base + (uint32_t)s * stage_bytes;
+#pragma unroll
+                for (int k = 0; k < kE / 16; ++k)                 // 16 edges = two 8-row groups = 2048 bytes per step
+                    tc_mma_bf16(tmem, umma_desc_mn_sw128(sa + 2048u * k, 8192u), umma_desc_mn_sw128(sa + kUmABytes + 2048u * k, 8192u),
+                                idesc, (uint32_t)((ks | k) != 0));
+                tc_commit(empty(s));
+                if (ks == nstages - 1) tc_commit(tfull);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- warps 2-5: scale the X rows of each landed stage by the edge weights, then the epilogue
+        const int t = threadIdx.x - 64;                           // 0 .. 127
+        for (int ks = 0; ks < nstages; ++ks) {
+            const int s = ks % kStages;
+            mbar_wait(full(s), (ks / kStages) & 1);
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = t + 128 * i;                      // 16-byte piece of the 16 KB X tile
+                const int row = (idx >> 3) & 63;                  // edge within the stage (both atoms hold rows 0 .. 63)
+                const int e = e0 + ks * kE + row;
+                const float v = e < e1 ? A.val[e] : 0.f;
+                uint4 w = lds128u(sa + (uint32_t)idx * 16u);
+                uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a, b;
+                    unpack_bf16x2(wp[j], a, b);
+                    wp[j] = pack_bf16x2(a * v, b * v);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)idx * 16u), "r"(w.x), "r"(w.y), "r"(w.z),
+                             "r"(w.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(scaled(s));
+        }
+        const int q = warp & 3;
+        const uint32_t stg = base + (uint32_t)kStages * stage_bytes + (uint32_t)(warp - 2) * kUmStgBytes;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float* gw = A.gW + ((size_t)p * A.I + m0 + q * 32) * A.O + n0;
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                sts128(stg + (uint32_t)(lane * kUmStgStride + 4 * j) * 4u,
+                       make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3])));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = i * 8 + (lane >> 2), ch = lane & 3;
+                const float4 v4 = lds128(stg + (uint32_t)(row * kUmStgStride + 4 * ch) * 4u);
+                atomicAdd(reinterpret_cast<float4*>(gw + (size_t)row * A.O + c0 + 4 * ch), v4);
+            }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -254,10 +439,54 @@ inline int launch_gemm_umma(UmmaArgs A, const __nv_bfloat16* X, int64_t N, const
     }
     int cols = 32;
     while (cols < NT) cols <<= 1;
-    const size_t smem = umma_smem_bytes(NT);
-    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int stages = 2;
+    if (const char* e = getenv("RGCN_UMMA_STAGES")) stages = atoi(e);
+    stages = stages < 2 ? 2 : (stages > kUmMaxStages ? kUmMaxStages : stages);
+    const size_t smem = umma_smem_bytes(NT, stages);
     dim3 grid((unsigned)chunks, (unsigned)(A.O / NT));
-    RGCN_LAUNCH(k_gemm_umma, grid, kUmThreads, smem, st, ta, tb, A, cols);
+    auto go = [&](auto kernel) -> int {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_LAUNCH(kernel, grid, kUmThreads, smem, st, ta, tb, A, cols);
+        return RGCN_OK;
+    };
+    if (stages == 2) return go(k_gemm_umma<2>);
+    if (stages == 3) return go(k_gemm_umma<3>);
+    return go(k_gemm_umma<4>);
+}
+
+inline bool umma_wgrad_shape_supported(int I, int O) { return umma_shape_supported(I, O) && I % kUmM == 0; }
+
+inline int umma_gather_map(CUtensorMap* tm, const __nv_bfloat16* M, int64_t rows, int width) {
+    rb_encode_fn enc = rb_encoder();
+    RGCN_REQUIRE(enc, RGCN_ERR_CUDA, "tensor-core GEMM: cuTensorMapEncodeTiled is not available from this driver");
+    memset(tm, 0, sizeof(*tm));
+    const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)width * 2};
+    const cuuint32_t box[2] = {64, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(M), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RGCN_REQUIRE(r == CUDA_SUCCESS, RGCN_ERR_CUDA, "tensor-core GEMM: gather tensor map failed with %d", (int)r);
+    return RGCN_OK;
+}
+
+// gW (R', I, O) must be zeroed by the caller; X (N, I) and Gb (N, O) are bf16
+inline int launch_wgrad_umma(UmmaWgradArgs A, const __nv_bfloat16* X, const __nv_bfloat16* Gb, int64_t N, int chunks,
+                             cudaStream_t st) {
+    const int NT = umma_col_tile(A.O);
+    A.NT = NT;
+    CUtensorMap tx, tg;
+    int rc = umma_gather_map(&tx, X, N, A.I);
+    if (rc) return rc;
+    rc = umma_gather_map(&tg, Gb, N, A.O);
+    if (rc) return rc;
+    int cols = 32;
+    while (cols < NT) cols <<= 1;
+    const size_t smem = umma_smem_bytes(NT, 2);
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)chunks, (unsigned)((A.I / kUmM) * (A.O / NT)));
+    RGCN_LAUNCH(k_wgrad_umma, grid, kUmThreads, smem, st, tx, tg, A, cols);
     return RGCN_OK;
 }
 
