@@ -532,6 +532,18 @@ def run_ours(args):
             sub['reference_gpu'] = ref_gpu
             if 'value' in ref_gpu:
                 sub['am16_fp32_vs_reference_gpu_per_edge'] = sub['am16_fp32']['value'] / ref_gpu['value']
+            if os.environ.get('RGCN_BENCH_SYN_NONE', '1') != '0':
+                # the undecomposed 512 x 512 variant of the synthetic layer: the tcgen05 gathered-GEMM kernels
+                try:
+                    torch.cuda.empty_cache()
+                    rec = engine_layer_record('syn_none', 2, 1)
+                    flops = 2.0 * rec['nnz'] * 512 * 512
+                    rec['tensor_tflops_fwd'] = flops / (rec['ms_fwd'] * 1e-3) / 1e12
+                    rec['tensor_frac_fwd'] = rec['tensor_tflops_fwd'] / peaks.get('bf16_tflops_sustained', 1400.0)
+                    rec['kernels'] = 'k_gemm_umma (forward, feature gradient), k_wgrad_umma: tcgen05 + TMA gather4 + TMEM'
+                    sub['syn_none'] = rec
+                except Exception as exc:  # noqa: BLE001
+                    sub['syn_none'] = {'error': f'{type(exc).__name__}: {str(exc)[:200]}'}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
