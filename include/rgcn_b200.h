@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RGCN_ABI_VERSION 14
+#define RGCN_ABI_VERSION 15
 #define RGCN_CHUNK_EDGES 1024   /* edges per relation-major work chunk (r_chunkptr) */
 #define RGCN_TILE_ROWS_PER_ITEM 256   /* rows per phase-2 work item of the tiled kernels */
 #define RGCN_SPAN_EDGES 1024          /* edges per phase-1 work item (span) of the tiled kernels */
@@ -187,12 +187,15 @@ typedef struct rgcn_graph {
     float* val;             /* nnz, in the caller's edge order: the reference's `vals` (layers.py:273) */
     int32_t* status;        /* 8 x int32: [0] = number of triples with s, p or o out of range (utils.py:163-164),
                                [1] / [2] = largest destination / source tile in edges, [3] = kernel watchdog flag,
-                               [4] / [5] = number of long destination / source rows */
+                               [4] / [5] = number of long destination / source rows, [6] = edges of the largest
+                               relation */
     int32_t* d_long;        /* nnz / RGCN_LONG_ROW + 1: destination rows with more than RGCN_LONG_ROW edges */
     int32_t* s_long;        /* nnz / RGCN_LONG_ROW + 1: source rows with more than RGCN_LONG_ROW edges */
     int64_t num_long_dst;   /* host copy of status[4], or -1 if the caller did not read it back (kernels then launch
                                the upper bound nnz / RGCN_LONG_ROW of CTAs and exit early) */
     int64_t num_long_src;   /* host copy of status[5], or -1 */
+    int64_t max_rel_edges;  /* host copy of status[6], or 0 if not read back: lets the dense tensor-core forward walk the
+                               relation chunks quantile by quantile (destination ranges stay L2-resident) */
     int64_t tile_edges;     /* 0: no tiling (ft / bt unused) */
     int64_t num_tiles;      /* T = (nnz - 1) / tile_edges + 1 (trailing tiles may be empty) */
     int64_t tile_capacity;  /* host copy of max(status[1], status[2]), filled by the caller after the build */

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tensor_core_gemm" 2>&1 | tail -12
-timeout 300 python tools/umma_vs_fma.py 10000000 2>&1 | tail -3 | tee $O/r2w_umma_vs_fma.json
+RGCN_UMMA_ORDER=l timeout 900 python bench.py --workload syn_none --steps 3 --warmup 3 --no-cpu-baseline > $O/r2w_bench_syn_none_lin.json 2> $O/r2w_syn_none.err; tail -3 $O/r2w_syn_none.err | cut -c1-300
+python tools/benchline.py < $O/r2w_bench_syn_none_lin.json

@@ -13,9 +13,9 @@ W = (torch.randn(Rp, I, O, device=dev) * 0.05).requires_grad_(True)
 x = torch.randn(N, I, device=dev).to(torch.bfloat16).requires_grad_(True)
 G = torch.randn(N, O, device=dev)
 res = {}
-for mode in ('1', '0'):
+for mode in ('1', '1m1', '0'):
     os.environ['RGCN_UMMA'] = mode[0]
-    os.environ['RGCN_UMMA_STAGES'] = mode[2:] if len(mode) > 1 else '2'
+    os.environ['RGCN_UMMA_WGRAD_MT'] = '1' if mode == '1m1' else '2'
     for _ in range(2):
         out = rgcn_propagate(plan, 'dense', I, O, x, weights=W)
         out.backward(G)
@@ -34,6 +34,7 @@ for mode in ('1', '0'):
     res[mode] = (e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps, out.detach().float().clone(), W.grad.clone())
 f1, b1, o1, g1 = res['1']; f0, b0, o0, g0 = res['0']
 flops = 2.0 * E * I * O
+print(json.dumps({'wgrad_tile_variants_fwd_bwd_ms': {k: (round(v[0], 2), round(v[1], 2)) for k, v in res.items()}}))
 print(json.dumps({'edges': E, 'ms_fwd_umma': f1, 'ms_fwd_fma': f0, 'speedup_fwd': f0 / f1, 'tflops_fwd_umma': flops / f1 / 1e9,
                   'ms_bwd_umma': b1, 'ms_bwd_fma': b0,
                   'max_abs_diff': float((o1 - o0).abs().max()), 'gW_max_abs_diff': float((g1 - g0).abs().max()), 'gW_scale': float(g0.abs().max()), 'scale': float(o0.abs().max())}))

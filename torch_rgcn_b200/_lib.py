@@ -36,7 +36,7 @@ class Graph(C.Structure):
                 ('s_rowptr', _p), ('s_dst', _p), ('s_rel', _p), ('s_val', _p),
                 ('r_relptr', _p), ('r_dst', _p), ('r_src', _p), ('r_val', _p),
                 ('r_dslot', _p), ('r_sslot', _p), ('r_chunkptr', _p),
-                ('val', _p), ('status', _p), ('d_long', _p), ('s_long', _p), ('num_long_dst', _i64), ('num_long_src', _i64),
+                ('val', _p), ('status', _p), ('d_long', _p), ('s_long', _p), ('num_long_dst', _i64), ('num_long_src', _i64), ('max_rel_edges', _i64),
                 ('tile_edges', _i64), ('num_tiles', _i64), ('tile_capacity', _i64), ('ring_depth', _i64),
                 ('ft', Tiling), ('bt', Tiling),
                 ('fuse_rows', _i64), ('fuse_cap', _i64), ('fuse_item_tiles', _i64), ('fuse_dirs', _i64),

@@ -217,15 +217,20 @@ __global__ void k_gather_slots(int64_t nnz, const int32_t* __restrict__ perm, co
     oval[e] = val[o];
 }
 
-// chunkptr[p] = number of RGCN_CHUNK_EDGES-sized chunks of relations < p (R' is small: one thread scans)
-__global__ void k_chunkptr(const int32_t* __restrict__ relptr, int64_t Rp, int32_t* __restrict__ chunkptr) {
+// chunkptr[p] = number of RGCN_CHUNK_EDGES-sized chunks of relations < p (R' is small: one thread scans);
+// status[6] = the largest relation in edges
+__global__ void k_chunkptr(const int32_t* __restrict__ relptr, int64_t Rp, int32_t* __restrict__ chunkptr,
+                           int32_t* __restrict__ status) {
     if (blockIdx.x || threadIdx.x) return;
-    int32_t acc = 0;
+    int32_t acc = 0, longest = 0;
     for (int64_t p = 0; p < Rp; ++p) {
         chunkptr[p] = acc;
-        acc += (relptr[p + 1] - relptr[p] + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
+        const int32_t n = relptr[p + 1] - relptr[p];
+        longest = n > longest ? n : longest;
+        acc += (n + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
     }
     chunkptr[Rp] = acc;
+    status[6] = longest;
 }
 
 
@@ -693,7 +698,7 @@ extern "C" int rgcn_graph_build(const int64_t* triples, int64_t nnz, int64_t N, 
         else {
             RGCN_LAUNCH(k_gather_slots, grid, kBlock, 0, stream, nnz, b.i1, b.inv_d, b.inv_s, g->r_dslot, g->r_sslot, g->val,
                         oval);
-            RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr);
+            RGCN_LAUNCH(k_chunkptr, 1, 32, 0, stream, g->r_relptr, Rp, g->r_chunkptr, g->status);
         }
     }
     RGCN_LAUNCH(k_long_rows, dim3(grid_for(N, kBlock), 2), kBlock, 0, stream, g->d_rowptr, g->s_rowptr, N, g->d_long, g->s_long,

@@ -556,7 +556,7 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         const int64_t n = s.N * (int64_t)s.O;
         RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, out, n, s.O, p->bias);
         UmmaArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, s.I, s.O, 0, out};
-        return launch_gemm_umma(U, static_cast<const __nv_bfloat16*>(X), s.N, wt, max_chunks(s), st);
+        return launch_gemm_umma(U, static_cast<const __nv_bfloat16*>(X), s.N, wt, max_chunks(s), st, g->max_rel_edges);
     }
     if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz) && max_chunks(s) <= 65535) {
         GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, A.W, s.I, s.O,

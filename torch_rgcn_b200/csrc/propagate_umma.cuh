@@ -42,7 +42,43 @@ struct UmmaArgs {
     const int32_t* gather; const int32_t* scatter; const float* val;
     int I, O, NT;
     float* out;
+    int maxc;                  // chunks of the largest relation: walk the chunks quantile by quantile; 0 = in list order
+    int group;                 // relations per quantile sweep (their weight tiles stay L2-resident together)
 };
+
+// Which chunk a CTA works on.  `slot` counts chunk slots, the column / row tiles of one chunk being adjacent CTAs (their
+// gathers meet in L2).  In list order, slot = chunk.  Quantile order (maxc > 0): relations are taken in groups of
+// `group`; within a group, slot = qq * group + j is the chunk of the group's j-th relation that covers the qq-th of maxc
+// quantiles of its (destination-sorted) edges.  The CTAs in flight at any time then scatter into one narrow range of
+// destination rows, which stays L2-resident while all relations of the group add to it — the output streams through
+// DRAM once per group instead of once per relation — and the group is small enough for its weight tiles to stay in L2
+// as well.  Slots no chunk maps to exit.
+__device__ __forceinline__ bool umma_chunk(const int32_t* __restrict__ relptr, const int32_t* __restrict__ chunkptr, int num_rels,
+                                           int maxc, int group, int slot, int& p, int& e0, int& e1) {
+    int c;
+    if (maxc > 0) {
+        const int per = maxc * group, g = slot / per, r = slot - g * per, qq = r / group;
+        p = g * group + (r - qq * group);
+        if (p >= num_rels) return false;
+        const int first = chunkptr[p], np = chunkptr[p + 1] - first;
+        if (np == 0) return false;
+        const int q = (int)(((long long)qq * np + maxc - 1) / maxc);
+        if (q >= np || (int)((long long)q * maxc / np) != qq) return false;
+        c = first + q;
+    } else {
+        c = slot;
+        if (c >= chunkptr[num_rels]) return false;
+        int lo = 0, hi = num_rels;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (chunkptr[mid] <= c) lo = mid; else hi = mid;
+        }
+        p = lo;
+    }
+    e0 = relptr[p] + (c - chunkptr[p]) * RGCN_CHUNK_EDGES;
+    e1 = min(relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    return true;
+}
 
 constexpr int kUmStgStride = 20;     // floats per staged row: 16 columns + 4 of padding (conflict-free 16-byte stores)
 constexpr int kUmStgBytes = 32 * kUmStgStride * 4;
@@ -112,17 +148,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     extern __shared__ unsigned char um_smem[];
     __shared__ __align__(8) unsigned long long bars[2 * kUmMaxStages + 2];
     __shared__ uint32_t tmem_slot;
-    const int c = blockIdx.x;
-    if (c >= A.chunkptr[A.num_rels]) return;
-    int lo = 0, hi = A.num_rels;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int p = lo;
-    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
-    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
-    const int NT = A.NT, n0 = blockIdx.y * NT;
+    const int NT = A.NT, ntile = A.O / NT, n0 = ((int)blockIdx.x % ntile) * NT;
+    int p, e0, e1;
+    if (!umma_chunk(A.relptr, A.chunkptr, A.num_rels, A.maxc, A.group, (int)blockIdx.x / ntile, p, e0, e1)) return;
     const int mtiles = (e1 - e0 + kUmM - 1) / kUmM, kblocks = (A.I + kUmK - 1) / kUmK;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = ((uint32_t)__cvta_generic_to_shared(um_smem) + 1023u) & ~1023u;
@@ -257,28 +285,26 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
            (1ull << 46) | (2ull << 61);
 }
 
-__global__ void __launch_bounds__(kUmThreads, 2)
+// kMT = 128-row tiles of gW_p per CTA: 1 (two CTAs per SM, two stages) or 2 (a 256 x NT tile on two TMEM accumulators that
+// share the G operand: a third less operand traffic per output; one CTA per SM, three stages)
+// Producer warps: a stage is (2 kMT + NT / 64) atoms x 16 gather4 copies, issued one at a time per warp, so kMT = 2 runs
+// two producer warps (warps 0 .. kProd - 1; MMA warp kProd; scale / epilogue warps kProd + 1 .. kProd + 4).
+template <int kMT>
+__global__ void __launch_bounds__((kMT + 5) * 32, kMT == 1 ? 2 : 1)
 k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, UmmaWgradArgs A, int tmem_cols) {
-    constexpr int kStages = 2, kE = 64;                   // edges per stage
+    constexpr int kStages = kMT == 1 ? 2 : 3, kE = 64, kProd = kMT;                   // edges per stage
     extern __shared__ unsigned char um_smem[];
     __shared__ __align__(8) unsigned long long bars[3 * kStages + 1];
     __shared__ uint32_t tmem_slot;
-    const int c = blockIdx.x;
-    if (c >= A.chunkptr[A.num_rels]) return;
-    int lo = 0, hi = A.num_rels;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int p = lo;
-    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
-    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
-    const int NT = A.NT, mtiles = A.I / kUmM;
-    const int m0 = ((int)blockIdx.y % mtiles) * kUmM, n0 = ((int)blockIdx.y / mtiles) * NT;
+    const int NT = A.NT, mtiles = A.I / (kUmM * kMT), ntiles = mtiles * (A.O / NT), tile = (int)blockIdx.x % ntiles;
+    const int m0 = (tile % mtiles) * kUmM * kMT, n0 = (tile / mtiles) * NT;
+    int p, e0, e1;
+    if (!umma_chunk(A.relptr, A.chunkptr, A.num_rels, 0, 1, (int)blockIdx.x / ntiles, p, e0, e1)) return;
     const int nstages = (e1 - e0 + kE - 1) / kE, natoms_b = NT / 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = ((uint32_t)__cvta_generic_to_shared(um_smem) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = kUmABytes + (uint32_t)NT * 128u;
+    constexpr uint32_t kXBytes = kUmABytes * kMT;          // X tile of a stage: 2 kMT atoms of 64 edges x 128 bytes
+    const uint32_t stage_bytes = kXBytes + (uint32_t)NT * 128u;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
@@ -290,7 +316,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kProd) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -300,9 +326,9 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 0) {
-        // ---- producer: lane = (atom parity, quad of four edges)
-        const int quad = lane & 15, half = lane >> 4;
+    if (warp < kProd) {
+        // ---- producers: copy i of a stage = (atom i / 16, quad of four edges i % 16), dealt over the producer lanes
+        const int quad = lane & 15, first = (int)threadIdx.x >> 4, natoms = 2 * kMT + natoms_b;
         for (int ks = 0; ks < nstages; ++ks) {
             const int s = ks % kStages;
             int rs[4], rd[4];
@@ -312,15 +338,16 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 rs[j] = A.src[ee]; rd[j] = A.dst[ee];
             }
             mbar_wait(empty(s), ((ks / kStages) & 1) ^ 1);
-            if (lane == 0) mbar_expect_tx(full(s), stage_bytes);
+            if (threadIdx.x == 0) mbar_expect_tx(full(s), stage_bytes);
             __syncwarp();
             const uint32_t sa = base + (uint32_t)s * stage_bytes;
-            tma_gather4(sa + (uint32_t)half * 8192u + (uint32_t)quad * 512u, &tmX, full(s), m0 + half * 64, rs[0], rs[1], rs[2], rs[3]);
-            for (int a = half; a < natoms_b; a += 2)
-                tma_gather4(sa + kUmABytes + (uint32_t)a * 8192u + (uint32_t)quad * 512u, &tmG, full(s), n0 + a * 64, rd[0], rd[1],
-                            rd[2], rd[3]);
+            for (int a = first; a < natoms; a += 2 * kProd) {
+                const uint32_t dst = sa + (uint32_t)a * 8192u + (uint32_t)quad * 512u;   // X atoms first, G atoms behind them
+                if (a < 2 * kMT) tma_gather4(dst, &tmX, full(s), m0 + a * 64, rs[0], rs[1], rs[2], rs[3]);
+                else tma_gather4(dst, &tmG, full(s), n0 + (a - 2 * kMT) * 64, rd[0], rd[1], rd[2], rd[3]);
+            }
         }
-    } else if (warp == 1) {
+    } else if (warp == kProd) {
         // ---- MMA issuer: both operands MN-major (bits 15 / 16 of the instruction descriptor)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
                                ((uint32_t)(kUmM >> 4) << 24);
@@ -331,9 +358,13 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             if (lane == 0) {
                 const uint32_t sa = base + (uint32_t)s * stage_bytes;
 #pragma unroll
-                for (int k = 0; k < kE / 16; ++k)                 // 16 edges = two 8-row groups = 2048 bytes per step
-                    tc_mma_bf16(tmem, umma_desc_mn_sw128(sa + 2048u * k, 8192u), umma_desc_mn_sw128(sa + kUmABytes + 2048u * k, 8192u),
-                                idesc, (uint32_t)((ks | k) != 0));
+                for (int k = 0; k < kE / 16; ++k) {               // 16 edges = two 8-row groups = 2048 bytes per step
+                    const uint64_t bd = umma_desc_mn_sw128(sa + kXBytes + 2048u * k, 8192u);
+#pragma unroll
+                    for (int mt = 0; mt < kMT; ++mt)
+                        tc_mma_bf16(tmem + (uint32_t)(mt * NT), umma_desc_mn_sw128(sa + (uint32_t)mt * kUmABytes + 2048u * k, 8192u), bd,
+                                    idesc, (uint32_t)((ks | k) != 0));
+                }
                 tc_commit(empty(s));
                 if (ks == nstages - 1) tc_commit(tfull);
             }
@@ -341,14 +372,14 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         }
     } else {
         // ---- warps 2-5: scale the X rows of each landed stage by the edge weights, then the epilogue
-        const int t = threadIdx.x - 64;                           // 0 .. 127
+        const int t = threadIdx.x - (kProd + 1) * 32;              // 0 .. 127
         for (int ks = 0; ks < nstages; ++ks) {
             const int s = ks % kStages;
             mbar_wait(full(s), (ks / kStages) & 1);
             const uint32_t sa = base + (uint32_t)s * stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = t + 128 * i;                      // 16-byte piece of the 16 KB X tile
+            for (int i = 0; i < 8 * kMT; ++i) {
+                const int idx = t + 128 * i;                      // 16-byte piece of the X tile
                 const int row = (idx >> 3) & 63;                  // edge within the stage (both atoms hold rows 0 .. 63)
                 const int e = e0 + ks * kE + row;
                 const float v = e < e1 ? A.val[e] : 0.f;
@@ -367,13 +398,14 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             mbar_arrive(scaled(s));
         }
         const int q = warp & 3;
-        const uint32_t stg = base + (uint32_t)kStages * stage_bytes + (uint32_t)(warp - 2) * kUmStgBytes;
+        const uint32_t stg = base + (uint32_t)kStages * stage_bytes + (uint32_t)(warp - kProd - 1) * kUmStgBytes;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        float* gw = A.gW + ((size_t)p * A.I + m0 + q * 32) * A.O + n0;
-        for (int c0 = 0; c0 < NT; c0 += 16) {
+        for (int cc = 0; cc < kMT * NT; cc += 16) {
+            const int mt = cc / NT, c0 = cc - mt * NT;
+            float* gw = A.gW + ((size_t)p * A.I + m0 + mt * kUmM + q * 32) * A.O + n0;
             uint32_t r[16];
-            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, r);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 sts128(stg + (uint32_t)(lane * kUmStgStride + 4 * j) * 4u,
@@ -391,7 +423,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1)
+    if (warp == kProd)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
@@ -409,7 +441,9 @@ inline bool umma_shape_supported(int I, int O) {
 }
 
 // `wt` = bf16 K-major weights from k_pack_wt_bf16: (R', O, I); X = gathered bf16 matrix (N, I); out (N, O) pre-set.
-inline int launch_gemm_umma(UmmaArgs A, const __nv_bfloat16* X, int64_t N, const __nv_bfloat16* wt, int chunks, cudaStream_t st) {
+// max_rel_edges > 0 (and `scatter` sorted within a relation, i.e. the forward): quantile order of the chunks
+inline int launch_gemm_umma(UmmaArgs A, const __nv_bfloat16* X, int64_t N, const __nv_bfloat16* wt, int chunks, cudaStream_t st,
+                            int64_t max_rel_edges = 0) {
     rb_encode_fn enc = rb_encoder();
     RGCN_REQUIRE(enc, RGCN_ERR_CUDA, "tensor-core GEMM: cuTensorMapEncodeTiled is not available from this driver");
     const int NT = umma_col_tile(A.O);
@@ -443,7 +477,25 @@ inline int launch_gemm_umma(UmmaArgs A, const __nv_bfloat16* X, int64_t N, const
     if (const char* e = getenv("RGCN_UMMA_STAGES")) stages = atoi(e);
     stages = stages < 2 ? 2 : (stages > kUmMaxStages ? kUmMaxStages : stages);
     const size_t smem = umma_smem_bytes(NT, stages);
-    dim3 grid((unsigned)chunks, (unsigned)(A.O / NT));
+    // quantile order only while most slots hold a chunk (relation sizes within ~4x of the largest on average)
+    int64_t slots = chunks;
+    const int64_t maxc = (max_rel_edges + RGCN_CHUNK_EDGES - 1) / RGCN_CHUNK_EDGES;
+    A.maxc = 0;
+    A.group = 1;
+    int64_t group = ((int64_t)32 << 20) / ((int64_t)A.I * A.O * 2);      // ~32 MB of bf16 weights per sweep
+    if (const char* e = getenv("RGCN_UMMA_GROUP")) group = atoi(e);
+    group = group < 1 ? 1 : (group > A.num_rels ? A.num_rels : group);
+    const int64_t ngroups = (A.num_rels + group - 1) / group;
+    // Quantile order is opt-in (RGCN_UMMA_ORDER=q): measured on the 200 M-edge 512 x 512 layer it LOSES to list order
+    // (forward 273 ms vs 232 ms, any group size) — the sorted, streaming read-modify-write of list order is cheaper than
+    // 150 concurrent chunks reducing into the same few thousand rows; kept for graphs whose output fits L2.
+    const char* order = getenv("RGCN_UMMA_ORDER");
+    if (order && order[0] == 'q' && maxc > 0 && maxc * ngroups * group <= 4 * (int64_t)chunks) {
+        A.maxc = (int)maxc; A.group = (int)group; slots = maxc * ngroups * group;
+    }
+    const int64_t nblk = slots * (A.O / NT);
+    RGCN_REQUIRE(nblk < (1ll << 31), RGCN_ERR_UNSUPPORTED, "tensor-core GEMM: %lld CTAs exceed the grid", (long long)nblk);
+    dim3 grid((unsigned)nblk);
     auto go = [&](auto kernel) -> int {
         RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RGCN_LAUNCH(kernel, grid, kUmThreads, smem, st, ta, tb, A, cols);
@@ -481,13 +533,20 @@ inline int launch_wgrad_umma(UmmaWgradArgs A, const __nv_bfloat16* X, const __nv
     if (rc) return rc;
     rc = umma_gather_map(&tg, Gb, N, A.O);
     if (rc) return rc;
+    int mt = (A.I % (2 * kUmM) == 0 && 2 * NT <= 512) ? 2 : 1;
+    if (const char* e = getenv("RGCN_UMMA_WGRAD_MT")) mt = (atoi(e) == 2 && A.I % (2 * kUmM) == 0 && 2 * NT <= 512) ? 2 : 1;
     int cols = 32;
-    while (cols < NT) cols <<= 1;
-    const size_t smem = umma_smem_bytes(NT, 2);
-    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)chunks, (unsigned)((A.I / kUmM) * (A.O / NT)));
-    RGCN_LAUNCH(k_wgrad_umma, grid, kUmThreads, smem, st, tx, tg, A, cols);
-    return RGCN_OK;
+    while (cols < mt * NT) cols <<= 1;
+    const size_t smem = 1024 + (size_t)(mt == 1 ? 2 : 3) * ((size_t)mt * kUmABytes + (size_t)NT * 128) + 4 * kUmStgBytes;
+    const int64_t nblk = (int64_t)chunks * (A.I / (kUmM * mt)) * (A.O / NT);
+    RGCN_REQUIRE(nblk < (1ll << 31), RGCN_ERR_UNSUPPORTED, "tensor-core weight gradient: %lld CTAs exceed the grid", (long long)nblk);
+    dim3 grid((unsigned)nblk);
+    auto go = [&](auto kernel) -> int {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_LAUNCH(kernel, grid, (mt + 5) * 32, smem, st, tx, tg, A, cols);
+        return RGCN_OK;
+    };
+    return mt == 2 ? go(k_wgrad_umma<2>) : go(k_wgrad_umma<1>);
 }
 
 }  // namespace rgcn

@@ -88,6 +88,7 @@ class GraphPlan:
                 for k, v in arrs.items():
                     setattr(fl, k, v.data_ptr())
         g.num_long_dst = g.num_long_src = -1
+        g.max_rel_edges = 0
         self.c = g
         if val is not None:
             val = val.to(device=dev, dtype=torch.float32).contiguous()
@@ -114,6 +115,7 @@ class GraphPlan:
             st = self.status.tolist()               # one host sync per plan build (the reference's asserts sync too)
             g.tile_capacity = self.tile_capacity = max(st[1], st[2])
             g.num_long_dst, g.num_long_src = st[4], st[5]
+            g.max_rel_edges = st[6]
             bad = st[0]
             assert bad == 0 or not validate, f'{bad} triples have a node or relation id out of range ' \
                                              f'(num_nodes={num_nodes}, num_relations={num_rels})'
