@@ -43,6 +43,12 @@ WORKLOADS = {
     'wn18': dict(shape='wn18', kind='lp', in_f=16, out_f=16, decomp=None, dtype='f32', vertical=False,
                  label='WN18-shaped lp rgcn layer (40,943 nodes, R\'=37, 70,721 sampled triples -> nnz=253,106), '
                        '16->16, fp32; graph build inside the step'),
+    # the LP layer of configs/rgcn/lp-FB-toy.yaml (500 wide, 100 blocks of 5 x 5, dense 500 x 500 self-loop weight) on an
+    # FB15k-237-shaped graph: block relations in the generic kernel, the self-loop relation as a gathered GEMM
+    'fb15k_block': dict(shape='fb15k237', kind='lp', in_f=500, out_f=500, decomp={'type': 'block', 'num_blocks': 100},
+                        dtype='f32', vertical=False,
+                        label='FB15k-237-shaped lp rgcn layer (14,541 nodes, R\'=475, 136,057 sampled triples), block-diagonal '
+                              'nb=100 (5x5) + dense self-loop weight, 500->500, fp32; graph build inside the step'),
     # the whole two-layer NodeClassifier step (featureless layer 1 -> ReLU -> layer 2 -> CE loss)
     'aifb_model': dict(shape='aifb', kind='nc_model', in_f=None, out_f=4, hidden=16, decomp=None, dtype='f32',
                        vertical=False, label='AIFB-shaped 2-layer NodeClassifier step (8,285 nodes, R\'=91, '

@@ -275,6 +275,42 @@ def test_lp_vs_oracle_seeded(cuda_device, decomp, vertical):
     _compare(out, ref_g, layer, feats, ref_out, atol=ATOL, rtol=2e-4)
 
 
+@pytest.mark.parametrize('width,nb,mode', [(40, 8, 'eval'), (40, 8, 'schlichtkrull-dropout'), (40, 8, 'self-loop'),
+                                           (500, 100, 'schlichtkrull-dropout')])
+def test_lp_wide_block_layer_with_dense_self_loop(cuda_device, width, nb, mode):
+    """The LP block layer at the widths the reference ships (configs/rgcn/lp-FB-toy.yaml: 500 wide, 100 blocks of 5 x 5,
+    a dense 500 x 500 self-loop weight): block relations in the generic kernel, the self-loop relation as one gathered
+    GEMM in the tiled kernels (forward, feature gradient, blocks_self gradient), with both self-loop dropout modes."""
+    from torch_rgcn_b200.layers import RelationalGraphConvolutionLP
+    from torch_rgcn_b200.synthetic import random_triples
+    N, R, E = (900, 5, 4000) if width > 100 else (2500, 9, 12000)
+    t = random_triples(N, R, E, seed=3).to(cuda_device)
+    torch.manual_seed(8)
+    drop = {'general': 0.0, 'self_loop': 0.3, 'self_loop_type': mode if mode != 'eval' else 'schlichtkrull-dropout'}
+    layer = RelationalGraphConvolutionLP(num_nodes=N, num_relations=2 * R + 1, in_features=width, out_features=width,
+                                         edge_dropout=drop, decomposition={'type': 'block', 'num_blocks': nb},
+                                         vertical_stacking=False, w_init='glorot-normal', b_init='zeros').to(cuda_device)
+    with torch.no_grad():
+        layer.bias.normal_()
+    feats = torch.randn(N, width, device=cuda_device, requires_grad=True)
+    keep = mask = None
+    layer.train(mode != 'eval')
+    gen = torch.Generator().manual_seed(1)
+    if mode == 'self-loop':
+        keep = torch.rand(N, generator=gen) > 0.3
+        layer._test_keep = keep
+    elif mode == 'schlichtkrull-dropout':
+        mask = (torch.rand(N, width, generator=gen) > 0.3).float() / 0.7
+        layer._test_self_mask = mask
+    out = layer(t, feats)
+    G = torch.randn_like(out)
+    out.backward(G)
+    ref_out, ref_g = orc.lp_layer(t.cpu().numpy(), N, 2 * R + 1, _params_np(layer), feats.detach().cpu().numpy(), False,
+                                  G.cpu().numpy(), keep=None if keep is None else keep.numpy(),
+                                  self_mask=None if mask is None else mask.numpy())
+    _compare(out, ref_g, layer, feats, ref_out, atol=ATOL, rtol=2e-4)
+
+
 def test_lp_empty_graph_and_isolated_nodes(cuda_device):
     """E = 0: only self-loops remain; with self-loop dropout some nodes receive nothing at all."""
     from torch_rgcn_b200.layers import RelationalGraphConvolutionLP

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
     __shared__ __align__(16) float Gs[TE][T];
     const int I = A.I, O = A.O;
     const int tiles_j = (O + T - 1) / T;
-    const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j, p = blockIdx.y;
+    const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j, p = blockIdx.y + A.rel0;
+    const float* mask = (A.mask && p == A.mask_rel) ? A.mask : nullptr;
     const int e0 = A.relptr[p], e1 = A.relptr[p + 1];
     const int n = e1 - e0;
     if (n <= 0) return;
@@ -119,6 +120,13 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
             if (cj + 1 < O) gv.y = gr[1];
             if (cj + 2 < O) gv.z = gr[2];
             if (cj + 3 < O) gv.w = gr[3];
+            if (mask) {
+                const float* mr = mask + (size_t)A.dst[e] * O + tj * T + lc;
+                if (cj + 0 < O) gv.x *= mr[0];
+                if (cj + 1 < O) gv.y *= mr[1];
+                if (cj + 2 < O) gv.z *= mr[2];
+                if (cj + 3 < O) gv.w *= mr[3];
+            }
         }
         __syncthreads();                                     // the previous slab has been consumed
         *reinterpret_cast<float4*>(&Xs[le][lc]) = xv;
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
     }
-    float* gw = A.gW + (size_t)p * I * O;
+    float* gw = A.gW + (size_t)(p - A.rel0) * I * O;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = ti * T + ty * 4 + i;
@@ -164,6 +172,7 @@ struct GemmArgs {
     const float* in_mask;         // (N, I): multiplies the gathered rows of relation mask_rel
     int mask_rel;
     float* out;
+    int only_rel_plus1;           // 0: all relations; else only relation only_rel_plus1 - 1, whose weight is W[0]
 };
 
 template <typename XT>
@@ -179,13 +188,14 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
         if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
     }
     const int p = lo;
+    if (A.only_rel_plus1 && p + 1 != A.only_rel_plus1) return;
     const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
     const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
     const int I = A.I, O = A.O, tj = blockIdx.x;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int le = tid >> 2, lk = (tid & 3) * 4;             // X loader: edge le of the sub-tile, inner offsets lk .. lk + 3
     const int wk = tid >> 4, wc = (tid & 15) * 4;            // W loader: inner row wk of the slab, columns wc .. wc + 3
-    const float* Wp = A.W + (size_t)p * I * O;
+    const float* Wp = A.W + (A.only_rel_plus1 ? 0 : (size_t)p * I * O);
     const float* imask = (A.in_mask && p == A.mask_rel) ? A.in_mask : nullptr;
     const float* omask = (A.out_mask && p == A.mask_rel) ? A.out_mask : nullptr;
     const bool vec_w = (O & 3) == 0, vec_x = (I & 3) == 0 && sizeof(XT) == 4;
@@ -265,14 +275,21 @@ __global__ void k_init_rows(float* __restrict__ out, int64_t n, int O, const flo
     if (i < n) out[i] = bias ? bias[i % O] : 0.f;
 }
 
+// RGCN_SPLIT_SELF=0 keeps the dense self-loop weight of LP block layers on the generic kernels (A/B measurements)
+bool split_self_enabled() {
+    const char* e = getenv("RGCN_SPLIT_SELF");
+    return !(e && e[0] == '0');
+}
+
 bool dense_tiled_shape(int form, int featureless, int I, int O, int64_t nnz) {
     return form == RGCN_W_DENSE && !featureless && (int64_t)I * O >= 1024 && nnz > 0;
 }
 
 template <typename XT>
-int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bias, int chunks, cudaStream_t st) {
+int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bias, int chunks, cudaStream_t st,
+                            bool init = true) {
     const int64_t n = N * (int64_t)A.O;
-    RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, A.out, n, A.O, bias);
+    if (init) RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, A.out, n, A.O, bias);
     RGCN_REQUIRE(chunks <= 65535, RGCN_ERR_UNSUPPORTED, "dense tiled propagation: %d chunks exceed the grid", chunks);
     dim3 grid((unsigned)((A.O + 63) / 64), (unsigned)chunks);
     RGCN_LAUNCH((k_prop_dense_tiled<XT>), grid, 256, 0, st, A, X);
@@ -281,7 +298,8 @@ int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bia
 
 template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
-    if (A.form == RGCN_W_DENSE && !A.mask && (int64_t)A.I * A.O >= 1024) {
+    if (A.form == RGCN_W_DENSE && (int64_t)A.I * A.O >= 1024) {
+        Rp -= A.rel0;                                  // relations rel0 .. R' - 1 (the self relation alone, or all)
         const int tiles = ((A.I + 63) / 64) * ((A.O + 63) / 64);
         // up to 64 slices per relation, sized for the longest one a graph of nnz edges can hold (the self-loop
         // relation of an LP step has more edges than all others together); CTAs of slices past a relation's end exit
@@ -564,8 +582,18 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         if (bf16) return launch_prop_dense_tiled(Gm, static_cast<const __nv_bfloat16*>(X), s.N, p->bias, max_chunks(s), st);
         return launch_prop_dense_tiled(Gm, static_cast<const float*>(X), s.N, p->bias, max_chunks(s), st);
     }
-    if (bf16) return launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
-    return launch_prop(A, static_cast<const float*>(X), st);
+    // LP block decomposition with a dense self-loop weight (layers.py:534-548): the block relations take the generic
+    // kernel, the self-loop relation — N edges through one (I, O) matrix, a plain GEMM — the tiled one
+    const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && !p->featureless && (int64_t)s.I * s.O >= 1024 &&
+                            s.nnz > 0 && max_chunks(s) <= 65535 && split_self_enabled();
+    if (split_self) A.skip_rel_plus1 = (int)s.Rp;
+    if (bf16) rc = launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
+    else rc = launch_prop(A, static_cast<const float*>(X), st);
+    if (rc || !split_self) return rc;
+    GemmArgs Gs{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, p->blocks_self, s.I, s.O,
+                p->self_mask, nullptr, (int)s.Rp - 1, out, (int)s.Rp};
+    if (bf16) return launch_prop_dense_tiled(Gs, static_cast<const __nv_bfloat16*>(X), s.N, nullptr, max_chunks(s), st, false);
+    return launch_prop_dense_tiled(Gs, static_cast<const float*>(X), s.N, nullptr, max_chunks(s), st, false);
 }
 
 extern "C" size_t rgcn_backward_workspace_bytes(const rgcn_graph* g, const rgcn_params* p, int x_dtype) {
@@ -784,7 +812,15 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
                         nullptr, p->self_mask, (int)s.Rp - 1, gx_f32};
             rc = launch_prop_dense_tiled(Gm, G, s.N, (const float*)nullptr, max_chunks(s), st);
         } else {
+            const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && IO >= 1024 && s.nnz > 0 &&
+                                    max_chunks(s) <= 65535 && split_self_enabled();
+            if (split_self) A.skip_rel_plus1 = (int)s.Rp;
             rc = launch_prop(A, G, st);
+            if (!rc && split_self) {
+                GemmArgs Gs{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.blocks_self, s.O, s.I,
+                            nullptr, p->self_mask, (int)s.Rp - 1, gx_f32, (int)s.Rp};
+                rc = launch_prop_dense_tiled(Gs, G, s.N, (const float*)nullptr, max_chunks(s), st, false);
+            }
         }
         if (rc) return rc;
         rc = finish_gx();
@@ -847,8 +883,20 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         rc = launch_wgrad_umma(U, static_cast<const __nv_bfloat16*>(X), gb16_dense, s.N, max_chunks(s), st);
     }
     if (rc > 0) {
-        if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
-        else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+        // the dense self-loop weight of an LP block layer: its gradient is one gathered GEMM over the self-loop relation
+        WGradArgs Ws = Wg;
+        const bool split_self = p->form == RGCN_W_BLOCK && gr->blocks_self && IO >= 1024 && split_self_enabled();
+        if (split_self) Wg.gself = nullptr;
+        rc = RGCN_OK;
+        if (!split_self || gr->blocks) {
+            if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
+            else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+        }
+        if (!rc && split_self) {
+            Ws.form = RGCN_W_DENSE; Ws.gW = gr->blocks_self; Ws.rel0 = (int)s.Rp - 1;
+            if (x_dtype == RGCN_BF16) rc = launch_wgrad(Ws, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
+            else rc = launch_wgrad(Ws, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
+        }
     }
     if (rc) return rc;
     if (p->form == RGCN_W_BASIS) {

@@ -30,6 +30,7 @@ struct PropArgs {
     const float* out_mask;    // (nrows, O): multiplies the transformed segment of relation mask_rel
     const float* in_mask;     // (N, I): multiplies source rows of relation mask_rel before aggregation
     int mask_rel;
+    int skip_rel_plus1;         // 0: none; else edges of relation skip_rel_plus1 - 1 are left to another kernel
     float* out;
     const int32_t* long_list;   // rows with more than RGCN_LONG_ROW edges (may be NULL: no special handling)
     const int32_t* long_count;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256) k_prop_generic(PropArgs A, const XT* __re
                     }
                     continue;
                 }
+                if (r + 1 == A.skip_rel_plus1) continue;
                 if (r != cur) {
                     if (cur >= 0) transform(cur);
 #pragma unroll
@@ -180,6 +182,7 @@ struct WGradArgs {
     float* gblocks;   // (Rb, nb, bi, bo)
     float* gself;     // (I, O)
     int tile;         // edges staged per smem tile
+    int rel0;         // tiled dense kernel: first relation of the launch, and the relation gW[0] belongs to
 };
 
 template <typename XT, int KE>

@@ -10,6 +10,7 @@ SHAPES = {
     'mutag': (23644, 23, 74227),
     'am': (1666764, 133, 5988321),
     'wn18': (40943, 18, 141442),
+    'fb15k237': (14541, 237, 272115),
     'syn': (5000000, 128, 100000000),
 }
 
