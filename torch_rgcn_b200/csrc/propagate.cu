@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
     const float* imask = (A.in_mask && p == A.mask_rel) ? A.in_mask : nullptr;
     const float* omask = (A.out_mask && p == A.mask_rel) ? A.out_mask : nullptr;
     const bool vec_w = (O & 3) == 0, vec_x = (I & 3) == 0 && sizeof(XT) == 4;
-    for (int sub = e0; sub < e1; sub += T) {
+    for (int sub = e0 + T * (int)blockIdx.z; sub < e1; sub += T * (int)gridDim.z) {
         const int e = sub + le;
         const int64_t grow = e < e1 ? A.gather[e] : -1;
         float acc[4][4] = {};
@@ -275,6 +275,152 @@ __global__ void k_init_rows(float* __restrict__ out, int64_t n, int O, const flo
     if (i < n) out[i] = bias ? bias[i % O] : 0.f;
 }
 
+// Block-diagonal weights of any block size (the 100 blocks of 5 x 5 of configs/rgcn/lp-FB-toy.yaml, 10 of 5 x 5, ...) that
+// the templated relation-batched kernels do not cover.  Relation-major and edge-parallel instead of one warp per
+// destination row: a CTA owns a chunk of <= RGCN_CHUNK_EDGES edges of one relation, so the relation's blocks (a few KB)
+// stay in L1; a warp takes one edge at a time, stages the gathered row in shared memory and adds
+// val * x blockdiag(W_p) to the destination row (out holds the bias beforehand).  The self-loop relation of an LP layer
+// (dense blocks_self) is skipped here and served by the tiled GEMM kernel.
+struct BlockEdgeArgs {
+    const int32_t* relptr; const int32_t* chunkptr; int num_rels;
+    const int32_t* gather; const int32_t* scatter; const float* val;
+    const float* blocks;          // (Rb, nb, bi, bo)
+    int num_block_rels, nb, bi, bo, I, O;
+    float* out;
+};
+
+template <typename XT>
+__global__ void __launch_bounds__(256) k_block_edges(BlockEdgeArgs A, const XT* __restrict__ X) {
+    extern __shared__ float be_smem[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    if (p >= A.num_block_rels) return;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int I = A.I, O = A.O, bi = A.bi, bo = A.bo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* wofs = reinterpret_cast<int*>(be_smem);              // per output column: offset of W[kb][0][jj] in the relation's blocks
+    int* xofs = wofs + O;                                     // per output column: first input of its block
+    float* xs = be_smem + 2 * O + (size_t)warp * I;
+    for (int j = threadIdx.x; j < O; j += blockDim.x) {
+        const int kb = j / bo, jj = j - kb * bo;
+        wofs[j] = kb * bi * bo + jj;
+        xofs[j] = kb * bi;
+    }
+    __syncthreads();
+    const float* Wp = A.blocks + (size_t)p * A.nb * bi * bo;
+    for (int e = e0 + warp; e < e1; e += 8) {
+        const XT* xr = X + (size_t)A.gather[e] * I;
+        for (int i = lane; i < I; i += 32) xs[i] = to_f32(xr[i]);
+        __syncwarp();
+        const float v = A.val[e];
+        float* orow = A.out + (size_t)A.scatter[e] * O;
+        for (int j = lane; j < O; j += 32) {                  // (16-byte reductions of 4 outputs per lane measured slower:
+            const float* w = Wp + wofs[j];                     //  strided weight reads and shared-memory bank conflicts)
+            const float* x = xs + xofs[j];
+            float sum = 0.f;
+            for (int ii = 0; ii < bi; ++ii) sum = fmaf(x[ii], __ldg(w + ii * bo), sum);
+            atomicAdd(orow + j, v * sum);
+        }
+        __syncwarp();
+    }
+}
+
+// gblocks[p, kb, ii, jj] += sum_e val_e X[src_e, kb bi + ii] G[dst_e, kb bo + jj]: a CTA per relation chunk; a warp stages
+// the two rows of an edge, lane l owns the elements l, l + 32, ... of the relation's blocks in registers across its
+// edges and adds them to the gradient once per chunk.
+template <typename XT, int KE>
+__global__ void __launch_bounds__(256) k_block_wgrad(BlockEdgeArgs A, const XT* __restrict__ X, const float* __restrict__ G,
+                                                     float* __restrict__ gblocks) {
+    extern __shared__ float be_smem[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    if (p >= A.num_block_rels) return;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int I = A.I, O = A.O, bi = A.bi, bo = A.bo, nel = A.nb * bi * bo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xs = be_smem + (size_t)warp * (I + O);
+    float* gs = xs + I;
+    uint32_t xg[KE];                                          // input index | output index << 16 of the lane's elements
+    float acc[KE];
+    const int el0 = blockIdx.y * 32 * KE;                     // this CTA's part of the relation's block elements
+#pragma unroll
+    for (int k = 0; k < KE; ++k) {
+        const int el = el0 + lane + 32 * k;
+        acc[k] = 0.f;
+        xg[k] = 0;
+        if (el < nel) {
+            const int kb = el / (bi * bo), rem = el - kb * bi * bo, ii = rem / bo;
+            xg[k] = (uint32_t)(kb * bi + ii) | ((uint32_t)(kb * bo + (rem - ii * bo)) << 16);
+        }
+    }
+    for (int e = e0 + warp; e < e1; e += 8) {
+        const float v = A.val[e];
+        const XT* xr = X + (size_t)A.gather[e] * I;
+        const float* gr = G + (size_t)A.scatter[e] * O;
+        for (int i = lane; i < I; i += 32) xs[i] = v * to_f32(xr[i]);
+        for (int j = lane; j < O; j += 32) gs[j] = gr[j];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < KE; ++k) acc[k] = fmaf(xs[xg[k] & 0xffffu], gs[xg[k] >> 16], acc[k]);
+        __syncwarp();
+    }
+    float* dest = gblocks + (size_t)p * nel;
+#pragma unroll
+    for (int k = 0; k < KE; ++k) {
+        const int el = el0 + lane + 32 * k;
+        if (el < nel && acc[k] != 0.f) atomicAdd(dest + el, acc[k]);
+    }
+}
+
+// shapes for the two kernels above: featured block layers the templated kernels do not take, blocks of one relation
+// small enough for the per-lane register tile of the weight gradient
+bool block_edges_shape(int nb, int bi, int bo, int I, int O) {
+    const char* e = getenv("RGCN_BLOCK_EDGES");
+    if (e && e[0] == '0') return false;
+    return nb * bi * bo <= 32 * 80 * 4 && I >= 32 && O >= 32 && I < 65536 && O < 65536 &&
+           (size_t)(2 * O + 8 * (I + O)) * 4 <= 96 * 1024;
+}
+
+template <typename XT>
+int launch_block_edges(const BlockEdgeArgs& A, const XT* X, int chunks, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * A.O + 8 * A.I) * sizeof(float);
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_block_edges<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RGCN_LAUNCH((k_block_edges<XT>), chunks, 256, smem, st, A, X);
+    return RGCN_OK;
+}
+
+template <typename XT>
+int launch_block_wgrad(const BlockEdgeArgs& A, const XT* X, const float* G, float* gblocks, int chunks, cudaStream_t st) {
+    const size_t smem = (size_t)8 * (A.I + A.O) * sizeof(float);
+    const int nel = A.nb * A.bi * A.bo;
+    auto go = [&](auto kernel, int ke) -> int {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)chunks, (unsigned)((nel + 32 * ke - 1) / (32 * ke)));   // y: parts of 32 * KE block elements
+        RGCN_LAUNCH(kernel, grid, 256, smem, st, A, X, G, gblocks);
+        return RGCN_OK;
+    };
+    // one part per relation chunk whenever the elements fit the register tile (splitting 2,500 elements over three
+    // CTAs of 32 per lane measured slower than one CTA of 80 per lane: every part re-stages the same rows)
+    if (nel <= 32 * 8) return go(k_block_wgrad<XT, 8>, 8);
+    const char* ke = getenv("RGCN_BLOCK_WGRAD_KE");
+    if (nel <= 32 * 32 || (ke && atoi(ke) == 32)) return go(k_block_wgrad<XT, 32>, 32);
+    return go(k_block_wgrad<XT, 80>, 80);
+}
+
 // RGCN_SPLIT_SELF=0 keeps the dense self-loop weight of LP block layers on the generic kernels (A/B measurements)
 bool split_self_enabled() {
     const char* e = getenv("RGCN_SPLIT_SELF");
@@ -287,11 +433,16 @@ bool dense_tiled_shape(int form, int featureless, int I, int O, int64_t nnz) {
 
 template <typename XT>
 int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bias, int chunks, cudaStream_t st,
-                            bool init = true) {
+                            bool init = true, int64_t nnz_hint = 1 << 30) {
     const int64_t n = N * (int64_t)A.O;
     if (init) RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, A.out, n, A.O, bias);
     RGCN_REQUIRE(chunks <= 65535, RGCN_ERR_UNSUPPORTED, "dense tiled propagation: %d chunks exceed the grid", chunks);
-    dim3 grid((unsigned)((A.O + 63) / 64), (unsigned)chunks);
+    // small graphs: the 64-edge sub-tiles of a chunk are dealt over up to 16 CTAs so that the grid fills the GPU
+    const int tiles = (A.O + 63) / 64;
+    const int64_t edges = A.only_rel_plus1 ? N : nnz_hint;
+    int64_t z = (4 * kNumSMs) / (tiles * (edges / RGCN_CHUNK_EDGES + 1)) + 1;
+    z = z > 16 ? 16 : z;
+    dim3 grid((unsigned)tiles, (unsigned)chunks, (unsigned)z);
     RGCN_LAUNCH((k_prop_dense_tiled<XT>), grid, 256, 0, st, A, X);
     return RGCN_OK;
 }
@@ -579,15 +730,25 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz) && max_chunks(s) <= 65535) {
         GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, A.W, s.I, s.O,
                     p->self_mask, nullptr, (int)s.Rp - 1, out};
-        if (bf16) return launch_prop_dense_tiled(Gm, static_cast<const __nv_bfloat16*>(X), s.N, p->bias, max_chunks(s), st);
-        return launch_prop_dense_tiled(Gm, static_cast<const float*>(X), s.N, p->bias, max_chunks(s), st);
+        if (bf16) return launch_prop_dense_tiled(Gm, static_cast<const __nv_bfloat16*>(X), s.N, p->bias, max_chunks(s), st, true, s.nnz);
+        return launch_prop_dense_tiled(Gm, static_cast<const float*>(X), s.N, p->bias, max_chunks(s), st, true, s.nnz);
     }
     // LP block decomposition with a dense self-loop weight (layers.py:534-548): the block relations take the generic
     // kernel, the self-loop relation — N edges through one (I, O) matrix, a plain GEMM — the tiled one
     const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && !p->featureless && (int64_t)s.I * s.O >= 1024 &&
                             s.nnz > 0 && max_chunks(s) <= 65535 && split_self_enabled();
     if (split_self) A.skip_rel_plus1 = (int)s.Rp;
-    if (bf16) rc = launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
+    // blocks of any size: edge-parallel relation-major kernel (needs the self-loop relation, if dense, served separately)
+    const bool block_edges = p->form == RGCN_W_BLOCK && !p->featureless && (!p->blocks_self || split_self) &&
+                             (!p->self_mask || split_self) && s.nnz > 0 && block_edges_shape(s.nb, s.bi, s.bo, s.I, s.O);
+    if (block_edges) {
+        const int64_t n = s.N * (int64_t)s.O;
+        RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, out, n, s.O, p->bias);
+        BlockEdgeArgs B{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, p->blocks, s.Rb, s.nb, s.bi, s.bo,
+                        s.I, s.O, out};
+        if (bf16) rc = launch_block_edges(B, static_cast<const __nv_bfloat16*>(X), max_chunks(s), st);
+        else rc = launch_block_edges(B, static_cast<const float*>(X), max_chunks(s), st);
+    } else if (bf16) rc = launch_prop(A, static_cast<const __nv_bfloat16*>(X), st);
     else rc = launch_prop(A, static_cast<const float*>(X), st);
     if (rc || !split_self) return rc;
     GemmArgs Gs{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, p->blocks_self, s.I, s.O,
@@ -810,12 +971,22 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         } else if (dense_tiled_shape(A.form, 0, s.O, s.I, s.nnz) && max_chunks(s) <= 65535) {
             GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.W, s.O, s.I,
                         nullptr, p->self_mask, (int)s.Rp - 1, gx_f32};
-            rc = launch_prop_dense_tiled(Gm, G, s.N, (const float*)nullptr, max_chunks(s), st);
+            rc = launch_prop_dense_tiled(Gm, G, s.N, (const float*)nullptr, max_chunks(s), st, true, s.nnz);
         } else {
             const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && IO >= 1024 && s.nnz > 0 &&
                                     max_chunks(s) <= 65535 && split_self_enabled();
             if (split_self) A.skip_rel_plus1 = (int)s.Rp;
-            rc = launch_prop(A, G, st);
+            const bool block_edges = p->form == RGCN_W_BLOCK && (!p->blocks_self || split_self) &&
+                                     (!p->self_mask || split_self) && s.nnz > 0 && block_edges_shape(s.nb, s.bo, s.bi, s.O, s.I);
+            if (block_edges) {
+                const int64_t n = s.N * (int64_t)s.I;
+                RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, gx_f32, n, s.I, (const float*)nullptr);
+                BlockEdgeArgs B{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.blocks, s.Rb, s.nb,
+                                s.bo, s.bi, s.O, s.I, gx_f32};
+                rc = launch_block_edges(B, G, max_chunks(s), st);
+            } else {
+                rc = launch_prop(A, G, st);
+            }
             if (!rc && split_self) {
                 GemmArgs Gs{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.blocks_self, s.O, s.I,
                             nullptr, p->self_mask, (int)s.Rp - 1, gx_f32, (int)s.Rp};
@@ -888,7 +1059,14 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
         const bool split_self = p->form == RGCN_W_BLOCK && gr->blocks_self && IO >= 1024 && split_self_enabled();
         if (split_self) Wg.gself = nullptr;
         rc = RGCN_OK;
-        if (!split_self || gr->blocks) {
+        const bool block_edges = p->form == RGCN_W_BLOCK && gr->blocks && (!gr->blocks_self || split_self) &&
+                                 (!p->self_mask || split_self) && block_edges_shape(s.nb, s.bi, s.bo, s.I, s.O);
+        if (block_edges) {
+            BlockEdgeArgs B{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, nullptr, s.Rb, s.nb, s.bi,
+                            s.bo, s.I, s.O, nullptr};
+            if (x_dtype == RGCN_BF16) rc = launch_block_wgrad(B, static_cast<const __nv_bfloat16*>(X), G, gr->blocks, max_chunks(s), st);
+            else rc = launch_block_wgrad(B, static_cast<const float*>(X), G, gr->blocks, max_chunks(s), st);
+        } else if (!split_self || gr->blocks) {
             if (x_dtype == RGCN_BF16) rc = launch_wgrad(Wg, static_cast<const __nv_bfloat16*>(X), G, s.nnz, (int)s.Rp, st);
             else rc = launch_wgrad(Wg, static_cast<const float*>(X), G, s.nnz, (int)s.Rp, st);
         }
