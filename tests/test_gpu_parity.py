@@ -210,6 +210,9 @@ CASES = [
     ('block16', 3000, 11, 40000, 16, 16, {'type': 'block', 'num_blocks': 2}, False, False, False),
     ('block64', 2500, 9, 30000, 64, 64, {'type': 'block', 'num_blocks': 4}, True, False, False),
     ('block_5x5', 1500, 4, 15000, 50, 50, {'type': 'block', 'num_blocks': 10}, False, False, False),
+    ('block_4x4', 1500, 4, 15000, 64, 64, {'type': 'block', 'num_blocks': 16}, True, False, False),
+    ('block_2x2', 1500, 4, 15000, 80, 80, {'type': 'block', 'num_blocks': 40}, False, False, False),
+    ('block_3x7', 1500, 4, 15000, 36, 84, {'type': 'block', 'num_blocks': 12}, False, False, False),   # any-size block kernels
     ('basis200', 1200, 6, 12000, 200, 200, {'type': 'basis', 'num_bases': 2}, False, False, False),
     ('basis16x2', 3000, 11, 40000, 16, 2, {'type': 'basis', 'num_bases': 30}, True, False, False),
     ('featureless16', 3000, 11, 40000, None, 16, None, False, True, False),

@@ -275,6 +275,25 @@ __global__ void k_init_rows(float* __restrict__ out, int64_t n, int O, const flo
     if (i < n) out[i] = bias ? bias[i % O] : 0.f;
 }
 
+// Stage a gathered row in shared memory, `scale` applied: the loads of a batch of 16 x 32 elements are issued together
+// (a plain strided loop makes one round trip to L2 / DRAM per few elements).
+template <typename T>
+__device__ __forceinline__ void stage_row(float* __restrict__ dst, const T* __restrict__ src, int n, int lane, float scale) {
+    for (int base = 0; base < n; base += 512) {
+        float r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int i = base + lane + 32 * k;
+            r[k] = i < n ? to_f32(src[i]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int i = base + lane + 32 * k;
+            if (i < n) dst[i] = scale * r[k];
+        }
+    }
+}
+
 // Block-diagonal weights of any block size (the 100 blocks of 5 x 5 of configs/rgcn/lp-FB-toy.yaml, 10 of 5 x 5, ...) that
 // the templated relation-batched kernels do not cover.  Relation-major and edge-parallel instead of one warp per
 // destination row: a CTA owns a chunk of <= RGCN_CHUNK_EDGES edges of one relation, so the relation's blocks (a few KB)
@@ -291,7 +310,7 @@ struct BlockEdgeArgs {
 
 template <typename XT>
 __global__ void __launch_bounds__(256) k_block_edges(BlockEdgeArgs A, const XT* __restrict__ X) {
-    extern __shared__ float be_smem[];
+    extern __shared__ __align__(16) float be_smem[];
     const int c = blockIdx.x;
     if (c >= A.chunkptr[A.num_rels]) return;
     int lo = 0, hi = A.num_rels;
@@ -317,7 +336,7 @@ __global__ void __launch_bounds__(256) k_block_edges(BlockEdgeArgs A, const XT* 
     const float* Wp = A.blocks + (size_t)p * A.nb * bi * bo;
     for (int e = e0 + warp; e < e1; e += 8) {
         const XT* xr = X + (size_t)A.gather[e] * I;
-        for (int i = lane; i < I; i += 32) xs[i] = to_f32(xr[i]);
+        stage_row(xs, xr, I, lane, 1.f);
         __syncwarp();
         const float v = A.val[e];
         float* orow = A.out + (size_t)A.scatter[e] * O;
@@ -338,7 +357,7 @@ __global__ void __launch_bounds__(256) k_block_edges(BlockEdgeArgs A, const XT* 
 template <typename XT, int KE>
 __global__ void __launch_bounds__(256) k_block_wgrad(BlockEdgeArgs A, const XT* __restrict__ X, const float* __restrict__ G,
                                                      float* __restrict__ gblocks) {
-    extern __shared__ float be_smem[];
+    extern __shared__ __align__(16) float be_smem[];
     const int c = blockIdx.x;
     if (c >= A.chunkptr[A.num_rels]) return;
     int lo = 0, hi = A.num_rels;
@@ -371,8 +390,8 @@ __global__ void __launch_bounds__(256) k_block_wgrad(BlockEdgeArgs A, const XT* 
         const float v = A.val[e];
         const XT* xr = X + (size_t)A.gather[e] * I;
         const float* gr = G + (size_t)A.scatter[e] * O;
-        for (int i = lane; i < I; i += 32) xs[i] = v * to_f32(xr[i]);
-        for (int j = lane; j < O; j += 32) gs[j] = gr[j];
+        stage_row(xs, xr, I, lane, v);
+        stage_row(gs, gr, O, lane, 1.f);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < KE; ++k) acc[k] = fmaf(xs[xg[k] & 0xffffu], gs[xg[k] >> 16], acc[k]);
@@ -386,6 +405,152 @@ __global__ void __launch_bounds__(256) k_block_wgrad(BlockEdgeArgs A, const XT* 
     }
 }
 
+// Small square blocks with a compile-time size (2 x 2, 4 x 4, 5 x 5 — what `num_blocks` = width / 5 of the shipped LP
+// configs gives): lane = block.  The relation's blocks and the staged row sit in shared memory (lane strides of B*B and B
+// floats: conflict-free for odd B), the B*B products of a block are independent FMAs in registers, and the weight
+// gradient keeps a lane's blocks (KB = nb / 32 of them) in registers across the chunk.
+template <typename XT, int B>
+__global__ void __launch_bounds__(256) k_block_edges_sq(BlockEdgeArgs A, const XT* __restrict__ X) {
+    extern __shared__ __align__(16) float be_smem[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    if (p >= A.num_block_rels) return;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int I = A.I, O = A.O, nb = A.nb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* ws = be_smem;                                      // the relation's blocks: nb * B * B floats
+    float* xs = ws + (nb * B * B + 3) / 4 * 4 + (size_t)warp * (I + O);
+    float* os = xs + I;                                       // the edge's message, turned into coalesced 16-byte reductions
+    const float* Wp = A.blocks + (size_t)p * nb * B * B;
+    for (int i = threadIdx.x; i < nb * B * B; i += blockDim.x) ws[i] = Wp[i];
+    __syncthreads();
+    for (int e = e0 + warp; e < e1; e += 8) {
+        const XT* xr = X + (size_t)A.gather[e] * I;
+        stage_row(xs, xr, I, lane, 1.f);
+        __syncwarp();
+        const float v = A.val[e];
+        float* orow = A.out + (size_t)A.scatter[e] * O;
+        for (int kb = lane; kb < nb; kb += 32) {
+            const float* w = ws + kb * B * B;
+            const float* x = xs + kb * B;
+            float acc[B];
+#pragma unroll
+            for (int jj = 0; jj < B; ++jj) acc[jj] = 0.f;
+#pragma unroll
+            for (int ii = 0; ii < B; ++ii) {
+                const float xv = x[ii];
+#pragma unroll
+                for (int jj = 0; jj < B; ++jj) acc[jj] = fmaf(xv, w[ii * B + jj], acc[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < B; ++jj) os[kb * B + jj] = v * acc[jj];
+        }
+        __syncwarp();
+        if (((O | I) & 3) == 0) {
+            for (int j = 4 * lane; j < O; j += 128)
+                atomicAdd(reinterpret_cast<float4*>(orow + j), *reinterpret_cast<const float4*>(os + j));
+        } else {
+            for (int j = lane; j < O; j += 32) atomicAdd(orow + j, os[j]);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename XT, int B, int KB>
+__global__ void __launch_bounds__(256) k_block_wgrad_sq(BlockEdgeArgs A, const XT* __restrict__ X, const float* __restrict__ G,
+                                                        float* __restrict__ gblocks) {
+    extern __shared__ __align__(16) float be_smem[];
+    const int c = blockIdx.x;
+    if (c >= A.chunkptr[A.num_rels]) return;
+    int lo = 0, hi = A.num_rels;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.chunkptr[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    if (p >= A.num_block_rels) return;
+    const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
+    const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
+    const int I = A.I, O = A.O, nb = A.nb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xs = be_smem + (size_t)warp * (I + O);
+    float* gs = xs + I;
+    float acc[KB][B * B];
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+#pragma unroll
+        for (int i = 0; i < B * B; ++i) acc[k][i] = 0.f;
+    for (int e = e0 + warp; e < e1; e += 8) {
+        const float v = A.val[e];
+        const XT* xr = X + (size_t)A.gather[e] * I;
+        const float* gr = G + (size_t)A.scatter[e] * O;
+        stage_row(xs, xr, I, lane, v);
+        stage_row(gs, gr, O, lane, 1.f);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int kb = lane + 32 * k;
+            if (kb < nb) {
+                float gv[B];
+#pragma unroll
+                for (int jj = 0; jj < B; ++jj) gv[jj] = gs[kb * B + jj];
+#pragma unroll
+                for (int ii = 0; ii < B; ++ii) {
+                    const float xv = xs[kb * B + ii];
+#pragma unroll
+                    for (int jj = 0; jj < B; ++jj) acc[k][ii * B + jj] = fmaf(xv, gv[jj], acc[k][ii * B + jj]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    float* dest = gblocks + (size_t)p * nb * B * B;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int kb = lane + 32 * k;
+        if (kb < nb) {
+#pragma unroll
+            for (int i = 0; i < B * B; ++i)
+                if (acc[k][i] != 0.f) atomicAdd(dest + kb * B * B + i, acc[k][i]);
+        }
+    }
+}
+
+inline bool block_sq_shape(int nb, int bi, int bo, int I, int O) {
+    const char* e = getenv("RGCN_BLOCK_SQ");
+    if (e && e[0] == '0') return false;
+    return bi == bo && (bi == 2 || bi == 4 || bi == 5) && nb <= 128 &&
+           (size_t)(nb * bi * bo + 8 * (I + O)) * 4 <= 96 * 1024;
+}
+
+template <typename XT, int B>
+int launch_block_edges_sq(const BlockEdgeArgs& A, const XT* X, int chunks, cudaStream_t st) {
+    const size_t smem = (size_t)((A.nb * B * B + 3) / 4 * 4 + 8 * (A.I + A.O)) * sizeof(float);
+    RGCN_CHECK_CUDA(cudaFuncSetAttribute((k_block_edges_sq<XT, B>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RGCN_LAUNCH((k_block_edges_sq<XT, B>), chunks, 256, smem, st, A, X);
+    return RGCN_OK;
+}
+
+template <typename XT, int B>
+int launch_block_wgrad_sq(const BlockEdgeArgs& A, const XT* X, const float* G, float* gblocks, int chunks, cudaStream_t st) {
+    const size_t smem = (size_t)8 * (A.I + A.O) * sizeof(float);
+    auto go = [&](auto kernel) -> int {
+        RGCN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_LAUNCH(kernel, chunks, 256, smem, st, A, X, G, gblocks);
+        return RGCN_OK;
+    };
+    if (A.nb <= 32) return go(k_block_wgrad_sq<XT, B, 1>);
+    if (A.nb <= 64) return go(k_block_wgrad_sq<XT, B, 2>);
+    return go(k_block_wgrad_sq<XT, B, 4>);
+}
+
 // shapes for the two kernels above: featured block layers the templated kernels do not take, blocks of one relation
 // small enough for the per-lane register tile of the weight gradient
 bool block_edges_shape(int nb, int bi, int bo, int I, int O) {
@@ -397,6 +562,11 @@ bool block_edges_shape(int nb, int bi, int bo, int I, int O) {
 
 template <typename XT>
 int launch_block_edges(const BlockEdgeArgs& A, const XT* X, int chunks, cudaStream_t st) {
+    if (block_sq_shape(A.nb, A.bi, A.bo, A.I, A.O)) {
+        if (A.bi == 2) return launch_block_edges_sq<XT, 2>(A, X, chunks, st);
+        if (A.bi == 4) return launch_block_edges_sq<XT, 4>(A, X, chunks, st);
+        return launch_block_edges_sq<XT, 5>(A, X, chunks, st);
+    }
     const size_t smem = (size_t)(2 * A.O + 8 * A.I) * sizeof(float);
     RGCN_CHECK_CUDA(cudaFuncSetAttribute(k_block_edges<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RGCN_LAUNCH((k_block_edges<XT>), chunks, 256, smem, st, A, X);
@@ -405,6 +575,11 @@ int launch_block_edges(const BlockEdgeArgs& A, const XT* X, int chunks, cudaStre
 
 template <typename XT>
 int launch_block_wgrad(const BlockEdgeArgs& A, const XT* X, const float* G, float* gblocks, int chunks, cudaStream_t st) {
+    if (block_sq_shape(A.nb, A.bi, A.bo, A.I, A.O)) {
+        if (A.bi == 2) return launch_block_wgrad_sq<XT, 2>(A, X, G, gblocks, chunks, st);
+        if (A.bi == 4) return launch_block_wgrad_sq<XT, 4>(A, X, G, gblocks, chunks, st);
+        return launch_block_wgrad_sq<XT, 5>(A, X, G, gblocks, chunks, st);
+    }
     const size_t smem = (size_t)8 * (A.I + A.O) * sizeof(float);
     const int nel = A.nb * A.bi * A.bo;
     auto go = [&](auto kernel, int ke) -> int {
