@@ -59,6 +59,7 @@ constexpr int kRbConsumers = kRbBlocks * kRbTurns;      // warps 0-7: warp = tur
 constexpr int kRbProducers = 4;                         // warps 8-11
 constexpr int kRbThreads = (kRbConsumers + kRbProducers) * 32;
 constexpr int kRbWidth = 64;                            // columns one launch computes: 4 blocks of 16
+constexpr int kRbItemWeight = 48;                       // cost of a work item's flush in tiles (CTA partition)
 static_assert(kRbStageTiles * kRbTurns == RGCN_FUSE_AHEAD, "a tile record names the relation of the warp's next stage");
 
 // gathered rows in shared memory: 128-byte rows with the TMA 128-byte swizzle, or 144-byte rows (linear copies)
@@ -195,9 +196,19 @@ __global__ void k_fused_init_shared(const int32_t* __restrict__ items, int n_ite
     }
 }
 
-template <typename OT, bool kGather4>
-__global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constant__ CUtensorMap tmap, RbArgs A,
+// kNarrow: the layer IS one 64-column group (64 -> 64, the headline shape): pitch, column offset and the relation stride
+// of the weight fragments are compile-time constants.
+template <typename OT, bool kGather4, bool kNarrow>
+__global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constant__ CUtensorMap tmap, RbArgs A_,
                                                             OT* __restrict__ out) {
+    struct Geo {
+        const RbArgs& a;
+        __device__ __forceinline__ int ld() const { return kNarrow ? kRbWidth : a.ld; }
+        __device__ __forceinline__ int col0() const { return kNarrow ? 0 : a.col0; }
+        __device__ __forceinline__ int rel_stride() const { return kNarrow ? kRbBlocks * 32 : a.rel_stride; }
+    };
+    const RbArgs& A = A_;
+    const Geo geo{A_};
     using XL = RbX<kGather4>;
     extern __shared__ unsigned char smem_rb[];
     const uint32_t base = (smem_u32(smem_rb) + 1023u) & ~1023u;
@@ -211,19 +222,21 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
 
     // ---- this CTA's share: a contiguous range of work items holding ~1/gridDim of the work
     const int4* items = reinterpret_cast<const int4*>(A.items);
-    // Cut by weight = tiles + items: item i starts at weight (first tile of i) + i, so both long items and runs of
-    // empty items (row blocks without edges still have to write their bias rows) spread over the CTAs.
+    // Cut by weight = tiles + kRbItemWeight * items: item i starts at weight (first tile of i) + kRbItemWeight * i, so both
+    // long items and runs of empty items spread over the CTAs.  An item costs its flush whether or not it has edges
+    // (640 rows x 256 B written from shared memory: measured ~5 us, the time of ~48 tiles) — with a weight of 1 the one CTA
+    // that inherited the ~1000 edge-less row blocks of a row-sharded 512-wide layer ran 5 ms per launch.
     const int IL = A.item_lo, IH = A.item_hi;
     auto first_item_at = [&](long long w) {                             // first item of [IL, IH) with start weight >= w
         int lo = IL, hi = IH;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if ((long long)__ldg(&items[mid].y) + mid < w) lo = mid + 1; else hi = mid;
+            if ((long long)__ldg(&items[mid].y) + (long long)kRbItemWeight * mid < w) lo = mid + 1; else hi = mid;
         }
         return lo;
     };
-    const long long w_lo = (long long)(IL < A.n_items ? __ldg(&items[IL].y) : A.total_tiles) + IL;
-    const long long w_hi = (long long)(IH < A.n_items ? __ldg(&items[IH].y) : A.total_tiles) + IH;
+    const long long w_lo = (long long)(IL < A.n_items ? __ldg(&items[IL].y) : A.total_tiles) + (long long)kRbItemWeight * IL;
+    const long long w_hi = (long long)(IH < A.n_items ? __ldg(&items[IH].y) : A.total_tiles) + (long long)kRbItemWeight * IH;
     const int G = gridDim.x, c = blockIdx.x;
     const int i0 = c == 0 ? IL : first_item_at(w_lo + (w_hi - w_lo) * c / G);
     const int i1 = c == G - 1 ? IH : first_item_at(w_lo + (w_hi - w_lo) * (c + 1) / G);
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                              (uint32_t)nt * kRbRecBytes, fb);
                 }
                 __syncwarp();
-                if (go) tma_gather4(xdst + (uint32_t)(q & 3) * 512u, &tmap, fb, A.col0, cur.x, cur.y, cur.z, cur.w);
+                if (go) tma_gather4(xdst + (uint32_t)(q & 3) * 512u, &tmap, fb, geo.col0(), cur.x, cur.y, cur.z, cur.w);
             } else {
                 const int rows[4] = {cur.x, cur.y, cur.z, cur.w};
                 int n = 0;
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                     for (int k = 0; k < 4; ++k)
                         if (rows[k] >= 0)
                             bulk_g2s(xdst + (uint32_t)((q & 3) * 4 + k) * XL::row_bytes,
-                                     A.src + ((size_t)rows[k] * A.ld + A.col0) * 2, 128u, fb);
+                                     A.src + ((size_t)rows[k] * geo.ld() + geo.col0()) * 2, 128u, fb);
                 }
             }
             slot += NP;
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     // threads one 128-byte row (bf16 output, 16-byte stores)
     const int fc4 = ctid & 15;                                          // float4 column of this thread in a row
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias + A.col0) + fc4);
+    if (A.bias) bias4 = __ldg(reinterpret_cast<const float4*>(A.bias + geo.col0()) + fc4);
     auto acc_addr_c = [&](int r, int c4) {                              // un-swizzled float4 c4 of local row r
         return acc0 + (uint32_t)r * 256u + (uint32_t)((((c4 >> 2) ^ (r & 1)) << 6) | ((c4 & 3) << 4));
     };
@@ -343,7 +356,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                     const float4 v = lds128(a0), w = lds128(a1);
                     const uint4 pk = make_uint4(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w), pack_bf16x2(w.x, w.y),
                                                 pack_bf16x2(w.z, w.w));
-                    const size_t o = (size_t)(row0 + r) * A.ld + A.col0 + 8 * c8;
+                    const size_t o = (size_t)(row0 + r) * geo.ld() + geo.col0() + 8 * c8;
                     if (A.n_peers == 0) {
                         *reinterpret_cast<uint4*>(out + o) = pk;
                     } else {
@@ -360,7 +373,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
                 const uint32_t a = acc_addr(r);
                 if (r < nrows) {
                     const float4 v = lds128(a);
-                    const size_t o = (size_t)(row0 + r) * A.ld + A.col0 + 4 * fc4;
+                    const size_t o = (size_t)(row0 + r) * geo.ld() + geo.col0() + 4 * fc4;
                     if (!item.w) *reinterpret_cast<float4*>(out + o) = v;
                     else atomicAdd(reinterpret_cast<float4*>(out + o), v);
                 }
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     for (int j = 0; j < kRbStageTiles; ++j) {
         const long long tile = (long long)tile_begin + turn * kRbStageTiles + j;
         const int rel = tile < tile_end ? __ldg(A.rec + tile * RGCN_FUSE_REC_WORDS + 33) : 0;
-        wr[j] = __ldg(wmine + (size_t)rel * A.rel_stride);
+        wr[j] = __ldg(wmine + (size_t)rel * geo.rel_stride());
     }
 
     uint4 rv[kRbStageTiles];            // per tile {offset of row g | rank, val, offset of row g + 8 | rank, val}
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) k_rowblock(const __grid_constan
     int fslot = turn;                   // pipeline slot and phase parity of this warp's next front stage (NS >= 2)
     uint32_t fpar = 0;
     const unsigned char* wbytes = reinterpret_cast<const unsigned char*>(wmine);
-    const uint32_t wrel_bytes = (uint32_t)A.rel_stride * 16u;
+    const uint32_t wrel_bytes = (uint32_t)geo.rel_stride() * 16u;
     auto front_tile = [&](uint32_t xs, uint32_t rs, int j) {
         rv[j] = lds128u(rs + j * kRbRecBytes + g * 16);
         hd[j] = lds32(rs + j * kRbRecBytes + 128);
@@ -658,7 +671,9 @@ inline int launch_fused_rows(const rgcn_graph* g, bool backward, const float* W,
         }
         return RGCN_OK;
     };
-    return tune.gather4 ? go(k_rowblock<OT, true>) : go(k_rowblock<OT, false>);
+    const char* nw = getenv("RGCN_FUSED_NARROW");
+    if (nb == 4 && !(nw && nw[0] == '0')) return tune.gather4 ? go(k_rowblock<OT, true, true>) : go(k_rowblock<OT, false, true>);
+    return tune.gather4 ? go(k_rowblock<OT, true, false>) : go(k_rowblock<OT, false, false>);
 }
 
 }  // namespace rgcn
