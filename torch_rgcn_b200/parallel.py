@@ -191,6 +191,10 @@ class _RowShardedApply(torch.autograd.Function):
         ctx.shard = shard
         ctx.n_params = len(params)
         ctx.save_for_backward(features, *params)
+        make = getattr(shard, '_generic_exchange', None)      # stand-in shards (CPU tests) exchange through the group
+        ex = make(out.device, out.size(1), features) if make is not None else None
+        if ex is not None:
+            return ex.gather_rows(0, out, shard.lo, shard.hi, shard.num_nodes, out.dtype)
         return gather_row_blocks(out, shard.num_nodes, shard.rows_per, shard.lo, shard.hi, shard.group, shard.out_comm_dtype)
 
     @staticmethod
@@ -199,7 +203,10 @@ class _RowShardedApply(torch.autograd.Function):
         features, *params = ctx.saved_tensors
         need = ctx.needs_input_grad                       # (shard, features, *params)
         g_feat, g_params = shard.backward_local(features, params, grad_out.contiguous(), need[1], need[2:])
-        if g_feat is not None:
+        ex = getattr(shard, '_gx', None)
+        if g_feat is not None and ex is not None:
+            g_feat = ex.gather_rows(1, g_feat, shard.lo, shard.hi, shard.num_nodes, g_feat.dtype)
+        elif g_feat is not None:
             g_feat = gather_row_blocks(g_feat, shard.num_nodes, shard.rows_per, shard.lo, shard.hi, shard.group,
                                        shard.grad_comm_dtype)
         for name, g in zip(shard.param_names, g_params):
@@ -215,17 +222,18 @@ class _Exchange:
     other buffer, and the barrier that ends every exchange keeps it from getting two steps ahead, so no barrier is
     needed before the writes.  slot(direction) -> (local buffer, handle, peer views, peer pointers)."""
 
-    def __init__(self, rows, device, group):
+    def __init__(self, rows, device, group, widths=(64, 64), dtype=torch.bfloat16):
         import torch.distributed._symmetric_memory as symm
         pg = group if group is not None else dist.group.WORLD
-        self.rows = rows
+        self.rows, self.widths, self.dtype = rows, tuple(widths), dtype
         self.slots = [[], []]                    # [direction][parity]
         self.step = [0, 0]
         for direction in range(2):
+            w = self.widths[direction]
             for _ in range(2):
-                t = symm.empty(rows, 64, dtype=torch.bfloat16, device=device)
+                t = symm.empty(rows, w, dtype=dtype, device=device)
                 h = symm.rendezvous(t, pg)
-                peers = [h.get_buffer(q, (rows, 64), torch.bfloat16) for q in range(h.world_size)]
+                peers = [h.get_buffer(q, (rows, w), dtype) for q in range(h.world_size)]
                 self.slots[direction].append((t, h, peers, [int(x) for x in h.buffer_ptrs]))
 
     def slot(self, direction):
@@ -233,13 +241,27 @@ class _Exchange:
         self.step[direction] = k + 1
         return self.slots[direction][k & 1]
 
+    def gather_rows(self, direction, x, lo, hi, num_nodes, out_dtype):
+        """x (N, d) with rows [lo, hi) valid on this rank -> (N, d) with every rank's rows: the copy engines push the
+        rank's rows (in the exchange dtype) into every rank's buffer over NVLink, one barrier, one widening copy."""
+        buf, h, peers, _ptrs = self.slot(direction)
+        W, r = h.world_size, h.rank
+        with torch.cuda.device(x.device):
+            if lo < hi:
+                mine = x[lo:hi] if x.dtype == self.dtype else x[lo:hi].to(self.dtype)
+                for q in range(W):
+                    peers[(r + q) % W][lo:hi].copy_(mine, non_blocking=True)
+            h.barrier(channel=0)
+        return buf[:num_nodes].to(out_dtype, copy=True)        # always a copy: the buffer is reused two steps later
+
     @staticmethod
-    def create(rows, device, group):
+    def create(rows, device, group, widths=(64, 64), dtype=torch.bfloat16):
         """None when symmetric memory cannot be set up (no peer access, a CPU group): callers use NCCL instead."""
-        if os.environ.get('RGCN_SHARD_COMM', 'symm') != 'symm' or dist.get_world_size(group) > 8:
+        if os.environ.get('RGCN_SHARD_COMM', 'symm') != 'symm' or dist.get_world_size(group) > 8 or \
+                dist.get_backend(group) != 'nccl':
             return None
         try:
-            return _Exchange(rows, device, group)
+            return _Exchange(rows, device, group, widths, dtype)
         except Exception as exc:  # noqa: BLE001
             if dist.get_rank(group) == 0:
                 print(f'torch_rgcn_b200: symmetric memory unavailable ({type(exc).__name__}: {str(exc)[:200]}); '
@@ -371,9 +393,22 @@ class RowShardedNC(torch.nn.Module):
         self.chunks = int(chunks if chunks is not None else os.environ.get('RGCN_SHARD_CHUNKS', '2'))
         self._plans = None
         self._exchange = None
+        self._gx = None                                   # exchange buffers of the generic path
+        self._gx_key = None
 
     def sync_parameter_grads(self):
         """Nothing to do (kept for interface parity with RelationShardedNC)."""
+
+    def _generic_exchange(self, device, out_width, features):
+        """Symmetric-memory exchange buffers of the generic path (bf16 layers with features: rows travel as bf16), or None:
+        then the rows go through NCCL all-gathers."""
+        if features is None or features.dtype != torch.bfloat16:
+            return None
+        key = (str(device), out_width, features.size(1))
+        if self._gx_key != key:
+            self._gx_key = key
+            self._gx = _Exchange.create(self.num_nodes, device, self.group, (out_width, features.size(1)), torch.bfloat16)
+        return self._gx
 
     def _fused_rows(self, features):
         """Block height of the fused row-block kernel if this layer takes the overlapped 64-wide path, else 0."""
