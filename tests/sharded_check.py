@@ -33,6 +33,10 @@ def main():
         dict(in_f=16, out_f=8, decomp={'type': 'basis', 'num_bases': 5}, vertical=True, dtype=torch.float32),
         dict(in_f=64, out_f=64, decomp={'type': 'block', 'num_blocks': 4}, vertical=False, dtype=torch.bfloat16),
         dict(in_f=None, out_f=16, decomp=None, vertical=False, dtype=torch.float32),
+        # generic row-sharded path of bf16 layers: fused kernels per 64-column group / tcgen05 GEMMs on the local plans,
+        # rows exchanged through symmetric memory (different widths per direction in the second case)
+        dict(in_f=128, out_f=128, decomp={'type': 'block', 'num_blocks': 8}, vertical=True, dtype=torch.bfloat16),
+        dict(in_f=64, out_f=128, decomp=None, vertical=False, dtype=torch.bfloat16),
     ]
     for ci, c in enumerate(cases):
         t = random_triples(N, R, E, seed=ci, device=dev, rel_dist='zipf')
@@ -55,10 +59,15 @@ def main():
             x = torch.randn(N, c['in_f'], device=dev, generator=g).to(c['dtype'])
             x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
         o1 = ref(x1) if x1 is not None else ref()
-        o2 = sh(x2) if x2 is not None else sh()
         G = torch.randn(o1.shape, device=dev, generator=g)
+        for _ in range(3):                                   # several steps: the exchange buffers alternate
+            for prm in lay.parameters():
+                prm.grad = None
+            if x2 is not None:
+                x2.grad = None
+            o2 = sh(x2) if x2 is not None else sh()
+            o2.backward(G)
         o1.backward(G)
-        o2.backward(G)
         sh.sync_parameter_grads()
         tol = dict(atol=2e-4, rtol=2e-4) if c['dtype'] == torch.float32 else dict(atol=3e-2, rtol=3e-2)
         torch.testing.assert_close(o2, o1, **tol)
