@@ -104,22 +104,33 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int le = tid >> 4, lc = (tid & 15) * 4;            // loader role: edge le of the slab, columns lc .. lc + 3
     float acc[4][4] = {};
-    for (int s0 = b0; s0 < b1; s0 += TE) {
+    // loads of slab s + 1 are in flight while slab s is multiplied (software pipeline through registers)
+    auto load_slab = [&](int s0, float4& xv, float4& gv) {
         const int e = s0 + le;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+        xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        gv = xv;
         if (e < b1) {
             const float v = A.val[e];
             const XT* xr = X + (size_t)A.src[e] * I + ti * T + lc;
             const float* gr = G + (size_t)A.dst[e] * O + tj * T + lc;
             const int ci = ti * T + lc, cj = tj * T + lc;
-            if (ci + 0 < I) xv.x = v * to_f32(xr[0]);
-            if (ci + 1 < I) xv.y = v * to_f32(xr[1]);
-            if (ci + 2 < I) xv.z = v * to_f32(xr[2]);
-            if (ci + 3 < I) xv.w = v * to_f32(xr[3]);
-            if (cj + 0 < O) gv.x = gr[0];
-            if (cj + 1 < O) gv.y = gr[1];
-            if (cj + 2 < O) gv.z = gr[2];
-            if (cj + 3 < O) gv.w = gr[3];
+            if (sizeof(XT) == 4 && (I & 3) == 0 && ci + 3 < I) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xr));
+                xv = make_float4(v * t.x, v * t.y, v * t.z, v * t.w);
+            } else {
+                if (ci + 0 < I) xv.x = v * to_f32(xr[0]);
+                if (ci + 1 < I) xv.y = v * to_f32(xr[1]);
+                if (ci + 2 < I) xv.z = v * to_f32(xr[2]);
+                if (ci + 3 < I) xv.w = v * to_f32(xr[3]);
+            }
+            if ((O & 3) == 0 && cj + 3 < O) {
+                gv = __ldg(reinterpret_cast<const float4*>(gr));
+            } else {
+                if (cj + 0 < O) gv.x = gr[0];
+                if (cj + 1 < O) gv.y = gr[1];
+                if (cj + 2 < O) gv.z = gr[2];
+                if (cj + 3 < O) gv.w = gr[3];
+            }
             if (mask) {
                 const float* mr = mask + (size_t)A.dst[e] * O + tj * T + lc;
                 if (cj + 0 < O) gv.x *= mr[0];
@@ -128,10 +139,15 @@ __global__ void __launch_bounds__(256) k_wgrad_dense_tiled(WGradArgs A, const XT
                 if (cj + 3 < O) gv.w *= mr[3];
             }
         }
+    };
+    float4 xv, gv;
+    load_slab(b0, xv, gv);
+    for (int s0 = b0; s0 < b1; s0 += TE) {
         __syncthreads();                                     // the previous slab has been consumed
         *reinterpret_cast<float4*>(&Xs[le][lc]) = xv;
         *reinterpret_cast<float4*>(&Gs[le][lc]) = gv;
         __syncthreads();
+        if (s0 + TE < b1) load_slab(s0 + TE, xv, gv);
 #pragma unroll
         for (int k = 0; k < TE; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
@@ -203,9 +219,10 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
         const int e = sub + le;
         const int64_t grow = e < e1 ? A.gather[e] : -1;
         float acc[4][4] = {};
-        for (int k0 = 0; k0 < I; k0 += TK) {
-            float xv[4] = {0.f, 0.f, 0.f, 0.f};
-            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        // loads of slab k0 + TK are in flight while slab k0 is multiplied (software pipeline through registers)
+        auto load_slab = [&](int k0, float (&xv)[4], float4& wv) {
+            xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
+            wv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow >= 0) {
                 const int k = k0 + lk;
                 const XT* xr = X + (size_t)grow * I + k;
@@ -233,11 +250,17 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
                     if (col + 3 < O) wv.w = wr[3];
                 }
             }
+        };
+        float xv[4];
+        float4 wv;
+        load_slab(0, xv, wv);
+        for (int k0 = 0; k0 < I; k0 += TK) {
             __syncthreads();                                 // the previous slab has been consumed
 #pragma unroll
             for (int i = 0; i < 4; ++i) Xs[lk + i][le] = xv[i];
             *reinterpret_cast<float4*>(&Ws[wk][wc]) = wv;
             __syncthreads();
+            if (k0 + TK < I) load_slab(k0 + TK, xv, wv);
 #pragma unroll
             for (int k = 0; k < TK; ++k) {
                 const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
