@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
     constexpr int TK = 16, T = 64;
     __shared__ __align__(16) float Xs[TK][T + 4];
     __shared__ __align__(16) float Ws[TK][T];
-    const int c = blockIdx.y;
+    const int tiles_o = (A.O + 63) / 64;
+    const int c = (int)(blockIdx.x / tiles_o);                // column tiles of a chunk are adjacent CTAs
     if (c >= A.chunkptr[A.num_rels]) return;
     int lo = 0, hi = A.num_rels;
     while (hi - lo > 1) {
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
     if (A.only_rel_plus1 && p + 1 != A.only_rel_plus1) return;
     const int e0 = A.relptr[p] + (c - A.chunkptr[p]) * RGCN_CHUNK_EDGES;
     const int e1 = min(A.relptr[p + 1], e0 + RGCN_CHUNK_EDGES);
-    const int I = A.I, O = A.O, tj = blockIdx.x;
+    const int I = A.I, O = A.O, tj = (int)(blockIdx.x % tiles_o);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int le = tid >> 2, lk = (tid & 3) * 4;             // X loader: edge le of the sub-tile, inner offsets lk .. lk + 3
     const int wk = tid >> 4, wc = (tid & 15) * 4;            // W loader: inner row wk of the slab, columns wc .. wc + 3
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) k_prop_dense_tiled(GemmArgs A, const XT* 
     const float* imask = (A.in_mask && p == A.mask_rel) ? A.in_mask : nullptr;
     const float* omask = (A.out_mask && p == A.mask_rel) ? A.out_mask : nullptr;
     const bool vec_w = (O & 3) == 0, vec_x = (I & 3) == 0 && sizeof(XT) == 4;
-    for (int sub = e0 + T * (int)blockIdx.z; sub < e1; sub += T * (int)gridDim.z) {
+    for (int sub = e0 + T * (int)blockIdx.y; sub < e1; sub += T * (int)gridDim.y) {
         const int e = sub + le;
         const int64_t grow = e < e1 ? A.gather[e] : -1;
         float acc[4][4] = {};
@@ -634,20 +635,20 @@ int launch_prop_dense_tiled(GemmArgs A, const XT* X, int64_t N, const float* bia
                             bool init = true, int64_t nnz_hint = 1 << 30) {
     const int64_t n = N * (int64_t)A.O;
     if (init) RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, A.out, n, A.O, bias);
-    RGCN_REQUIRE(chunks <= 65535, RGCN_ERR_UNSUPPORTED, "dense tiled propagation: %d chunks exceed the grid", chunks);
     // small graphs: the 64-edge sub-tiles of a chunk are dealt over up to 16 CTAs so that the grid fills the GPU
     const int tiles = (A.O + 63) / 64;
     const int64_t edges = A.only_rel_plus1 ? N : nnz_hint;
     int64_t z = (4 * kNumSMs) / (tiles * (edges / RGCN_CHUNK_EDGES + 1)) + 1;
     z = z > 16 ? 16 : z;
-    dim3 grid((unsigned)tiles, (unsigned)chunks, (unsigned)z);
+    RGCN_REQUIRE((int64_t)tiles * chunks < (1ll << 31), RGCN_ERR_UNSUPPORTED, "dense tiled propagation: grid too large");
+    dim3 grid((unsigned)((int64_t)tiles * chunks), (unsigned)z);
     RGCN_LAUNCH((k_prop_dense_tiled<XT>), grid, 256, 0, st, A, X);
     return RGCN_OK;
 }
 
 template <typename XT>
 int launch_wgrad(const WGradArgs& A, const XT* X, const float* G, int64_t nnz, int Rp, cudaStream_t st) {
-    if (A.form == RGCN_W_DENSE && (int64_t)A.I * A.O >= 1024) {
+    if (A.form == RGCN_W_DENSE && (int64_t)A.I * A.O >= 1024 && Rp - A.rel0 <= 65535) {
         Rp -= A.rel0;                                  // relations rel0 .. R' - 1 (the self relation alone, or all)
         const int tiles = ((A.I + 63) / 64) * ((A.O + 63) / 64);
         // up to 64 slices per relation, sized for the longest one a graph of nnz edges can hold (the self-loop
@@ -925,7 +926,7 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
         UmmaArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, s.I, s.O, 0, out};
         return launch_gemm_umma(U, static_cast<const __nv_bfloat16*>(X), s.N, wt, max_chunks(s), st, g->max_rel_edges);
     }
-    if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz) && max_chunks(s) <= 65535) {
+    if (dense_tiled_shape(A.form, p->featureless, s.I, s.O, s.nnz)) {
         GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_src, g->r_dst, g->r_val, A.W, s.I, s.O,
                     p->self_mask, nullptr, (int)s.Rp - 1, out};
         if (bf16) return launch_prop_dense_tiled(Gm, static_cast<const __nv_bfloat16*>(X), s.N, p->bias, max_chunks(s), st, true, s.nnz);
@@ -934,7 +935,7 @@ extern "C" int rgcn_forward(const rgcn_graph* g, const rgcn_params* p, const voi
     // LP block decomposition with a dense self-loop weight (layers.py:534-548): the block relations take the generic
     // kernel, the self-loop relation — N edges through one (I, O) matrix, a plain GEMM — the tiled one
     const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && !p->featureless && (int64_t)s.I * s.O >= 1024 &&
-                            s.nnz > 0 && max_chunks(s) <= 65535 && split_self_enabled();
+                            s.nnz > 0 && split_self_enabled();
     if (split_self) A.skip_rel_plus1 = (int)s.Rp;
     // blocks of any size: edge-parallel relation-major kernel (needs the self-loop relation, if dense, served separately)
     const bool block_edges = p->form == RGCN_W_BLOCK && !p->featureless && (!p->blocks_self || split_self) &&
@@ -1166,13 +1167,12 @@ extern "C" int rgcn_backward(const rgcn_graph* g, const rgcn_params* p, const vo
             RGCN_LAUNCH(k_init_rows, grid_for(n, 256), 256, 0, st, gx_f32, n, s.I, (const float*)nullptr);
             UmmaArgs U{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, s.O, s.I, 0, gx_f32};
             rc = launch_gemm_umma(U, gb16, s.N, wb, max_chunks(s), st);
-        } else if (dense_tiled_shape(A.form, 0, s.O, s.I, s.nnz) && max_chunks(s) <= 65535) {
+        } else if (dense_tiled_shape(A.form, 0, s.O, s.I, s.nnz)) {
             GemmArgs Gm{g->r_relptr, g->r_chunkptr, (int)s.Rp, g->r_dst, g->r_src, g->r_val, A.W, s.O, s.I,
                         nullptr, p->self_mask, (int)s.Rp - 1, gx_f32};
             rc = launch_prop_dense_tiled(Gm, G, s.N, (const float*)nullptr, max_chunks(s), st, true, s.nnz);
         } else {
-            const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && IO >= 1024 && s.nnz > 0 &&
-                                    max_chunks(s) <= 65535 && split_self_enabled();
+            const bool split_self = p->form == RGCN_W_BLOCK && p->blocks_self && IO >= 1024 && s.nnz > 0 && split_self_enabled();
             if (split_self) A.skip_rel_plus1 = (int)s.Rp;
             const bool block_edges = p->form == RGCN_W_BLOCK && (!p->blocks_self || split_self) &&
                                      (!p->self_mask || split_self) && s.nnz > 0 && block_edges_shape(s.nb, s.bo, s.bi, s.O, s.I);
